@@ -1,0 +1,157 @@
+"""Multi-head attention modules.
+
+Parity: reference ``unicore/modules/multihead_attention.py`` - ``SelfMultiheadAttention:12``
+(packed ``in_proj``, ``scaling = (head_dim * scaling_factor) ** -0.5``, additive ``attn_bias``,
+boolean ``key_padding_mask``, ``return_attn`` yielding ``(out, pre-softmax logits incl. bias,
+probabilities)``) and ``CrossMultiheadAttention:121``.
+
+B200 path: unless ``return_attn`` is requested, the whole ``QK^T -> +bias/mask -> softmax ->
+dropout -> @V`` chain runs in the tcgen05 kernel behind ``ops.fused_attention``; q/k/v are strided
+views of the projection output (no transpose/contiguous copies) and the bias is *not* expanded over
+the batch.  With ``return_attn`` the materialised path (bmm + ``softmax_dropout`` kernel) is used.
+"""
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from unicore import ops
+
+
+def _bias_as_4d(attn_bias: Optional[Tensor], bsz: int, heads: int, tgt: int, src: int) -> Optional[Tensor]:
+    """Normalise the accepted bias layouts to ``[1|B, H, tgt, src]``."""
+    if attn_bias is None:
+        return None
+    if attn_bias.dim() == 4:
+        return attn_bias
+    if attn_bias.dim() == 3:
+        lead = attn_bias.shape[0]
+        if lead == bsz * heads:
+            return attn_bias.view(bsz, heads, tgt, src)
+        if lead == heads:
+            return attn_bias.view(1, heads, tgt, src)
+    if attn_bias.dim() == 2:
+        return attn_bias.view(1, 1, tgt, src).expand(1, heads, tgt, src)
+    raise ValueError("unsupported attn_bias shape {}".format(tuple(attn_bias.shape)))
+
+
+def _materialised_attention(q, k, v, scaling, key_padding_mask, attn_bias4, dropout, training, return_attn):
+    """q,k,v: [B, L, H, D]. Returns (out [B, Lq, H*D], logits?, probs?)."""
+    bsz, tgt_len, heads, dim = q.shape
+    src_len = k.shape[1]
+    qh = (q * scaling).permute(0, 2, 1, 3).reshape(bsz * heads, tgt_len, dim)
+    kh = k.permute(0, 2, 1, 3).reshape(bsz * heads, src_len, dim)
+    vh = v.permute(0, 2, 1, 3).reshape(bsz * heads, src_len, dim)
+    attn_weights = torch.bmm(qh, kh.transpose(1, 2))
+    if key_padding_mask is not None:
+        attn_weights = attn_weights.view(bsz, heads, tgt_len, src_len)
+        attn_weights.masked_fill_(key_padding_mask[:, None, None, :].to(torch.bool), float("-inf"))
+        attn_weights = attn_weights.view(bsz * heads, tgt_len, src_len)
+    w4 = attn_weights.view(bsz, heads, tgt_len, src_len)
+    bias = attn_bias4.to(attn_weights.dtype) if attn_bias4 is not None else None
+    if not return_attn:
+        attn = ops.softmax_dropout(w4, dropout, training, bias=bias)
+        logits = probs = None
+    else:
+        if bias is not None:
+            w4 = w4 + bias
+        logits = w4.view(bsz * heads, tgt_len, src_len)
+        attn = ops.softmax_dropout(w4, dropout, training, inplace=False)
+        probs = attn.view(bsz * heads, tgt_len, src_len)
+    attn = attn.view(bsz * heads, tgt_len, src_len)
+    out = torch.bmm(attn, vh)
+    out = out.view(bsz, heads, tgt_len, dim).transpose(1, 2).reshape(bsz, tgt_len, heads * dim)
+    return out, logits, probs
+
+
+class SelfMultiheadAttention(nn.Module):
+    def __init__(self, embed_dim, num_heads, dropout=0.1, bias=True, scaling_factor=1):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.dropout = dropout
+        self.head_dim = embed_dim // num_heads
+        if self.head_dim * num_heads != embed_dim:
+            raise ValueError("embed_dim must be divisible by num_heads")
+        self.scaling = (self.head_dim * scaling_factor) ** -0.5
+        self.in_proj = nn.Linear(embed_dim, embed_dim * 3, bias=bias)
+        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+
+    def attend(self, query, key_padding_mask=None, attn_bias=None, return_attn=False):
+        """Everything up to (not including) ``out_proj``: returns ``(o [B, L, E], logits, probs)``."""
+        bsz, tgt_len, embed_dim = query.size()
+        if embed_dim != self.embed_dim:
+            raise ValueError("query dim {} != embed_dim {}".format(embed_dim, self.embed_dim))
+        if key_padding_mask is not None and key_padding_mask.dim() == 0:
+            key_padding_mask = None
+        qkv = self.in_proj(query).view(bsz, tgt_len, 3, self.num_heads, self.head_dim)
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]  # strided views [B, L, H, D]
+        bias4 = _bias_as_4d(attn_bias, bsz, self.num_heads, tgt_len, tgt_len)
+        if not return_attn and ops.fused_attention_supported(q, k, v, bias4, key_padding_mask):
+            o = ops.fused_attention(
+                q, k, v, bias=bias4, key_padding_mask=key_padding_mask,
+                dropout_p=self.dropout, training=self.training, scale=self.scaling,
+            ).reshape(bsz, tgt_len, embed_dim)
+            return o, None, None
+        return _materialised_attention(
+            q, k, v, self.scaling, key_padding_mask, bias4, self.dropout, self.training, return_attn
+        )
+
+    def forward(
+        self,
+        query,
+        key_padding_mask: Optional[Tensor] = None,
+        attn_bias: Optional[Tensor] = None,
+        return_attn: bool = False,
+    ) -> Tensor:
+        o, logits, probs = self.attend(query, key_padding_mask, attn_bias, return_attn)
+        o = self.out_proj(o)
+        return (o, logits, probs) if return_attn else o
+
+
+class CrossMultiheadAttention(nn.Module):
+    def __init__(self, embed_dim, num_heads, dropout=0.1, bias=True, scaling_factor=1):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.dropout = dropout
+        self.head_dim = embed_dim // num_heads
+        if self.head_dim * num_heads != embed_dim:
+            raise ValueError("embed_dim must be divisible by num_heads")
+        self.scaling = (self.head_dim * scaling_factor) ** -0.5
+        self.q_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+        self.k_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+        self.v_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+
+    def attend(self, query, key, value, key_padding_mask=None, attn_bias=None):
+        """Everything up to (not including) ``out_proj``."""
+        bsz, tgt_len, embed_dim = query.size()
+        if embed_dim != self.embed_dim:
+            raise ValueError("query dim {} != embed_dim {}".format(embed_dim, self.embed_dim))
+        src_len = key.size(1)
+        if key_padding_mask is not None and key_padding_mask.dim() == 0:
+            key_padding_mask = None
+        q = self.q_proj(query).view(bsz, tgt_len, self.num_heads, self.head_dim)
+        k = self.k_proj(key).view(bsz, src_len, self.num_heads, self.head_dim)
+        v = self.v_proj(value).view(bsz, src_len, self.num_heads, self.head_dim)
+        bias4 = _bias_as_4d(attn_bias, bsz, self.num_heads, tgt_len, src_len)
+        if ops.fused_attention_supported(q, k, v, bias4, key_padding_mask):
+            return ops.fused_attention(
+                q, k, v, bias=bias4, key_padding_mask=key_padding_mask,
+                dropout_p=self.dropout, training=self.training, scale=self.scaling,
+            ).reshape(bsz, tgt_len, embed_dim)
+        o, _, _ = _materialised_attention(
+            q, k, v, self.scaling, key_padding_mask, bias4, self.dropout, self.training, False
+        )
+        return o
+
+    def forward(
+        self,
+        query,
+        key,
+        value,
+        key_padding_mask: Optional[Tensor] = None,
+        attn_bias: Optional[Tensor] = None,
+    ) -> Tensor:
+        return self.out_proj(self.attend(query, key, value, key_padding_mask, attn_bias))

@@ -1,0 +1,448 @@
+"""Framework-wide helpers (sample movement, grad-norm/clip, seeding, flag value parsing, tensor
+trees, activation lookup, user-module import).
+
+Parity map (reference ``unicore/utils.py``): ``apply_to_sample:43``, ``move_to_cuda:64``,
+``move_to_cpu:75`` (half/bf16 -> fp32), ``multi_tensor_total_norm:87``, ``clip_grad_norm_:111``,
+``import_user_module:138``, ``get_activation_fn:174``, ``torch_seed:220``, ``CudaEnvironment:245``,
+``eval_str_list/dict/bool:278-303``, ``checkpoint_sequential:306``, tensor-tree helpers
+``:336-411``, ``fp32_to_bf16_sr:414``, ``set_jit_fusion_options:426``, ``validate_with_ema:437``.
+
+B200 differences: the grad-norm and stochastic-rounding helpers dispatch to the hand-written
+sm_100a kernels in ``unicore.ops`` (single-launch multi-tensor L2 norm, counter-based Philox SR)
+and fall back to plain PyTorch on CPU.
+"""
+import contextlib
+import copy
+import hashlib
+import importlib
+import logging
+import os
+import sys
+from functools import partial
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+import torch.utils.checkpoint
+
+logger = logging.getLogger(__name__)
+
+
+# --------------------------------------------------------------------------------------------
+# nested-sample helpers
+# --------------------------------------------------------------------------------------------
+def apply_to_sample(fn: Callable[[torch.Tensor], Any], sample):
+    """Apply ``fn`` to every tensor inside an arbitrarily nested dict/list/tuple/set."""
+    if hasattr(sample, "__len__") and len(sample) == 0:
+        return {}
+
+    def walk(node):
+        if torch.is_tensor(node):
+            return fn(node)
+        if isinstance(node, dict):
+            return {k: walk(v) for k, v in node.items()}
+        if isinstance(node, list):
+            return [walk(v) for v in node]
+        if isinstance(node, tuple):
+            return tuple(walk(v) for v in node)
+        if isinstance(node, set):
+            return {walk(v) for v in node}
+        return node
+
+    return walk(sample)
+
+
+def move_to_cuda(sample, device=None):
+    """Host->device copy of a sample; ``non_blocking`` only overlaps when the source is pinned
+    (see ``unicore.data.iterators.BufferedIterator(pin_memory=True)``)."""
+    device = device if device is not None else torch.cuda.current_device()
+    return apply_to_sample(lambda t: t.to(device=device, non_blocking=True), sample)
+
+
+def move_to_cpu(sample):
+    """Device->host copy; 16-bit floats are widened to fp32 (checkpoints are stored in fp32)."""
+
+    def to_cpu(t):
+        if t.dtype in (torch.float16, torch.bfloat16):
+            t = t.to(dtype=torch.float32)
+        return t.cpu()
+
+    return apply_to_sample(to_cpu, sample)
+
+
+def pin_sample(sample):
+    """Page-lock every tensor of a sample (B200 addition: makes ``move_to_cuda`` truly async)."""
+    if not torch.cuda.is_available():
+        return sample
+    return apply_to_sample(lambda t: t.pin_memory() if not t.is_pinned() else t, sample)
+
+
+# --------------------------------------------------------------------------------------------
+# gradient norm / clipping
+# --------------------------------------------------------------------------------------------
+def multi_tensor_total_norm(grads: Sequence[torch.Tensor], chunk_size: int = 2048 * 32) -> torch.Tensor:
+    """Global L2 norm of a list of tensors as an fp32 scalar tensor (no host sync)."""
+    from unicore import ops
+
+    grads = list(grads)
+    if len(grads) == 0:
+        return torch.zeros((), dtype=torch.float32)
+    return ops.multi_tensor_l2norm(grads, chunk_size=chunk_size)
+
+
+@torch.no_grad()
+def clip_grad_norm_(params, max_norm, aggregate_norm_fn=None) -> torch.Tensor:
+    """Clip the global grad norm of ``params`` to ``max_norm``; returns the *pre-clip* norm.
+
+    coefficient = clamp(max_norm / (norm + 1e-6), max=1) (reference ``utils.py:130-134``).
+    The scaling is a single fused multi-tensor launch on GPU and never synchronises the host.
+    """
+    from unicore import ops
+
+    if isinstance(params, torch.Tensor):
+        params = [params]
+    params = list(params)
+    grads = [p.grad.detach() for p in params if getattr(p, "grad", None) is not None]
+    if len(grads) == 0:
+        if len(params) > 0:
+            return params[0].new_tensor(0.0)
+        return torch.tensor(0.0)
+    total_norm = multi_tensor_total_norm(grads)
+    if aggregate_norm_fn is not None:
+        total_norm = aggregate_norm_fn(total_norm)
+    if max_norm > 0:
+        max_norm = float(max_norm)
+        clip_coef = (max_norm / (total_norm + 1e-6)).clamp_(max=1.0)
+        ops.multi_tensor_scale_(grads, clip_coef)
+    return total_norm
+
+
+# --------------------------------------------------------------------------------------------
+# plug-ins
+# --------------------------------------------------------------------------------------------
+def import_user_module(args) -> None:
+    """Import the package named by ``--user-dir`` so that its ``@register_*`` decorators run."""
+    module_path = getattr(args, "user_dir", None)
+    if module_path is None:
+        return
+    module_path = os.path.abspath(module_path)
+    if not os.path.exists(module_path):
+        # allow paths relative to the installed package (``unicore/../<user_dir>``)
+        alt = os.path.join(os.path.dirname(os.path.dirname(__file__)), args.user_dir)
+        if os.path.exists(alt):
+            module_path = alt
+        else:
+            raise FileNotFoundError(module_path)
+    registry = import_user_module.__dict__.setdefault("_seen", {})
+    parent, name = os.path.split(module_path.rstrip(os.sep))
+    if name in sys.modules and name not in registry:
+        existing = getattr(sys.modules[name], "__file__", None) or ""
+        if os.path.dirname(os.path.abspath(existing)) != module_path:
+            raise ImportError(
+                "Failed to import --user-dir={} because the module name ({}) is not globally "
+                "unique. Please rename the directory.".format(module_path, name)
+            )
+    if name in registry:
+        return
+    registry[name] = module_path
+    sys.path.insert(0, parent)
+    try:
+        importlib.import_module(name)
+    finally:
+        # keep parent on sys.path: plug-ins commonly do sibling imports lazily
+        pass
+
+
+# --------------------------------------------------------------------------------------------
+# activations
+# --------------------------------------------------------------------------------------------
+_ACTIVATIONS: Dict[str, Callable] = {
+    "relu": F.relu,
+    "gelu": F.gelu,
+    "tanh": torch.tanh,
+    "linear": lambda x: x,
+}
+
+
+def get_activation_fn(activation: str) -> Callable:
+    try:
+        return _ACTIVATIONS[activation]
+    except KeyError:
+        raise RuntimeError("--activation-fn {} not supported".format(activation))
+
+
+def get_available_activation_fns() -> List[str]:
+    return list(_ACTIVATIONS.keys())
+
+
+def has_parameters(module) -> bool:
+    for _ in module.parameters():
+        return True
+    return False
+
+
+# --------------------------------------------------------------------------------------------
+# RNG discipline
+# --------------------------------------------------------------------------------------------
+def get_rng_state() -> dict:
+    state = {"torch_rng_state": torch.get_rng_state()}
+    if torch.cuda.is_available():
+        state["cuda_rng_state"] = torch.cuda.get_rng_state()
+    return state
+
+
+def set_rng_state(state: dict) -> None:
+    torch.set_rng_state(state["torch_rng_state"])
+    if torch.cuda.is_available() and "cuda_rng_state" in state:
+        torch.cuda.set_rng_state(state["cuda_rng_state"])
+
+
+def _mix_seed(seed, addl) -> int:
+    """Deterministically fold a tuple of ints into one 31-bit-ish seed (stable across runs —
+    unlike Python's ``hash`` this does not depend on PYTHONHASHSEED)."""
+    if len(addl) == 0:
+        return int(seed)
+    blob = ",".join(str(int(s)) for s in (seed,) + tuple(addl)).encode()
+    return int.from_bytes(hashlib.blake2b(blob, digest_size=8).digest(), "little") % (2 ** 31 - 1)
+
+
+@contextlib.contextmanager
+def torch_seed(seed, *addl_seeds):
+    """Seed torch (CPU + current CUDA device) inside the block, restore the RNG state after.
+
+    Used for per-(update, micro-batch, rank) dropout reproducibility and the rank-invariant
+    optimizer-step stream that stochastic rounding relies on (reference ``trainer.py:602-607,712``).
+    """
+    if seed is None:
+        yield
+        return
+    seed = _mix_seed(seed, addl_seeds)
+    saved = get_rng_state()
+    torch.manual_seed(seed)  # seeds CUDA generators too
+    try:
+        yield
+    finally:
+        set_rng_state(saved)
+
+
+# --------------------------------------------------------------------------------------------
+# environment report
+# --------------------------------------------------------------------------------------------
+class CudaEnvironment(object):
+    """Snapshot of the local GPU, gathered from all ranks and printed once by rank 0."""
+
+    def __init__(self):
+        dev = torch.cuda.current_device()
+        prop = torch.cuda.get_device_properties("cuda:{}".format(dev))
+        self.name = prop.name
+        self.major = prop.major
+        self.minor = prop.minor
+        self.total_memory_in_GB = prop.total_memory / 1024 / 1024 / 1024
+        self.sm_count = prop.multi_processor_count
+
+    @staticmethod
+    def pretty_print_cuda_env_list(cuda_env_list):
+        n = len(cuda_env_list)
+        header = "CUDA environments for all {} workers".format(n)
+        bar = "*" * (len(header) + 8)
+        lines = [bar, "*** " + header + " ***"]
+        for rank, env in enumerate(cuda_env_list):
+            lines.append(
+                "rank {:3d}: capabilities = {:2d}.{:<2d}; total memory = {:.3f} GB; SMs = {}; name = {}".format(
+                    rank, env.major, env.minor, env.total_memory_in_GB,
+                    getattr(env, "sm_count", -1), env.name,
+                )
+            )
+        lines.append(bar)
+        for line in lines:
+            logger.info(line)
+
+
+# --------------------------------------------------------------------------------------------
+# flag value parsers (kept eval-compatible with the reference CLI: "--lr '[1e-3, 1e-4]'")
+# --------------------------------------------------------------------------------------------
+def csv_str_list(x):
+    return x.split(",")
+
+
+def _safe_eval(x):
+    import ast
+
+    try:
+        return ast.literal_eval(x)
+    except (ValueError, SyntaxError):
+        return eval(x)  # noqa: S307 - parity with reference semantics for expressions like 2**7
+
+
+def eval_str_list(x, type=float):
+    if x is None:
+        return None
+    if isinstance(x, str):
+        x = _safe_eval(x)
+    try:
+        return [type(v) for v in x]
+    except TypeError:
+        return [type(x)]
+
+
+def eval_str_dict(x, type=dict):
+    if x is None:
+        return None
+    if isinstance(x, str):
+        x = _safe_eval(x)
+    return x
+
+
+def eval_bool(x, default=False):
+    if x is None:
+        return default
+    try:
+        return bool(_safe_eval(x)) if isinstance(x, str) else bool(x)
+    except (TypeError, NameError):
+        return default
+
+
+# --------------------------------------------------------------------------------------------
+# activation checkpointing over a list of callables
+# --------------------------------------------------------------------------------------------
+def checkpoint_sequential(functions: Sequence[Callable], input, enabled: bool = True):
+    """Run ``functions`` in order, re-materialising each one's activations in backward.
+
+    ``input`` may be a tensor or a tuple of tensors; each function receives the unpacked tuple and
+    may return a tensor or a tuple.
+    """
+
+    def as_tuple(value):
+        return value if isinstance(value, tuple) else (value,)
+
+    def make_runner(fn):
+        def runner(*packed):
+            return as_tuple(fn(*packed))
+
+        return runner
+
+    packed = as_tuple(input)
+    was_tuple = isinstance(input, tuple)
+    for fn in functions:
+        if enabled and torch.is_grad_enabled():
+            packed = torch.utils.checkpoint.checkpoint(make_runner(fn), *packed, use_reentrant=False)
+        else:
+            packed = as_tuple(fn(*packed))
+    if not was_tuple and len(packed) == 1:
+        return packed[0]
+    return packed
+
+
+# --------------------------------------------------------------------------------------------
+# tensor / tree utilities used by downstream structure models (Uni-Fold style)
+# --------------------------------------------------------------------------------------------
+def permute_final_dims(tensor: torch.Tensor, inds: List[int]):
+    lead = tensor.dim() - len(inds)
+    return tensor.permute(*range(lead), *[lead + i for i in inds])
+
+
+def flatten_final_dims(t: torch.Tensor, num_dims: int):
+    return t.reshape(*t.shape[: t.dim() - num_dims], -1)
+
+
+def masked_mean(mask, value, dim, eps=1e-10):
+    mask = mask.expand(*value.shape)
+    return (mask * value).sum(dim=dim) / (mask.sum(dim=dim) + eps)
+
+
+def dict_multimap(fn, dicts):
+    head = dicts[0]
+    out = {}
+    for key, val in head.items():
+        column = [d[key] for d in dicts]
+        out[key] = dict_multimap(fn, column) if type(val) is dict else fn(column)
+    return out
+
+
+def one_hot(x, num_classes, dtype=torch.float32):
+    out = torch.zeros(*x.shape, num_classes, dtype=dtype, device=x.device)
+    return out.scatter_(-1, x.long().unsqueeze(-1), 1)
+
+
+def batched_gather(data, inds, dim=0, num_batch_dims=0):
+    if not (dim < 0 or dim - num_batch_dims >= 0):
+        raise ValueError("dim must address a non-batch dimension")
+    index = []
+    for i, size in enumerate(data.shape[:num_batch_dims]):
+        shape = [1] * inds.dim()
+        shape[i] = -1
+        index.append(torch.arange(size, device=inds.device).view(*shape))
+    rest = [slice(None)] * (data.dim() - num_batch_dims)
+    rest[dim - num_batch_dims if dim >= 0 else dim] = inds
+    index.extend(rest)
+    return data[tuple(index)]
+
+
+def dict_map(fn, dic, leaf_type):
+    return {
+        k: (dict_map(fn, v, leaf_type) if type(v) is dict else tree_map(fn, v, leaf_type))
+        for k, v in dic.items()
+    }
+
+
+def tree_map(fn, tree, leaf_type):
+    if isinstance(tree, dict):
+        return dict_map(fn, tree, leaf_type)
+    if isinstance(tree, list):
+        return [tree_map(fn, x, leaf_type) for x in tree]
+    if isinstance(tree, tuple):
+        return tuple(tree_map(fn, x, leaf_type) for x in tree)
+    if isinstance(tree, leaf_type):
+        try:
+            return fn(tree)
+        except Exception as exc:  # noqa: BLE001
+            raise ValueError("cannot apply {} on {}.".format(fn, tree)) from exc
+    raise ValueError("{} not supported".format(type(tree)))
+
+
+tensor_tree_map = partial(tree_map, leaf_type=torch.Tensor)
+
+
+# --------------------------------------------------------------------------------------------
+# stochastic rounding, JIT switches, EMA validation swap
+# --------------------------------------------------------------------------------------------
+def fp32_to_bf16_sr(t: torch.Tensor, o: torch.Tensor) -> None:
+    """Stochastically round fp32 ``t`` into bf16 ``o`` (unbiased: E[o] == t)."""
+    from unicore import ops
+
+    ops.fp32_to_bf16_sr(t, o)
+
+
+def set_jit_fusion_options() -> None:
+    """Kept for CLI parity. The B200 build does not rely on TorchScript fusers: hot element-wise
+    chains are explicit CUDA kernels, so we only make sure legacy fusers are off."""
+    try:
+        torch._C._jit_set_profiling_executor(True)
+        torch._C._jit_set_profiling_mode(True)
+        torch._C._jit_override_can_fuse_on_cpu(False)
+        torch._C._jit_override_can_fuse_on_gpu(False)
+        torch._C._jit_set_texpr_fuser_enabled(False)
+        torch._C._jit_set_nvfuser_enabled(False)
+    except Exception:  # noqa: BLE001 - private API, best effort
+        pass
+
+
+@contextlib.contextmanager
+def validate_with_ema(trainer, ema=False):
+    """Temporarily swap the trainer's model for (a half/bf16 copy of) the EMA weights."""
+    if not ema:
+        yield
+        return
+    live_model = trainer._wrapped_model
+    shadow = copy.deepcopy(trainer.ema.model_ema)
+    if trainer.args.fp16:
+        shadow.half()
+    elif trainer.args.bf16:
+        shadow.bfloat16()
+    trainer._wrapped_model = shadow
+    try:
+        yield
+    finally:
+        del shadow
+        trainer._wrapped_model = live_model

@@ -1,0 +1,61 @@
+"""Loader for the in-tree sm_100a extension ``unicore_b200._C``.
+
+The extension is built in-tree (``python setup.py build_ext --inplace`` or
+``__graft_entry__.build()``) so the ``.so`` travels with the source snapshot.  Policy:
+
+* CPU-only process (no CUDA device): the extension is optional, ops use PyTorch fallbacks.
+* CUDA device present: a missing/unloadable extension is a hard error unless
+  ``UNICORE_ALLOW_FALLBACK=1`` - silent eager fallbacks on a GPU box would hide that the native
+  path is not running.
+"""
+import importlib
+import logging
+import os
+
+import torch
+
+logger = logging.getLogger(__name__)
+
+_C = None
+_ERR = None
+try:
+    _C = importlib.import_module("unicore_b200._C")
+except Exception as exc:  # noqa: BLE001 - ImportError, OSError (missing libs), ...
+    _ERR = exc
+
+HAS_CUDA_EXT = _C is not None
+
+
+def _is_blackwell() -> bool:
+    try:
+        return torch.cuda.is_available() and torch.cuda.get_device_capability()[0] >= 10
+    except Exception:  # noqa: BLE001
+        return False
+
+
+if torch.cuda.is_available() and _C is None and os.environ.get("UNICORE_ALLOW_FALLBACK", "0") != "1":
+    raise ImportError(
+        "unicore_b200._C (sm_100a kernels) failed to load on a CUDA machine: {!r}. Build it with "
+        "`python setup.py build_ext --inplace` (or __graft_entry__.build()), or set "
+        "UNICORE_ALLOW_FALLBACK=1 to run on PyTorch fallbacks.".format(_ERR)
+    )
+
+# kernels are compiled for sm_100a only; on other GPUs use the fallbacks
+USE_NATIVE = HAS_CUDA_EXT and _is_blackwell() and os.environ.get("UNICORE_DISABLE_NATIVE", "0") != "1"
+
+
+def native():
+    """Return the extension module (raises if it is not loaded)."""
+    if _C is None:
+        raise RuntimeError("unicore_b200._C is not loaded: {!r}".format(_ERR))
+    return _C
+
+
+def use_native(*tensors) -> bool:
+    """True when the native kernels should handle these tensors."""
+    if not USE_NATIVE:
+        return False
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            return False
+    return True

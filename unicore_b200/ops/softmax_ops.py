@@ -1,0 +1,121 @@
+"""``softmax_dropout``: ``dropout(softmax(input + mask + bias, dim=-1))`` with broadcast mask/bias.
+
+Contract (reference ``unicore/modules/softmax_dropout.py:100-144`` + ``csrc/softmax_dropout``):
+* works **in place** on ``input`` by default (the buffer ends up holding the softmax
+  probabilities; the dropped-out result is returned);
+* ``mask`` broadcasts as ``[..., 1|H, 1|Q, K]`` (row ``r`` of the flattened input uses mask row
+  ``r // (rows / mask_rows)``); ``bias`` broadcasts over leading batch dims (row ``r`` uses bias
+  row ``r % bias_rows``); anything else is pre-added in PyTorch;
+* gradient flows to ``input`` and ``bias``.
+
+B200 kernel (``csrc/attn/softmax_dropout.cu``): one warp per row with 128-bit loads, rows of any
+length (dropout included for K > 1024, which the reference cannot fuse), current-stream launch,
+and **no stored dropout mask**: keep/drop decisions are a pure function of
+``(philox seed, offset, element index)`` and are regenerated in backward.
+"""
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from ._native import native, use_native
+
+
+def _mask_plan(mask: torch.Tensor, x: torch.Tensor) -> bool:
+    """True if ``mask`` fits the kernel's division-broadcast (else it must be pre-added)."""
+    if mask.dtype != x.dtype or mask.dim() != x.dim() or mask.shape[-1] != x.shape[-1]:
+        return False
+    if x.dim() < 3:
+        return False
+    h_ok = mask.shape[-3] in (1, x.shape[-3])
+    if not h_ok:
+        return False
+    if mask.shape[-3] == 1:
+        if mask.shape[-2] != 1:
+            return False
+    elif mask.shape[-2] not in (1, x.shape[-2]):
+        return False
+    # leading dims must match exactly (division mapping assumes contiguous outer order)
+    return tuple(mask.shape[:-3]) == tuple(x.shape[:-3])
+
+
+def _bias_plan(bias: torch.Tensor, x: torch.Tensor) -> bool:
+    """True if ``bias`` fits the kernel's modulo-broadcast."""
+    if bias.dtype != x.dtype or bias.dim() != x.dim():
+        return False
+    if bias.shape[-1] != x.shape[-1] or bias.shape[-2] != x.shape[-2]:
+        return False
+    nd = x.dim()
+    tail = 3 if nd > 3 else 2
+    if nd > 3 and bias.shape[-3] != x.shape[-3]:
+        return False
+    # going outwards: once a dim is broadcast (1), all dims further out must be broadcast too
+    inner_full = True
+    for i in range(nd - tail - 1, -1, -1):
+        if inner_full:
+            if bias.shape[i] not in (1, x.shape[i]):
+                return False
+        elif bias.shape[i] != 1:
+            return False
+        inner_full = bias.shape[i] != 1 or x.shape[i] == 1
+    return True
+
+
+class _SoftmaxDropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x3, mask3, bias3, p, training):
+        out, seed, offset = native().softmax_dropout_fwd(x3, mask3, bias3, float(p), bool(training))
+        ctx.p = float(p) if training else 0.0
+        ctx.rng = (seed, offset)
+        ctx.bias_rows = bias3.shape[0] if (bias3 is not None and bias3.requires_grad) else 0
+        ctx.save_for_backward(x3)  # now holds softmax probabilities (overwritten by the kernel)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (probs,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        if dy.data_ptr() == probs.data_ptr():
+            dy = dy.clone()
+        dx = native().softmax_dropout_bwd(dy, probs, ctx.p, ctx.rng[0], ctx.rng[1])
+        dbias = None
+        if ctx.bias_rows > 0:
+            dbias = dx.view(-1, ctx.bias_rows, dx.shape[-2], dx.shape[-1]).sum(dim=0)
+        return dx, None, dbias, None, None
+
+
+def softmax_dropout(input, dropout_prob, is_training=True, mask=None, bias=None, inplace=True):
+    """See module docstring. Returns a tensor shaped like ``input``."""
+    input = input.contiguous()
+    if not inplace:
+        input = input.clone()
+    if use_native(input, mask, bias) and input.dim() >= 2 and input.dtype in (
+        torch.float16, torch.bfloat16, torch.float32
+    ) and input.numel() > 0:
+        shape = input.shape
+        if input.dim() == 2:
+            input = input.unsqueeze(0)
+            mask = mask.unsqueeze(0) if mask is not None and mask.dim() == 2 else mask
+            bias = bias.unsqueeze(0) if bias is not None and bias.dim() == 2 else bias
+        if mask is not None:
+            if _mask_plan(mask, input):
+                mask = mask.contiguous().view(-1, mask.shape[-2], mask.shape[-1])
+            else:
+                input = input + mask if input.requires_grad else input.add_(mask)
+                mask = None
+        if bias is not None:
+            if _bias_plan(bias, input):
+                bias = bias.contiguous().view(-1, bias.shape[-2], bias.shape[-1])
+            else:
+                input = input + bias if input.requires_grad else input.add_(bias)
+                bias = None
+        x3 = input.view(-1, input.shape[-2], input.shape[-1])
+        if x3.requires_grad and x3.is_leaf:
+            x3 = x3.clone()  # cannot overwrite a leaf that needs grad
+        out = _SoftmaxDropoutFn.apply(x3, mask, bias, dropout_prob, is_training)
+        return out.view(shape)
+    if mask is not None:
+        input = input + mask
+    if bias is not None:
+        input = input + bias
+    return F.dropout(F.softmax(input, dim=-1), p=dropout_prob, training=is_training)
