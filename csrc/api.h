@@ -1,0 +1,114 @@
+// Host-callable launchers of the unicore_b200 kernels (plain C++/CUDA-runtime types only, so the
+// .cu translation units do not need the PyTorch headers and compile in seconds).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ub {
+
+// dtype tags shared by host and device code
+enum DType : int { kF32 = 0, kF16 = 1, kBF16 = 2 };
+
+constexpr int kMaxTensorsPerLaunch = 24;
+
+// ---- multi-tensor L2 norm / scale -----------------------------------------------------------------
+struct NormTensors {
+  const void* ptr[kMaxTensorsPerLaunch];
+  long long numel[kMaxTensorsPerLaunch];
+  int dtype[kMaxTensorsPerLaunch];
+  int count;
+};
+// acc: float[1] running sum of squares (zeroed by the caller before the first launch)
+// partials: float[>= max_ctas] scratch, counter: unsigned[1] zeroed scratch
+// out: float[1] receives sqrt(acc) when finalize != 0
+void launch_l2norm(const NormTensors& t, float* acc, float* partials, unsigned* counter, float* out, int finalize,
+                   cudaStream_t stream);
+int l2norm_max_ctas();
+
+struct ScaleTensors {
+  void* ptr[kMaxTensorsPerLaunch];
+  long long numel[kMaxTensorsPerLaunch];
+  int dtype[kMaxTensorsPerLaunch];
+  int count;
+};
+// x *= scale * (scale_dev ? *scale_dev : 1)
+void launch_scale(const ScaleTensors& t, float scale, const float* scale_dev, cudaStream_t stream);
+
+// ---- multi-tensor Adam ---------------------------------------------------------------------------------
+struct AdamTensors {
+  void* p[kMaxTensorsPerLaunch];       // fp32 master (or 16-bit param)
+  void* g[kMaxTensorsPerLaunch];       // gradient
+  float* m[kMaxTensorsPerLaunch];
+  float* v[kMaxTensorsPerLaunch];
+  void* p_half[kMaxTensorsPerLaunch];  // optional 16-bit copy of the updated param
+  float* ema[kMaxTensorsPerLaunch];    // optional fp32 EMA buffer updated in the same pass
+  long long numel[kMaxTensorsPerLaunch];
+  int p_dtype[kMaxTensorsPerLaunch], g_dtype[kMaxTensorsPerLaunch], half_dtype[kMaxTensorsPerLaunch];
+  float step_size[kMaxTensorsPerLaunch];   // lr * sqrt(1-b2^t)/(1-b1^t) (or lr)
+  float decay_mul[kMaxTensorsPerLaunch];   // 1 - step_size * weight_decay
+  float beta1[kMaxTensorsPerLaunch], beta2[kMaxTensorsPerLaunch], eps[kMaxTensorsPerLaunch];
+  unsigned long long elem_base[kMaxTensorsPerLaunch];  // RNG stream offset of the tensor's first element
+  int count;
+};
+struct AdamLaunch {
+  float inv_scale;            // grads are multiplied by inv_scale / (*scale_dev if given)
+  const float* scale_dev;     // optional device scalar divisor
+  int zero_grad;              // clear g after reading it
+  int stochastic_rounding;    // bf16 p_half written with stochastic rounding
+  float ema_decay;
+  unsigned long long seed, offset;  // philox key for stochastic rounding
+};
+void launch_adam(const AdamTensors& t, const AdamLaunch& cfg, cudaStream_t stream);
+
+void launch_fp32_to_bf16_sr(const float* in, void* out, long long n, unsigned long long seed,
+                            unsigned long long offset, cudaStream_t stream);
+void launch_ema(float* ema, const float* p, long long n, float decay, cudaStream_t stream);
+
+// ---- LayerNorm / RMSNorm -----------------------------------------------------------------------------------
+void launch_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                          int rows, int cols, float eps, int dtype, cudaStream_t stream);
+// dgamma_part/dbeta_part: float[parts * cols] scratch; counter zeroed; dgamma/dbeta in `dtype`
+int norm_bwd_parts(int rows, int cols);
+void launch_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                          void* dx, void* dgamma, void* dbeta, float* dgamma_part, float* dbeta_part,
+                          unsigned* counter, int rows, int cols, int dtype, cudaStream_t stream);
+void launch_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int rows, int cols, float eps,
+                        int dtype, cudaStream_t stream);
+void launch_rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* gamma, void* dx, void* dgamma,
+                        float* dgamma_part, unsigned* counter, int rows, int cols, int dtype, cudaStream_t stream);
+
+// ---- softmax + dropout ---------------------------------------------------------------------------------------
+// x: [rows, K] overwritten with softmax probabilities; out: dropout result (may alias x when p == 0)
+// mask row = row / mask_div (mask_rows = rows / mask_div), bias row = row % bias_rows
+void launch_softmax_dropout_fwd(void* x, void* out, const void* mask, const void* bias, long long rows, int K,
+                                long long mask_div, long long bias_rows, float p, unsigned long long seed,
+                                unsigned long long offset, int dtype, cudaStream_t stream);
+// dy: [rows, K] overwritten with dx
+void launch_softmax_dropout_bwd(void* dy, const void* probs, long long rows, int K, float p, unsigned long long seed,
+                                unsigned long long offset, int dtype, cudaStream_t stream);
+
+// ---- fused element-wise ---------------------------------------------------------------------------------------
+void launch_bias_gelu_fwd(const void* x, const void* bias, void* y, long long rows, int cols, int dtype,
+                          cudaStream_t stream);
+void launch_bias_gelu_bwd(const void* dy, const void* x, const void* bias, void* dx, long long rows, int cols,
+                          int dtype, cudaStream_t stream);
+// y = LN(residual + dropout(x + bias)); summed = residual + dropout(x + bias) (saved for backward)
+void launch_bias_dropout_add_ln_fwd(const void* x, const void* bias, const void* residual, const void* gamma,
+                                    const void* beta, void* y, void* summed, float* mean, float* rstd, int rows,
+                                    int cols, float p, float eps, unsigned long long seed, unsigned long long offset,
+                                    int dtype, cudaStream_t stream);
+// dsum = dLN(dy); dx = dropout_mask * dsum / (1-p)
+void launch_bias_dropout_add_ln_bwd(const void* dy, const void* summed, const float* mean, const float* rstd,
+                                    const void* gamma, void* dsum, void* dx, void* dgamma, void* dbeta,
+                                    float* dgamma_part, float* dbeta_part, unsigned* counter, int rows, int cols,
+                                    float p, unsigned long long seed, unsigned long long offset, int dtype,
+                                    cudaStream_t stream);
+// loss_rows[i] = lse_i - logit_i[target_i] (0 when target == ignore_index); lse saved for backward
+void launch_softmax_xent_fwd(const void* logits, const long long* target, float* loss_rows, float* lse, int rows,
+                             int cols, long long ignore_index, int dtype, cudaStream_t stream);
+// dlogits = (softmax - onehot) * dloss (0 for ignored rows), written in `dtype`
+void launch_softmax_xent_bwd(const void* logits, const long long* target, const float* lse, const float* dloss,
+                             void* dlogits, int rows, int cols, long long ignore_index, int dtype,
+                             cudaStream_t stream);
+
+}  // namespace ub

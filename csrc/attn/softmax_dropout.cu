@@ -1,0 +1,366 @@
+// softmax(x + mask + bias) followed by dropout, forward and backward, for sm_100a.
+//
+// Stand-alone counterpart of reference csrc/softmax_dropout/* (used when attention probabilities
+// must be materialised, e.g. return_attn=True / head_dim 8 models; the BERT path uses the fused
+// tcgen05 attention kernel instead).  Differences from the reference kernels:
+//   * a row is owned by a group of 1..256 threads that keeps it in registers; 128-bit accesses;
+//   * any row length that is a multiple of the vector width up to 8192 takes the fast path WITH
+//     dropout (reference: dropout only for K <= 1024, block kernel on the default stream above);
+//     other lengths use a scalar three-pass kernel;
+//   * no dropout bit-mask tensor: keep/drop is recomputed from Philox(seed, offset, index) in
+//     backward, which removes one output stream in forward and one input stream in backward;
+//   * fully masked rows produce zeros instead of NaN.
+// Contract kept: x is overwritten with the probabilities; mask row = row / mask_div; bias row =
+// row % bias_rows; backward overwrites dy with dx = (d - sum(d*y)) * y, d = keep ? dy/(1-p) : 0.
+#include <math_constants.h>
+
+#include "../api.h"
+#include "../common.cuh"
+
+namespace ub {
+
+constexpr int kSmThreads = 256;
+
+template <bool kMax>
+UB_DEVICE float group_reduce(float v, int tpr, float* scratch) {
+  const int lim = tpr < 32 ? tpr : 32;
+  for (int o = lim >> 1; o > 0; o >>= 1) {
+    const float other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = kMax ? fmaxf(v, other) : v + other;
+  }
+  if (tpr > 32) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpg = tpr >> 5, gfirst = (warp / wpg) * wpg;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float r = scratch[gfirst];
+    for (int w = 1; w < wpg; ++w) r = kMax ? fmaxf(r, scratch[gfirst + w]) : r + scratch[gfirst + w];
+    v = r;
+  }
+  return v;
+}
+
+struct SmGeom {
+  long long rows;
+  int K, tpr, nvec;
+  long long mask_div, bias_rows;
+};
+
+template <typename T, int VPT>
+__global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
+    T* __restrict__ x, T* __restrict__ out, const T* __restrict__ mask, const T* __restrict__ bias, SmGeom g, float p,
+    float keep_scale, unsigned long long seed, unsigned long long offset) {
+  constexpr int EPV = VecTraits<T>::kElems;
+  __shared__ float scratch[8];
+  const int tpr = g.tpr, rows_per_cta = kSmThreads / tpr;
+  const int grp = threadIdx.x / tpr, j = threadIdx.x % tpr;
+  const uint32_t thresh = dropout_thresh16(p);
+  const bool drop = p > 0.f;
+  const long long stride_rows = (long long)gridDim.x * rows_per_cta;
+  const long long iters = (g.rows + stride_rows - 1) / stride_rows;
+  for (long long it = 0; it < iters; ++it) {
+    const long long row = (it * gridDim.x + blockIdx.x) * rows_per_cta + grp;
+    const bool active = row < g.rows;
+    float v[VPT][EPV];
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int vi = j + k * tpr;
+      if (active && vi < g.nvec) {
+        unpack<T>(ld_global_nc_v4(x + row * g.K + (long long)vi * EPV), v[k]);
+        if (mask != nullptr) {
+          float t[EPV];
+          unpack<T>(ld_global_v4(mask + (row / g.mask_div) * g.K + (long long)vi * EPV), t);
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) v[k][e] += t[e];
+        }
+        if (bias != nullptr) {
+          float t[EPV];
+          unpack<T>(ld_global_v4(bias + (row % g.bias_rows) * g.K + (long long)vi * EPV), t);
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) v[k][e] += t[e];
+        }
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) mx = fmaxf(mx, v[k][e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) v[k][e] = -CUDART_INF_F;
+      }
+    }
+    mx = group_reduce<true>(mx, tpr, scratch);
+    if (mx == -CUDART_INF_F) mx = 0.f;  // fully masked row
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) {
+        v[k][e] = exp2f((v[k][e] - mx) * 1.4426950408889634f);
+        sum += v[k][e];
+      }
+    }
+    sum = group_reduce<false>(sum, tpr, scratch);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < VPT; ++k) {
+        const int vi = j + k * tpr;
+        if (vi < g.nvec) {
+          const long long off = row * g.K + (long long)vi * EPV;
+          float pr[EPV];
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) pr[e] = v[k][e] * inv;
+          const Vec16 packed = pack<T>(pr);
+          st_global_v4(x + off, packed);
+          if (drop) {
+            const uint32_t keep = dropout_keep8(seed, offset, (unsigned long long)off >> 3, thresh) >> (off & 7);
+            float rounded[EPV], o[EPV];
+            unpack<T>(packed, rounded);  // dropout acts on the stored (rounded) probabilities
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) o[e] = ((keep >> e) & 1u) ? rounded[e] * keep_scale : 0.f;
+            st_global_v4(out + off, pack<T>(o));
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int VPT>
+__global__ void __launch_bounds__(kSmThreads) softmax_dropout_bwd_kernel(
+    T* __restrict__ dy, const T* __restrict__ probs, SmGeom g, float p, float keep_scale, unsigned long long seed,
+    unsigned long long offset) {
+  constexpr int EPV = VecTraits<T>::kElems;
+  __shared__ float scratch[8];
+  const int tpr = g.tpr, rows_per_cta = kSmThreads / tpr;
+  const int grp = threadIdx.x / tpr, j = threadIdx.x % tpr;
+  const uint32_t thresh = dropout_thresh16(p);
+  const bool drop = p > 0.f;
+  const long long stride_rows = (long long)gridDim.x * rows_per_cta;
+  const long long iters = (g.rows + stride_rows - 1) / stride_rows;
+  for (long long it = 0; it < iters; ++it) {
+    const long long row = (it * gridDim.x + blockIdx.x) * rows_per_cta + grp;
+    const bool active = row < g.rows;
+    float d[VPT][EPV], y[VPT][EPV];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int vi = j + k * tpr;
+      if (active && vi < g.nvec) {
+        const long long off = row * g.K + (long long)vi * EPV;
+        unpack<T>(ld_global_nc_v4(dy + off), d[k]);
+        unpack<T>(ld_global_nc_v4(probs + off), y[k]);
+        if (drop) {
+          const uint32_t keep = dropout_keep8(seed, offset, (unsigned long long)off >> 3, thresh) >> (off & 7);
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) d[k][e] = ((keep >> e) & 1u) ? d[k][e] * keep_scale : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+          d[k][e] *= y[k][e];
+          dot += d[k][e];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) d[k][e] = y[k][e] = 0.f;
+      }
+    }
+    dot = group_reduce<false>(dot, tpr, scratch);
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < VPT; ++k) {
+        const int vi = j + k * tpr;
+        if (vi < g.nvec) {
+          float o[EPV];
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) o[e] = d[k][e] - y[k][e] * dot;
+          st_global_v4(dy + row * g.K + (long long)vi * EPV, pack<T>(o));
+        }
+      }
+    }
+  }
+}
+
+// ---- scalar fallback (row length not a multiple of the vector width): one warp per row ----------------
+template <typename T>
+__global__ void softmax_dropout_fwd_scalar(T* x, T* out, const T* mask, const T* bias, SmGeom g, float p,
+                                           float keep_scale, unsigned long long seed, unsigned long long offset) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const uint32_t thresh = dropout_thresh16(p);
+  for (long long row = warp; row < g.rows; row += nwarps) {
+    T* xr = x + row * g.K;
+    const T* mr = mask ? mask + (row / g.mask_div) * g.K : nullptr;
+    const T* br = bias ? bias + (row % g.bias_rows) * g.K : nullptr;
+    float mx = -CUDART_INF_F;
+    for (int c = lane; c < g.K; c += 32) {
+      float v = to_f32<T>(xr[c]) + (mr ? to_f32<T>(mr[c]) : 0.f) + (br ? to_f32<T>(br[c]) : 0.f);
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    if (mx == -CUDART_INF_F) mx = 0.f;
+    float sum = 0.f;
+    for (int c = lane; c < g.K; c += 32) {
+      float v = to_f32<T>(xr[c]) + (mr ? to_f32<T>(mr[c]) : 0.f) + (br ? to_f32<T>(br[c]) : 0.f);
+      sum += expf(v - mx);
+    }
+    sum = warp_sum(sum);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    for (int c = lane; c < g.K; c += 32) {
+      float v = to_f32<T>(xr[c]) + (mr ? to_f32<T>(mr[c]) : 0.f) + (br ? to_f32<T>(br[c]) : 0.f);
+      const T pr = from_f32<T>(expf(v - mx) * inv);
+      xr[c] = pr;
+      if (p > 0.f) {
+        const unsigned long long idx = (unsigned long long)(row * g.K + c);
+        const uint32_t keep = dropout_keep8(seed, offset, idx >> 3, thresh);
+        out[row * g.K + c] = ((keep >> (idx & 7)) & 1u) ? from_f32<T>(to_f32<T>(pr) * keep_scale) : from_f32<T>(0.f);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void softmax_dropout_bwd_scalar(T* dy, const T* probs, SmGeom g, float p, float keep_scale,
+                                           unsigned long long seed, unsigned long long offset) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const uint32_t thresh = dropout_thresh16(p);
+  for (long long row = warp; row < g.rows; row += nwarps) {
+    float dot = 0.f;
+    for (int c = lane; c < g.K; c += 32) {
+      const unsigned long long idx = (unsigned long long)(row * g.K + c);
+      float d = to_f32<T>(dy[idx]);
+      if (p > 0.f) {
+        const uint32_t keep = dropout_keep8(seed, offset, idx >> 3, thresh);
+        d = ((keep >> (idx & 7)) & 1u) ? d * keep_scale : 0.f;
+      }
+      dot += d * to_f32<T>(probs[idx]);
+    }
+    dot = warp_sum(dot);
+    for (int c = lane; c < g.K; c += 32) {
+      const unsigned long long idx = (unsigned long long)(row * g.K + c);
+      float d = to_f32<T>(dy[idx]);
+      if (p > 0.f) {
+        const uint32_t keep = dropout_keep8(seed, offset, idx >> 3, thresh);
+        d = ((keep >> (idx & 7)) & 1u) ? d * keep_scale : 0.f;
+      }
+      const float y = to_f32<T>(probs[idx]);
+      dy[idx] = from_f32<T>((d - dot) * y);
+    }
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------
+static int sm_count2() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+static bool make_sm_geom(SmGeom& g, long long rows, int K, int epv, int& vpt) {
+  g.rows = rows;
+  g.K = K;
+  if (K % epv != 0) return false;
+  g.nvec = K / epv;
+  int p2 = 1;
+  while (p2 < g.nvec) p2 <<= 1;
+  if (g.nvec <= 128) {
+    g.tpr = p2 < 32 ? p2 : 32;
+  } else {
+    int need = (g.nvec + 3) / 4;
+    p2 = 1;
+    while (p2 < need) p2 <<= 1;
+    g.tpr = p2;
+  }
+  if (g.tpr > 256) return false;
+  vpt = (g.nvec + g.tpr - 1) / g.tpr;
+  return vpt <= 4;
+}
+
+#define UB_SM_VPT(VPT_VALUE, ...)                              \
+  switch (VPT_VALUE) {                                         \
+    case 1: { constexpr int VPT = 1; __VA_ARGS__; break; }     \
+    case 2: { constexpr int VPT = 2; __VA_ARGS__; break; }     \
+    case 3: { constexpr int VPT = 3; __VA_ARGS__; break; }     \
+    case 4: { constexpr int VPT = 4; __VA_ARGS__; break; }     \
+    default: break;                                            \
+  }
+
+template <typename T>
+static void run_sm_fwd(void* x, void* out, const void* mask, const void* bias, long long rows, int K,
+                       long long mask_div, long long bias_rows, float p, unsigned long long seed,
+                       unsigned long long offset, cudaStream_t stream) {
+  SmGeom g;
+  int vpt = 0;
+  const bool vec = make_sm_geom(g, rows, K, VecTraits<T>::kElems, vpt) &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                     reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+  g.mask_div = mask_div > 0 ? mask_div : 1;
+  g.bias_rows = bias_rows > 0 ? bias_rows : 1;
+  const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (vec) {
+    const int rows_per_cta = kSmThreads / g.tpr;
+    long long need = (rows + rows_per_cta - 1) / rows_per_cta;
+    const long long cap = (long long)sm_count2() * 8;
+    const int grid = (int)(need < cap ? need : cap);
+    UB_SM_VPT(vpt, (softmax_dropout_fwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>(
+                       (T*)x, (T*)out, (const T*)mask, (const T*)bias, g, p, keep_scale, seed, offset)));
+  } else {
+    long long need = (rows + 7) / 8;
+    const long long cap = (long long)sm_count2() * 8;
+    const int grid = (int)(need < cap ? need : cap);
+    softmax_dropout_fwd_scalar<T><<<grid, 256, 0, stream>>>((T*)x, (T*)out, (const T*)mask, (const T*)bias, g, p,
+                                                            keep_scale, seed, offset);
+  }
+}
+
+template <typename T>
+static void run_sm_bwd(void* dy, const void* probs, long long rows, int K, float p, unsigned long long seed,
+                       unsigned long long offset, cudaStream_t stream) {
+  SmGeom g;
+  int vpt = 0;
+  const bool vec = make_sm_geom(g, rows, K, VecTraits<T>::kElems, vpt) &&
+                   ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(probs)) & 15) == 0;
+  g.mask_div = 1;
+  g.bias_rows = 1;
+  const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (vec) {
+    const int rows_per_cta = kSmThreads / g.tpr;
+    long long need = (rows + rows_per_cta - 1) / rows_per_cta;
+    const long long cap = (long long)sm_count2() * 8;
+    const int grid = (int)(need < cap ? need : cap);
+    UB_SM_VPT(vpt, (softmax_dropout_bwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>((T*)dy, (const T*)probs, g, p,
+                                                                                         keep_scale, seed, offset)));
+  } else {
+    long long need = (rows + 7) / 8;
+    const long long cap = (long long)sm_count2() * 8;
+    const int grid = (int)(need < cap ? need : cap);
+    softmax_dropout_bwd_scalar<T><<<grid, 256, 0, stream>>>((T*)dy, (const T*)probs, g, p, keep_scale, seed, offset);
+  }
+}
+
+void launch_softmax_dropout_fwd(void* x, void* out, const void* mask, const void* bias, long long rows, int K,
+                                long long mask_div, long long bias_rows, float p, unsigned long long seed,
+                                unsigned long long offset, int dtype, cudaStream_t stream) {
+  if (rows <= 0 || K <= 0) return;
+  if (dtype == kF32) run_sm_fwd<float>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, stream);
+  else if (dtype == kF16) run_sm_fwd<__half>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, stream);
+  else run_sm_fwd<__nv_bfloat16>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, stream);
+}
+
+void launch_softmax_dropout_bwd(void* dy, const void* probs, long long rows, int K, float p, unsigned long long seed,
+                                unsigned long long offset, int dtype, cudaStream_t stream) {
+  if (rows <= 0 || K <= 0) return;
+  if (dtype == kF32) run_sm_bwd<float>(dy, probs, rows, K, p, seed, offset, stream);
+  else if (dtype == kF16) run_sm_bwd<__half>(dy, probs, rows, K, p, seed, offset, stream);
+  else run_sm_bwd<__nv_bfloat16>(dy, probs, rows, K, p, seed, offset, stream);
+}
+
+}  // namespace ub

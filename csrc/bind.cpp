@@ -1,0 +1,450 @@
+// PyTorch bindings of the unicore_b200 sm_100a kernels (module ``unicore_b200._C``).
+// Only this translation unit sees the PyTorch headers; kernels are declared in csrc/api.h.
+#include <ATen/cuda/CUDAContext.h>
+#include <ATen/cuda/CUDAGeneratorImpl.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <mutex>
+#include <optional>
+#include <tuple>
+#include <vector>
+
+#include "api.h"
+#include "attn/fmha_api.h"
+#include "comm/comm_api.h"
+
+namespace {
+
+using torch::Tensor;
+using OptTensor = std::optional<Tensor>;
+
+int dtype_tag(const Tensor& t) {
+  switch (t.scalar_type()) {
+    case at::kFloat: return ub::kF32;
+    case at::kHalf: return ub::kF16;
+    case at::kBFloat16: return ub::kBF16;
+    default: TORCH_CHECK(false, "unsupported dtype ", t.scalar_type());
+  }
+  return -1;
+}
+
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+void check_cuda_contig(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+}
+
+const void* opt_ptr(const OptTensor& t) { return t.has_value() && t->defined() ? t->data_ptr() : nullptr; }
+
+// Reserve `increment` Philox counters from the default CUDA generator: (seed, offset).
+std::pair<uint64_t, uint64_t> philox_reserve(uint64_t increment) {
+  auto gen = at::get_generator_or_default<at::CUDAGeneratorImpl>(std::nullopt,
+                                                                 at::cuda::detail::getDefaultCUDAGenerator());
+  std::lock_guard<std::mutex> lock(gen->mutex_);
+  at::PhiloxCudaState st = gen->philox_cuda_state(increment);
+  TORCH_CHECK(!st.captured_, "unicore_b200 kernels do not support RNG under CUDA graph capture yet");
+  return {st.seed_.val, st.offset_.val};
+}
+
+void check_launch(const char* what) {
+  cudaError_t err = cudaGetLastError();
+  TORCH_CHECK(err == cudaSuccess, what, " launch failed: ", cudaGetErrorString(err));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// optimizer ops
+// ---------------------------------------------------------------------------------------------------
+Tensor multi_tensor_l2norm(const std::vector<Tensor>& tensors) {
+  TORCH_CHECK(!tensors.empty(), "empty tensor list");
+  const c10::cuda::CUDAGuard guard(tensors[0].device());
+  const int max_ctas = ub::l2norm_max_ctas();
+  // [0] running sum of squares, [1] ticket counter (as uint32), [2] result, [3..] per-CTA partials
+  Tensor ws = torch::zeros({3 + max_ctas}, tensors[0].options().dtype(at::kFloat));
+  float* base = ws.data_ptr<float>();
+  const size_t n = tensors.size();
+  for (size_t begin = 0; begin < n; begin += ub::kMaxTensorsPerLaunch) {
+    ub::NormTensors t{};
+    const size_t end = std::min(n, begin + (size_t)ub::kMaxTensorsPerLaunch);
+    for (size_t i = begin; i < end; ++i) {
+      check_cuda_contig(tensors[i], "l2norm input");
+      t.ptr[i - begin] = tensors[i].data_ptr();
+      t.numel[i - begin] = tensors[i].numel();
+      t.dtype[i - begin] = dtype_tag(tensors[i]);
+    }
+    t.count = (int)(end - begin);
+    ub::launch_l2norm(t, base, base + 3, reinterpret_cast<unsigned*>(base + 1), base + 2, end == n ? 1 : 0,
+                      cur_stream());
+  }
+  check_launch("l2norm");
+  return ws.select(0, 2);  // 0-dim view
+}
+
+void multi_tensor_scale(const std::vector<Tensor>& tensors, double scale, const OptTensor& scale_dev) {
+  if (tensors.empty()) return;
+  const c10::cuda::CUDAGuard guard(tensors[0].device());
+  const float* sd = nullptr;
+  if (scale_dev.has_value() && scale_dev->defined()) {
+    TORCH_CHECK(scale_dev->is_cuda() && scale_dev->scalar_type() == at::kFloat && scale_dev->numel() == 1);
+    sd = scale_dev->data_ptr<float>();
+  }
+  const size_t n = tensors.size();
+  for (size_t begin = 0; begin < n; begin += ub::kMaxTensorsPerLaunch) {
+    ub::ScaleTensors t{};
+    const size_t end = std::min(n, begin + (size_t)ub::kMaxTensorsPerLaunch);
+    for (size_t i = begin; i < end; ++i) {
+      check_cuda_contig(tensors[i], "scale input");
+      t.ptr[i - begin] = tensors[i].data_ptr();
+      t.numel[i - begin] = tensors[i].numel();
+      t.dtype[i - begin] = dtype_tag(tensors[i]);
+    }
+    t.count = (int)(end - begin);
+    ub::launch_scale(t, (float)scale, sd, cur_stream());
+  }
+  check_launch("scale");
+}
+
+void multi_tensor_adam(const std::vector<Tensor>& p, const std::vector<Tensor>& g, const std::vector<Tensor>& m,
+                       const std::vector<Tensor>& v, const std::vector<OptTensor>& p_half,
+                       const std::vector<double>& lr, const std::vector<double>& beta1,
+                       const std::vector<double>& beta2, const std::vector<double>& eps,
+                       const std::vector<int64_t>& step, const std::vector<bool>& bias_correction,
+                       const std::vector<double>& weight_decay, double grad_scale, const OptTensor& scale_dev,
+                       bool zero_grad, bool stochastic_rounding) {
+  const size_t n = p.size();
+  TORCH_CHECK(n > 0 && g.size() == n && m.size() == n && v.size() == n && p_half.size() == n);
+  const c10::cuda::CUDAGuard guard(p[0].device());
+  ub::AdamLaunch cfg{};
+  cfg.inv_scale = (float)(1.0 / grad_scale);
+  cfg.scale_dev = nullptr;
+  if (scale_dev.has_value() && scale_dev->defined()) {
+    TORCH_CHECK(scale_dev->is_cuda() && scale_dev->scalar_type() == at::kFloat && scale_dev->numel() == 1);
+    cfg.scale_dev = scale_dev->data_ptr<float>();
+  }
+  cfg.zero_grad = zero_grad ? 1 : 0;
+  cfg.stochastic_rounding = stochastic_rounding ? 1 : 0;
+  cfg.ema_decay = 0.f;
+  cfg.seed = cfg.offset = 0;
+  if (stochastic_rounding) {
+    auto so = philox_reserve(4);
+    cfg.seed = so.first;
+    cfg.offset = so.second;
+  }
+  unsigned long long elem_base = 0;
+  for (size_t begin = 0; begin < n; begin += ub::kMaxTensorsPerLaunch) {
+    ub::AdamTensors t{};
+    const size_t end = std::min(n, begin + (size_t)ub::kMaxTensorsPerLaunch);
+    for (size_t i = begin; i < end; ++i) {
+      const size_t k = i - begin;
+      check_cuda_contig(p[i], "adam p");
+      check_cuda_contig(g[i], "adam g");
+      check_cuda_contig(m[i], "adam m");
+      check_cuda_contig(v[i], "adam v");
+      TORCH_CHECK(m[i].scalar_type() == at::kFloat && v[i].scalar_type() == at::kFloat, "moments must be fp32");
+      TORCH_CHECK(p[i].numel() == g[i].numel() && p[i].numel() == m[i].numel() && p[i].numel() == v[i].numel(),
+                  "adam tensors must have equal numel");
+      t.p[k] = p[i].data_ptr();
+      t.g[k] = g[i].data_ptr();
+      t.m[k] = m[i].data_ptr<float>();
+      t.v[k] = v[i].data_ptr<float>();
+      t.p_dtype[k] = dtype_tag(p[i]);
+      t.g_dtype[k] = dtype_tag(g[i]);
+      t.p_half[k] = nullptr;
+      t.half_dtype[k] = ub::kF16;
+      if (p_half[i].has_value() && p_half[i]->defined()) {
+        check_cuda_contig(*p_half[i], "adam p_half");
+        TORCH_CHECK(p_half[i]->numel() == p[i].numel());
+        t.p_half[k] = p_half[i]->data_ptr();
+        t.half_dtype[k] = dtype_tag(*p_half[i]);
+      }
+      t.ema[k] = nullptr;
+      t.numel[k] = p[i].numel();
+      double step_size = lr[i];
+      if (bias_correction[i]) {
+        const double bc1 = 1.0 - std::pow(beta1[i], (double)step[i]);
+        const double bc2 = 1.0 - std::pow(beta2[i], (double)step[i]);
+        step_size = lr[i] * std::sqrt(bc2) / bc1;
+      }
+      t.step_size[k] = (float)step_size;
+      t.decay_mul[k] = (float)(1.0 - step_size * weight_decay[i]);
+      t.beta1[k] = (float)beta1[i];
+      t.beta2[k] = (float)beta2[i];
+      t.eps[k] = (float)eps[i];
+      t.elem_base[k] = elem_base;
+      elem_base += ((unsigned long long)p[i].numel() + 7ull) & ~7ull;
+    }
+    t.count = (int)(end - begin);
+    ub::launch_adam(t, cfg, cur_stream());
+  }
+  check_launch("adam");
+}
+
+void fp32_to_bf16_sr(const Tensor& in, Tensor out) {
+  check_cuda_contig(in, "in");
+  check_cuda_contig(out, "out");
+  TORCH_CHECK(in.scalar_type() == at::kFloat && out.scalar_type() == at::kBFloat16 && in.numel() == out.numel());
+  const c10::cuda::CUDAGuard guard(in.device());
+  auto so = philox_reserve(4);
+  ub::launch_fp32_to_bf16_sr(in.data_ptr<float>(), out.data_ptr(), in.numel(), so.first, so.second, cur_stream());
+  check_launch("fp32_to_bf16_sr");
+}
+
+void ema_update(Tensor ema, const Tensor& p, double decay) {
+  check_cuda_contig(ema, "ema");
+  check_cuda_contig(p, "p");
+  TORCH_CHECK(ema.scalar_type() == at::kFloat && p.scalar_type() == at::kFloat && ema.numel() == p.numel());
+  const c10::cuda::CUDAGuard guard(ema.device());
+  ub::launch_ema(ema.data_ptr<float>(), p.data_ptr<float>(), ema.numel(), (float)decay, cur_stream());
+  check_launch("ema");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// norms
+// ---------------------------------------------------------------------------------------------------
+std::tuple<Tensor, Tensor, Tensor> layernorm_fwd(const Tensor& x, const Tensor& gamma, const Tensor& beta, double eps) {
+  check_cuda_contig(x, "x");
+  check_cuda_contig(gamma, "gamma");
+  check_cuda_contig(beta, "beta");
+  TORCH_CHECK(x.dim() == 2 && gamma.numel() == x.size(1) && beta.numel() == x.size(1));
+  TORCH_CHECK(gamma.scalar_type() == x.scalar_type() && beta.scalar_type() == x.scalar_type());
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int rows = (int)x.size(0), cols = (int)x.size(1);
+  Tensor y = torch::empty_like(x);
+  Tensor mean = torch::empty({rows}, x.options().dtype(at::kFloat));
+  Tensor rstd = torch::empty({rows}, x.options().dtype(at::kFloat));
+  ub::launch_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr<float>(),
+                           rstd.data_ptr<float>(), rows, cols, (float)eps, dtype_tag(x), cur_stream());
+  check_launch("layernorm_fwd");
+  return {y, mean, rstd};
+}
+
+std::tuple<Tensor, Tensor, Tensor> layernorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& mean,
+                                                 const Tensor& rstd, const Tensor& gamma) {
+  check_cuda_contig(dy, "dy");
+  check_cuda_contig(x, "x");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int rows = (int)x.size(0), cols = (int)x.size(1);
+  Tensor dx = torch::empty_like(x);
+  Tensor dgamma = torch::empty_like(gamma), dbeta = torch::empty_like(gamma);
+  const int parts = ub::norm_bwd_parts(rows, cols);
+  Tensor part = torch::empty({2, parts, cols}, x.options().dtype(at::kFloat));
+  ub::launch_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                           gamma.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                           part.data_ptr<float>(), part.data_ptr<float>() + (size_t)parts * cols, nullptr, rows, cols,
+                           dtype_tag(x), cur_stream());
+  check_launch("layernorm_bwd");
+  return {dx, dgamma, dbeta};
+}
+
+std::tuple<Tensor, Tensor> rmsnorm_fwd(const Tensor& x, const Tensor& gamma, double eps) {
+  check_cuda_contig(x, "x");
+  check_cuda_contig(gamma, "gamma");
+  TORCH_CHECK(x.dim() == 2 && gamma.numel() == x.size(1) && gamma.scalar_type() == x.scalar_type());
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int rows = (int)x.size(0), cols = (int)x.size(1);
+  Tensor y = torch::empty_like(x);
+  Tensor rstd = torch::empty({rows}, x.options().dtype(at::kFloat));
+  ub::launch_rmsnorm_fwd(x.data_ptr(), gamma.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(), rows, cols, (float)eps,
+                         dtype_tag(x), cur_stream());
+  check_launch("rmsnorm_fwd");
+  return {y, rstd};
+}
+
+std::tuple<Tensor, Tensor> rmsnorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& rstd, const Tensor& gamma) {
+  check_cuda_contig(dy, "dy");
+  check_cuda_contig(x, "x");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int rows = (int)x.size(0), cols = (int)x.size(1);
+  Tensor dx = torch::empty_like(x);
+  Tensor dgamma = torch::empty_like(gamma);
+  const int parts = ub::norm_bwd_parts(rows, cols);
+  Tensor part = torch::empty({parts, cols}, x.options().dtype(at::kFloat));
+  ub::launch_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), rstd.data_ptr<float>(), gamma.data_ptr(), dx.data_ptr(),
+                         dgamma.data_ptr(), part.data_ptr<float>(), nullptr, rows, cols, dtype_tag(x), cur_stream());
+  check_launch("rmsnorm_bwd");
+  return {dx, dgamma};
+}
+
+// ---------------------------------------------------------------------------------------------------
+// softmax + dropout
+// ---------------------------------------------------------------------------------------------------
+std::tuple<Tensor, int64_t, int64_t> softmax_dropout_fwd(Tensor x, const OptTensor& mask, const OptTensor& bias, double p,
+                                                         bool training) {
+  check_cuda_contig(x, "input");
+  TORCH_CHECK(x.dim() == 3, "input must be 3-D [batch, q, k]");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const long long rows = x.size(0) * x.size(1);
+  const int K = (int)x.size(2);
+  long long mask_div = 1, bias_rows = 1;
+  if (mask.has_value() && mask->defined()) {
+    check_cuda_contig(*mask, "mask");
+    TORCH_CHECK(mask->scalar_type() == x.scalar_type() && mask->dim() == 3 && mask->size(2) == K);
+    const long long mask_rows = mask->size(0) * mask->size(1);
+    TORCH_CHECK(mask_rows > 0 && rows % mask_rows == 0, "mask rows must divide input rows");
+    mask_div = rows / mask_rows;
+  }
+  if (bias.has_value() && bias->defined()) {
+    check_cuda_contig(*bias, "bias");
+    TORCH_CHECK(bias->scalar_type() == x.scalar_type() && bias->dim() == 3 && bias->size(2) == K);
+    bias_rows = bias->size(0) * bias->size(1);
+    TORCH_CHECK(bias_rows > 0 && rows % bias_rows == 0, "bias rows must divide input rows");
+  }
+  const float pf = training ? (float)p : 0.f;
+  uint64_t seed = 0, offset = 0;
+  Tensor out = x;
+  if (pf > 0.f) {
+    auto so = philox_reserve(4);
+    seed = so.first;
+    offset = so.second;
+    out = torch::empty_like(x);
+  }
+  ub::launch_softmax_dropout_fwd(x.data_ptr(), out.data_ptr(), opt_ptr(mask), opt_ptr(bias), rows, K, mask_div,
+                                 bias_rows, pf, seed, offset, dtype_tag(x), cur_stream());
+  check_launch("softmax_dropout_fwd");
+  return {out, (int64_t)seed, (int64_t)offset};
+}
+
+Tensor softmax_dropout_bwd(Tensor dy, const Tensor& probs, double p, int64_t seed, int64_t offset) {
+  check_cuda_contig(dy, "grad_output");
+  check_cuda_contig(probs, "softmax_results");
+  TORCH_CHECK(dy.dim() == 3 && dy.sizes() == probs.sizes() && dy.scalar_type() == probs.scalar_type());
+  const c10::cuda::CUDAGuard guard(dy.device());
+  ub::launch_softmax_dropout_bwd(dy.data_ptr(), probs.data_ptr(), dy.size(0) * dy.size(1), (int)dy.size(2), (float)p,
+                                 (uint64_t)seed, (uint64_t)offset, dtype_tag(dy), cur_stream());
+  check_launch("softmax_dropout_bwd");
+  return dy;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused element-wise
+// ---------------------------------------------------------------------------------------------------
+Tensor bias_gelu_fwd(const Tensor& x, const OptTensor& bias) {
+  check_cuda_contig(x, "x");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int cols = (int)x.size(-1);
+  TORCH_CHECK(cols % 8 == 0 && (x.scalar_type() == at::kHalf || x.scalar_type() == at::kBFloat16));
+  Tensor y = torch::empty_like(x);
+  ub::launch_bias_gelu_fwd(x.data_ptr(), opt_ptr(bias), y.data_ptr(), x.numel() / cols, cols, dtype_tag(x),
+                           cur_stream());
+  check_launch("bias_gelu_fwd");
+  return y;
+}
+
+Tensor bias_gelu_bwd(const Tensor& dy, const Tensor& x, const OptTensor& bias) {
+  check_cuda_contig(dy, "dy");
+  check_cuda_contig(x, "x");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int cols = (int)x.size(-1);
+  Tensor dx = torch::empty_like(x);
+  ub::launch_bias_gelu_bwd(dy.data_ptr(), x.data_ptr(), opt_ptr(bias), dx.data_ptr(), x.numel() / cols, cols,
+                           dtype_tag(x), cur_stream());
+  check_launch("bias_gelu_bwd");
+  return dx;
+}
+
+std::tuple<Tensor, Tensor, Tensor, Tensor, int64_t, int64_t> bias_dropout_add_ln_fwd(
+    const Tensor& x, const OptTensor& bias, const Tensor& residual, const Tensor& gamma, const Tensor& beta, double p,
+    double eps) {
+  check_cuda_contig(x, "x");
+  check_cuda_contig(residual, "residual");
+  TORCH_CHECK(x.dim() == 2 && residual.sizes() == x.sizes() && residual.scalar_type() == x.scalar_type());
+  TORCH_CHECK(gamma.scalar_type() == x.scalar_type() && beta.scalar_type() == x.scalar_type());
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int rows = (int)x.size(0), cols = (int)x.size(1);
+  Tensor y = torch::empty_like(x), summed = torch::empty_like(x);
+  Tensor mean = torch::empty({rows}, x.options().dtype(at::kFloat));
+  Tensor rstd = torch::empty({rows}, x.options().dtype(at::kFloat));
+  uint64_t seed = 0, offset = 0;
+  if (p > 0.0) {
+    auto so = philox_reserve(4);
+    seed = so.first;
+    offset = so.second;
+  }
+  ub::launch_bias_dropout_add_ln_fwd(x.data_ptr(), opt_ptr(bias), residual.data_ptr(), gamma.data_ptr(),
+                                     beta.data_ptr(), y.data_ptr(), summed.data_ptr(), mean.data_ptr<float>(),
+                                     rstd.data_ptr<float>(), rows, cols, (float)p, (float)eps, seed, offset,
+                                     dtype_tag(x), cur_stream());
+  check_launch("bias_dropout_add_ln_fwd");
+  return {y, mean, rstd, summed, (int64_t)seed, (int64_t)offset};
+}
+
+std::tuple<Tensor, Tensor, Tensor, Tensor> bias_dropout_add_ln_bwd(const Tensor& dy, const Tensor& summed,
+                                                                   const Tensor& mean, const Tensor& rstd,
+                                                                   const Tensor& gamma, double p, int64_t seed,
+                                                                   int64_t offset) {
+  check_cuda_contig(dy, "dy");
+  check_cuda_contig(summed, "summed");
+  const c10::cuda::CUDAGuard guard(dy.device());
+  const int rows = (int)summed.size(0), cols = (int)summed.size(1);
+  Tensor dsum = torch::empty_like(summed);
+  Tensor dx = p > 0.0 ? torch::empty_like(summed) : dsum;
+  Tensor dgamma = torch::empty_like(gamma), dbeta = torch::empty_like(gamma);
+  const int parts = ub::norm_bwd_parts(rows, cols);
+  Tensor part = torch::empty({2, parts, cols}, summed.options().dtype(at::kFloat));
+  ub::launch_bias_dropout_add_ln_bwd(dy.data_ptr(), summed.data_ptr(), mean.data_ptr<float>(),
+                                     rstd.data_ptr<float>(), gamma.data_ptr(), dsum.data_ptr(), dx.data_ptr(),
+                                     dgamma.data_ptr(), dbeta.data_ptr(), part.data_ptr<float>(),
+                                     part.data_ptr<float>() + (size_t)parts * cols, nullptr, rows, cols, (float)p,
+                                     (uint64_t)seed, (uint64_t)offset, dtype_tag(summed), cur_stream());
+  check_launch("bias_dropout_add_ln_bwd");
+  return {dsum, dx, dgamma, dbeta};
+}
+
+std::tuple<Tensor, Tensor> softmax_xent_fwd(const Tensor& logits, const Tensor& target, int64_t ignore_index) {
+  check_cuda_contig(logits, "logits");
+  check_cuda_contig(target, "target");
+  TORCH_CHECK(logits.dim() == 2 && target.dim() == 1 && target.size(0) == logits.size(0));
+  TORCH_CHECK(target.scalar_type() == at::kLong);
+  const c10::cuda::CUDAGuard guard(logits.device());
+  const int rows = (int)logits.size(0), cols = (int)logits.size(1);
+  Tensor loss = torch::empty({rows}, logits.options().dtype(at::kFloat));
+  Tensor lse = torch::empty({rows}, logits.options().dtype(at::kFloat));
+  ub::launch_softmax_xent_fwd(logits.data_ptr(), (const long long*)target.data_ptr<int64_t>(), loss.data_ptr<float>(),
+                              lse.data_ptr<float>(), rows, cols, ignore_index, dtype_tag(logits), cur_stream());
+  check_launch("softmax_xent_fwd");
+  return {loss, lse};
+}
+
+Tensor softmax_xent_bwd(const Tensor& logits, const Tensor& target, const Tensor& lse, const Tensor& dloss,
+                        int64_t ignore_index) {
+  check_cuda_contig(logits, "logits");
+  TORCH_CHECK(dloss.is_cuda() && dloss.scalar_type() == at::kFloat && dloss.numel() == 1);
+  const c10::cuda::CUDAGuard guard(logits.device());
+  const int rows = (int)logits.size(0), cols = (int)logits.size(1);
+  Tensor dlogits = torch::empty_like(logits);
+  ub::launch_softmax_xent_bwd(logits.data_ptr(), (const long long*)target.data_ptr<int64_t>(), lse.data_ptr<float>(),
+                              dloss.data_ptr<float>(), dlogits.data_ptr(), rows, cols, ignore_index,
+                              dtype_tag(logits), cur_stream());
+  check_launch("softmax_xent_bwd");
+  return dlogits;
+}
+
+}  // namespace
+
+// defined in attn/fmha_bind.cpp and comm/comm_bind.cpp
+void register_fmha(pybind11::module_& m);
+void register_comm(pybind11::module_& m);
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "unicore_b200 sm_100a kernels";
+  m.def("multi_tensor_l2norm", &multi_tensor_l2norm);
+  m.def("multi_tensor_scale", &multi_tensor_scale);
+  m.def("multi_tensor_adam", &multi_tensor_adam);
+  m.def("fp32_to_bf16_sr", &fp32_to_bf16_sr);
+  m.def("ema_update", &ema_update);
+  m.def("layernorm_fwd", &layernorm_fwd);
+  m.def("layernorm_bwd", &layernorm_bwd);
+  m.def("rmsnorm_fwd", &rmsnorm_fwd);
+  m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("softmax_dropout_fwd", &softmax_dropout_fwd);
+  m.def("softmax_dropout_bwd", &softmax_dropout_bwd);
+  m.def("bias_gelu_fwd", &bias_gelu_fwd);
+  m.def("bias_gelu_bwd", &bias_gelu_bwd);
+  m.def("bias_dropout_add_ln_fwd", &bias_dropout_add_ln_fwd);
+  m.def("bias_dropout_add_ln_bwd", &bias_dropout_add_ln_bwd);
+  m.def("softmax_xent_fwd", &softmax_xent_fwd);
+  m.def("softmax_xent_bwd", &softmax_xent_bwd);
+  register_fmha(m);
+  register_comm(m);
+}

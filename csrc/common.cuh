@@ -1,0 +1,204 @@
+// Shared device helpers for the unicore_b200 sm_100a kernels.
+//   * 128-bit vector load/store wrappers and 16-bit <-> fp32 pack/unpack
+//   * warp / block reductions
+//   * counter-based Philox4x32-10 (no per-thread state, no curand_init)
+//   * dtype tags shared with the host binding (csrc/api.h)
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "api.h"
+
+namespace ub {
+
+#define UB_DEVICE __device__ __forceinline__
+
+// ------------------------------------------------------------------------------------------------
+// 16-byte vector access
+// ------------------------------------------------------------------------------------------------
+struct alignas(16) Vec16 {
+  uint32_t w[4];
+};
+
+UB_DEVICE Vec16 ld_global_v4(const void* p) {
+  Vec16 v;
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3])
+               : "l"(p));
+  return v;
+}
+// streaming load: read-once data, do not pollute L1
+UB_DEVICE Vec16 ld_global_nc_v4(const void* p) {
+  Vec16 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3])
+               : "l"(p));
+  return v;
+}
+UB_DEVICE void st_global_v4(void* p, const Vec16& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]),
+               "r"(v.w[3])
+               : "memory");
+}
+UB_DEVICE void st_global_na_v4(void* p, const Vec16& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]),
+               "r"(v.w[2]), "r"(v.w[3])
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// scalar conversions
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+UB_DEVICE float to_f32(T v);
+template <>
+UB_DEVICE float to_f32<float>(float v) { return v; }
+template <>
+UB_DEVICE float to_f32<__half>(__half v) { return __half2float(v); }
+template <>
+UB_DEVICE float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+UB_DEVICE T from_f32(float v);
+template <>
+UB_DEVICE float from_f32<float>(float v) { return v; }
+template <>
+UB_DEVICE __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <>
+UB_DEVICE __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// elements per 16-byte vector
+template <typename T>
+struct VecTraits { static constexpr int kElems = 16 / sizeof(T); };
+
+// unpack a 16-byte vector of T into fp32 lanes
+template <typename T>
+UB_DEVICE void unpack(const Vec16& v, float* out);
+template <>
+UB_DEVICE void unpack<float>(const Vec16& v, float* out) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = __uint_as_float(v.w[i]);
+}
+template <>
+UB_DEVICE void unpack<__half>(const Vec16& v, float* out) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h = *reinterpret_cast<const __half2*>(&v.w[i]);
+    float2 f = __half22float2(h);
+    out[2 * i] = f.x;
+    out[2 * i + 1] = f.y;
+  }
+}
+template <>
+UB_DEVICE void unpack<__nv_bfloat16>(const Vec16& v, float* out) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    // bf16 -> fp32 is a 16-bit shift
+    out[2 * i] = __uint_as_float(v.w[i] << 16);
+    out[2 * i + 1] = __uint_as_float(v.w[i] & 0xffff0000u);
+  }
+}
+
+template <typename T>
+UB_DEVICE Vec16 pack(const float* in);
+template <>
+UB_DEVICE Vec16 pack<float>(const float* in) {
+  Vec16 v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v.w[i] = __float_as_uint(in[i]);
+  return v;
+}
+template <>
+UB_DEVICE Vec16 pack<__half>(const float* in) {
+  Vec16 v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h = __floats2half2_rn(in[2 * i], in[2 * i + 1]);
+    v.w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return v;
+}
+template <>
+UB_DEVICE Vec16 pack<__nv_bfloat16>(const float* in) {
+  Vec16 v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+    v.w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------------------------
+UB_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+UB_DEVICE float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Sum across the whole CTA (blockDim.x multiple of 32, <= 1024). Result valid in ALL threads.
+// `smem` must hold 32 floats.
+UB_DEVICE float block_sum(float v, float* smem) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect smem reuse between consecutive calls
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  float r = (lane < nw) ? smem[lane] : 0.f;
+  return warp_sum(r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10, counter based.  philox(seed, offset, ctr) is a pure function: the same
+// (seed, offset, element index) yields the same random bits in forward and backward kernels and on
+// every data-parallel rank.
+// ------------------------------------------------------------------------------------------------
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+
+UB_DEVICE Philox4 philox4x32_10(uint64_t seed, uint64_t offset, uint64_t ctr) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = (uint32_t)offset, c3 = (uint32_t)(offset >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+// Dropout decisions for 8 consecutive elements whose first linear index is `idx8*8`:
+// one Philox call gives 8 x 16-bit uniforms; keep iff u16 >= thresh16 (thresh16 = round(p*65536)).
+// Returns an 8-bit keep mask (bit i = element i kept).
+UB_DEVICE uint32_t dropout_keep8(uint64_t seed, uint64_t offset, uint64_t idx8, uint32_t thresh16) {
+  const Philox4 r = philox4x32_10(seed, offset, idx8);
+  uint32_t m = 0;
+  const uint32_t ws[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m |= ((ws[i] & 0xffffu) >= thresh16 ? 1u : 0u) << (2 * i);
+    m |= ((ws[i] >> 16) >= thresh16 ? 1u : 0u) << (2 * i + 1);
+  }
+  return m;
+}
+
+UB_DEVICE uint32_t dropout_thresh16(float p) {
+  float t = p * 65536.f + 0.5f;
+  return t >= 65535.f ? 65535u : (uint32_t)t;
+}
+
+}  // namespace ub

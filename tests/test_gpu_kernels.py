@@ -1,0 +1,336 @@
+"""Numerics of every hand-written sm_100a kernel against plain PyTorch fp32 references."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.float16, torch.bfloat16]
+TOL = {torch.float32: 2e-5, torch.float16: 2e-3, torch.bfloat16: 1.6e-2}
+
+
+def _ops():
+    from unicore import ops
+
+    assert ops.USE_NATIVE, "native kernels must be active on the GPU box"
+    return ops
+
+
+def maxdiff(a, b):
+    return (a.float() - b.float()).abs().max().item()
+
+
+# ---------------------------------------------------------------------------------------------------
+# optimizer ops
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_l2norm(dtype):
+    ops = _ops()
+    torch.manual_seed(0)
+    ts = [torch.randn(n, device="cuda").to(dtype) for n in (1, 7, 8, 1023, 8192, 100003, 3_000_001)]
+    ts.append(torch.randn(4099, device="cuda").to(dtype)[3:])  # misaligned view
+    ref = torch.sqrt(sum(t.float().pow(2).sum() for t in ts))
+    got = ops.multi_tensor_l2norm(ts)
+    assert got.dtype == torch.float32 and got.dim() == 0
+    assert abs(got.item() - ref.item()) / ref.item() < 1e-5
+    many = [torch.randn(257, device="cuda").to(dtype) for _ in range(61)]  # > 24 tensors: several launches
+    ref = torch.sqrt(sum(t.float().pow(2).sum() for t in many))
+    assert abs(ops.multi_tensor_l2norm(many).item() - ref.item()) / ref.item() < 1e-5
+    bad = [torch.ones(100, device="cuda", dtype=dtype), torch.full((5,), float("inf"), device="cuda", dtype=dtype)]
+    assert math.isinf(ops.multi_tensor_l2norm(bad).item())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_scale(dtype):
+    ops = _ops()
+    ts = [torch.randn(n, device="cuda").to(dtype) for n in (5, 4096, 77777)]
+    ref = [t.float() * 0.37 for t in ts]
+    ops.multi_tensor_scale_(ts, 0.37)
+    for t, r in zip(ts, ref):
+        assert maxdiff(t, r) <= TOL[dtype] * 4
+    ts2 = [t.clone() for t in ts]
+    ops.multi_tensor_scale_(ts2, torch.tensor(2.0, device="cuda"))
+    for a, b in zip(ts2, ts):
+        assert maxdiff(a, b.float() * 2) <= TOL[dtype] * 4
+
+
+def _adam_ref(p, g, m, v, lr, b1, b2, eps, step, wd, scale):
+    g = g.float() / scale
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    ss = lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step)
+    p = p * (1 - ss * wd) - ss * m / (v.sqrt() + eps)
+    return p, m, v
+
+
+@pytest.mark.parametrize("gdtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n", [1, 9, 8192, 100001])
+def test_fused_adam(gdtype, n):
+    ops = _ops()
+    torch.manual_seed(1)
+    p = torch.randn(n, device="cuda")
+    g = (torch.randn(n, device="cuda") * 8).to(gdtype)
+    m = torch.randn(n, device="cuda") * 0.1
+    v = torch.rand(n, device="cuda") * 0.1
+    half = torch.empty(n, device="cuda", dtype=torch.float16 if gdtype != torch.bfloat16 else torch.bfloat16)
+    rp, rm, rv = _adam_ref(p.clone(), g, m.clone(), v.clone(), 1e-2, 0.9, 0.98, 1e-6, 3, 0.01, 8.0)
+    work = [dict(p=p, g=g, m=m, v=v, p_half=half, lr=1e-2, beta1=0.9, beta2=0.98, eps=1e-6, step=3,
+                 bias_correction=True, weight_decay=0.01)]
+    ops.fused_adam(work, grad_scale=torch.tensor(8.0, device="cuda"), zero_grad=True)
+    assert maxdiff(p, rp) < 1e-5 and maxdiff(m, rm) < 1e-5 and maxdiff(v, rv) < 1e-4
+    assert maxdiff(half, rp) < 1e-2
+    assert g.abs().max().item() == 0.0
+
+
+def test_fused_adam_many_tensors_and_fp32_step():
+    ops = _ops()
+    torch.manual_seed(2)
+    work, refs = [], []
+    for i in range(40):
+        n = 100 + 37 * i
+        p, g = torch.randn(n, device="cuda"), torch.randn(n, device="cuda")
+        m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        refs.append(_adam_ref(p.clone(), g, m.clone(), v.clone(), 1e-3, 0.9, 0.999, 1e-8, 1, 0.0, 1.0))
+        work.append(dict(p=p, g=g, m=m, v=v, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, step=1,
+                         bias_correction=True, weight_decay=0.0))
+    ops.fused_adam(work, grad_scale=1.0)
+    for w, (rp, rm, rv) in zip(work, refs):
+        assert maxdiff(w["p"], rp) < 1e-5 and maxdiff(w["m"], rm) < 1e-6
+
+
+def test_stochastic_rounding_unbiased():
+    ops = _ops()
+    x = torch.full((1 << 20,), 1.0 + 2 ** -10, device="cuda")  # between two bf16 values (spacing 2^-7)
+    out = torch.empty_like(x, dtype=torch.bfloat16)
+    ops.fp32_to_bf16_sr(x, out)
+    vals = out.float().unique()
+    assert set(vals.tolist()) <= {1.0, 1.0 + 2 ** -7}
+    assert abs(out.float().mean().item() - x[0].item()) < 2e-4
+    out2 = torch.empty_like(out)
+    ops.fp32_to_bf16_sr(x, out2)
+    assert not torch.equal(out, out2)  # fresh Philox offset each call
+
+
+def test_ema_update():
+    ops = _ops()
+    ema, p = torch.randn(100003, device="cuda"), torch.randn(100003, device="cuda")
+    ref = ema - (1 - 0.99) * (ema - p)
+    ops.ema_update_(ema, p, 0.99)
+    assert maxdiff(ema, ref) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# norms
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("dim", [8, 64, 128, 200, 512, 768, 1024, 1536, 4096, 8192])
+def test_layer_norm(dtype, dim):
+    ops = _ops()
+    torch.manual_seed(3)
+    rows = 257
+    x = (torch.randn(rows, dim, device="cuda") * 2 + 0.5).to(dtype).requires_grad_(True)
+    w = (torch.randn(dim, device="cuda") * 0.5 + 1).to(dtype).requires_grad_(True)
+    b = torch.randn(dim, device="cuda").to(dtype).requires_grad_(True)
+    dy = torch.randn(rows, dim, device="cuda").to(dtype)
+    y = ops.layer_norm(x, (dim,), w, b, 1e-5)
+    y.backward(dy)
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    yr = F.layer_norm(xr, (dim,), wr, br, 1e-5)
+    yr.backward(dy.float())
+    tol = TOL[dtype]
+    assert maxdiff(y, yr) < tol * 8
+    assert maxdiff(x.grad, xr.grad) < tol * 16
+    scale = max(1.0, wr.grad.abs().max().item())
+    assert maxdiff(w.grad, wr.grad) / scale < tol * 4
+    assert maxdiff(b.grad, br.grad) / max(1.0, br.grad.abs().max().item()) < tol * 4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("dim", [64, 768, 1000, 2048])
+def test_rms_norm(dtype, dim):
+    ops = _ops()
+    torch.manual_seed(4)
+    rows = 130
+    x = torch.randn(rows, dim, device="cuda").to(dtype).requires_grad_(True)
+    w = (torch.randn(dim, device="cuda") * 0.5 + 1).to(dtype).requires_grad_(True)
+    dy = torch.randn(rows, dim, device="cuda").to(dtype)
+    y = ops.rms_norm(x, (dim,), w, 1e-5)
+    y.backward(dy)
+    xr, wr = (t.detach().float().requires_grad_(True) for t in (x, w))
+    yr = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-5) * wr
+    yr.backward(dy.float())
+    tol = TOL[dtype]
+    assert maxdiff(y, yr) < tol * 8
+    assert maxdiff(x.grad, xr.grad) < tol * 16
+    assert maxdiff(w.grad, wr.grad) / max(1.0, wr.grad.abs().max().item()) < tol * 4
+
+
+def test_layer_norm_3d_and_module():
+    from unicore.modules import LayerNorm
+
+    ln = LayerNorm(768).cuda().half()
+    x = torch.randn(4, 33, 768, device="cuda", dtype=torch.half)
+    y = ln(x)
+    ref = F.layer_norm(x.float(), (768,), ln.weight.float(), ln.bias.float(), 1e-5)
+    assert maxdiff(y, ref) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------
+# softmax_dropout (shapes follow the reference test-suite: 4-D and 5-D "triangle" broadcasts)
+# ---------------------------------------------------------------------------------------------------
+def _gen_mask(shape, dtype):
+    m = (torch.rand(shape, device="cuda") > 0.8).to(dtype) * -3e4
+    return m
+
+
+def _check_softmax(x_shape, mask_shape, bias_shape, dtype):
+    ops = _ops()
+    torch.manual_seed(5)
+    x = torch.randn(x_shape, device="cuda").to(dtype)
+    mask = _gen_mask(mask_shape, dtype) if mask_shape else None
+    bias = torch.randn(bias_shape, device="cuda").to(dtype).requires_grad_(True) if bias_shape else None
+    xin = x.clone().requires_grad_(True)
+    out = ops.softmax_dropout(xin, 0.0, True, mask=mask, bias=bias, inplace=False)
+    dy = torch.randn_like(out)
+    out.backward(dy)
+    xr = x.float().requires_grad_(True)
+    br = bias.detach().float().requires_grad_(True) if bias is not None else None
+    z = xr
+    if mask is not None:
+        z = z + mask.float()
+    if br is not None:
+        z = z + br
+    ref = F.softmax(z, dim=-1)
+    ref.backward(dy.float())
+    tol = 1e-3 if dtype != torch.bfloat16 else 8e-3
+    assert maxdiff(out, ref) < tol
+    assert maxdiff(xin.grad, xr.grad) < tol
+    if bias is not None:
+        assert maxdiff(bias.grad, br.grad) / max(1.0, br.grad.abs().max().item()) < tol * 8
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("k", [8, 64, 128, 256, 512, 1024, 1536, 2048, 100])
+def test_softmax_4d(dtype, k):
+    _check_softmax((4, 8, 16, k), (4, 1, 1, k), (4, 8, 16, k), dtype)
+    _check_softmax((4, 8, 16, k), None, (1, 8, 16, k), dtype)
+    _check_softmax((4, 8, 16, k), (4, 8, 16, k), None, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("k", [64, 256])
+def test_softmax_tri(dtype, k):
+    _check_softmax((2, 8, 4, 16, k), (2, 8, 1, 1, k), (1, 1, 4, 16, k), dtype)
+    _check_softmax((2, 8, 4, 16, k), (2, 8, 4, 1, k), (1, 8, 4, 16, k), dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("k", [128, 512, 2048, 100])
+def test_softmax_dropout_statistics_and_backward(dtype, k):
+    ops = _ops()
+    torch.manual_seed(6)
+    p = 0.25
+    x = torch.randn(64, 32, k, device="cuda").to(dtype)
+    probs_ref = F.softmax(x.float(), dim=-1)
+    xin = x.clone().requires_grad_(True)
+    out = ops.softmax_dropout(xin, p, True, inplace=False)
+    kept = out != 0
+    frac = kept.float().mean().item()
+    assert abs(frac - (1 - p)) < 0.01, frac
+    # kept values are probs / (1-p)
+    err = ((out.float() - probs_ref / (1 - p)).abs() * kept).max().item()
+    assert err < (2e-3 if dtype != torch.bfloat16 else 1.6e-2)
+    dy = torch.randn_like(out)
+    out.backward(dy)
+    # reference backward with the SAME mask
+    xr = x.float().requires_grad_(True)
+    ref = F.softmax(xr, dim=-1) * kept.float() / (1 - p)
+    ref.backward(dy.float())
+    assert maxdiff(xin.grad, xr.grad) < (2e-3 if dtype != torch.bfloat16 else 1.6e-2)
+
+
+def test_softmax_inplace_contract():
+    ops = _ops()
+    x = torch.randn(8, 16, 256, device="cuda", dtype=torch.half)
+    ref = F.softmax(x.float(), -1)
+    out = ops.softmax_dropout(x, 0.0, False)  # eval: result is the (overwritten) input buffer
+    assert out.data_ptr() == x.data_ptr()
+    assert maxdiff(x, ref) < 1e-3
+    x2 = torch.randn(8, 16, 256, device="cuda", dtype=torch.half)
+    ref2 = F.softmax(x2.float(), -1)
+    out2 = ops.softmax_dropout(x2, 0.5, True)
+    assert maxdiff(x2, ref2) < 1e-3  # input now holds probabilities
+    assert out2.data_ptr() != x2.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused element-wise
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_bias_gelu(dtype):
+    ops = _ops()
+    torch.manual_seed(7)
+    x = torch.randn(300, 3072, device="cuda").to(dtype).requires_grad_(True)
+    b = torch.randn(3072, device="cuda").to(dtype).requires_grad_(True)
+    dy = torch.randn(300, 3072, device="cuda").to(dtype)
+    y = ops.bias_gelu(x, b)
+    y.backward(dy)
+    xr, br = x.detach().float().requires_grad_(True), b.detach().float().requires_grad_(True)
+    yr = F.gelu(xr + br)
+    yr.backward(dy.float())
+    tol = TOL[dtype]
+    assert maxdiff(y, yr) < tol * 8
+    assert maxdiff(x.grad, xr.grad) < tol * 8
+    assert maxdiff(b.grad, br.grad) / br.grad.abs().max().item() < tol * 4
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_bias_dropout_add_layer_norm(dtype, p):
+    ops = _ops()
+    torch.manual_seed(8)
+    rows, dim = 515, 768
+    x = torch.randn(rows, dim, device="cuda").to(dtype).requires_grad_(True)
+    bias = torch.randn(dim, device="cuda").to(dtype).requires_grad_(True)
+    res = torch.randn(rows, dim, device="cuda").to(dtype).requires_grad_(True)
+    w = (torch.randn(dim, device="cuda") * 0.3 + 1).to(dtype).requires_grad_(True)
+    b = torch.randn(dim, device="cuda").to(dtype).requires_grad_(True)
+    dy = torch.randn(rows, dim, device="cuda").to(dtype)
+    y = ops.bias_dropout_add_layer_norm(x, bias, res, w, b, p, 1e-5, True)
+    y.backward(dy)
+    # recover the dropout mask from dx (dx is zero exactly where the element was dropped)
+    if p > 0:
+        keep = (x.grad != 0).float()
+        assert abs(keep.mean().item() - (1 - p)) < 0.01
+    else:
+        keep = torch.ones(rows, dim, device="cuda")
+    xr, biasr, resr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, bias, res, w, b))
+    h = resr + (xr + biasr) * keep / (1 - p)
+    yr = F.layer_norm(h, (dim,), wr, br, 1e-5)
+    yr.backward(dy.float())
+    tol = TOL[dtype]
+    assert maxdiff(y, yr) < tol * 16
+    assert maxdiff(res.grad, resr.grad) < tol * 16
+    assert maxdiff(x.grad, xr.grad) < tol * 16
+    assert maxdiff(w.grad, wr.grad) / wr.grad.abs().max().item() < tol * 4
+    assert maxdiff(bias.grad, biasr.grad) / biasr.grad.abs().max().item() < tol * 4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("vocab", [30522, 1000, 37])
+def test_softmax_cross_entropy(dtype, vocab):
+    ops = _ops()
+    torch.manual_seed(9)
+    n = 301
+    logits = (torch.randn(n, vocab, device="cuda") * 3).to(dtype).requires_grad_(True)
+    target = torch.randint(0, vocab, (n,), device="cuda")
+    target[::7] = 0  # ignored rows
+    loss = ops.softmax_cross_entropy(logits, target, ignore_index=0)
+    (loss * 2.0).backward()
+    lr = logits.detach().float().requires_grad_(True)
+    ref = F.nll_loss(F.log_softmax(lr, dim=-1), target, ignore_index=0, reduction="sum")
+    (ref * 2.0).backward()
+    assert abs(loss.item() - ref.item()) / abs(ref.item()) < 1e-4
+    assert maxdiff(logits.grad, lr.grad) < (1e-5 if dtype == torch.float32 else 4e-3)

@@ -44,11 +44,53 @@ if torch.cuda.is_available() and _C is None and os.environ.get("UNICORE_ALLOW_FA
 USE_NATIVE = HAS_CUDA_EXT and _is_blackwell() and os.environ.get("UNICORE_DISABLE_NATIVE", "0") != "1"
 
 
+# kernels launched per binding call (used for the benchmark's ``gpu_launches`` figure)
+_LAUNCHES_PER_CALL = {
+    "layernorm_bwd": 2, "rmsnorm_bwd": 2, "bias_dropout_add_ln_bwd": 2, "fmha_bwd": 3,
+}
+_launch_count = 0
+
+
+class _CountingProxy:
+    """Forwards attribute access to the extension, counting kernel launches per call."""
+
+    def __init__(self, mod):
+        self._mod = mod
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            target = getattr(self._mod, name)
+            n = _LAUNCHES_PER_CALL.get(name, 1)
+
+            def fn(*args, __target=target, __n=n, **kwargs):
+                global _launch_count
+                _launch_count += __n
+                return __target(*args, **kwargs)
+
+            self._cache[name] = fn
+        return fn
+
+
+_PROXY = _CountingProxy(_C) if _C is not None else None
+
+
+def launch_counter_reset():
+    global _launch_count
+    _launch_count = 0
+    return 0
+
+
+def launch_counter_read():
+    return _launch_count
+
+
 def native():
     """Return the extension module (raises if it is not loaded)."""
     if _C is None:
         raise RuntimeError("unicore_b200._C is not loaded: {!r}".format(_ERR))
-    return _C
+    return _PROXY
 
 
 def use_native(*tensors) -> bool:
