@@ -83,8 +83,8 @@ void launch_rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const 
 void launch_softmax_dropout_fwd(void* x, void* out, const void* mask, const void* bias, long long rows, int K,
                                 long long mask_div, long long bias_rows, float p, unsigned long long seed,
                                 unsigned long long offset, int dtype, cudaStream_t stream);
-// dy: [rows, K] overwritten with dx
-void launch_softmax_dropout_bwd(void* dy, const void* probs, long long rows, int K, float p, unsigned long long seed,
+// dx may alias dy
+void launch_softmax_dropout_bwd(const void* dy, void* dx, const void* probs, long long rows, int K, float p, unsigned long long seed,
                                 unsigned long long offset, int dtype, cudaStream_t stream);
 
 // ---- fused element-wise ---------------------------------------------------------------------------------------

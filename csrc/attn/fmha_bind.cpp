@@ -1,3 +1,135 @@
-// Bindings of the fused attention kernels (filled in by csrc/attn/fmha_sm100.cu milestone).
+// PyTorch bindings of the fused attention kernels.
+#include <ATen/cuda/CUDAContext.h>
+#include <ATen/cuda/CUDAGeneratorImpl.h>
+#include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
-void register_fmha(pybind11::module_& m) { (void)m; }
+
+#include <mutex>
+#include <optional>
+
+#include "fmha_api.h"
+
+namespace {
+using torch::Tensor;
+using OptTensor = std::optional<Tensor>;
+
+std::pair<uint64_t, uint64_t> reserve_philox(uint64_t increment) {
+  auto gen = at::get_generator_or_default<at::CUDAGeneratorImpl>(std::nullopt,
+                                                                 at::cuda::detail::getDefaultCUDAGenerator());
+  std::lock_guard<std::mutex> lock(gen->mutex_);
+  at::PhiloxCudaState st = gen->philox_cuda_state(increment);
+  TORCH_CHECK(!st.captured_, "fmha: RNG under CUDA graph capture is not supported yet");
+  return {st.seed_.val, st.offset_.val};
+}
+
+void fill_common(ub::FmhaFwdParams& p, const Tensor& q, const Tensor& k, const Tensor& v, const OptTensor& bias,
+                 const OptTensor& kpm, double p_drop, double scale) {
+  TORCH_CHECK(q.is_cuda() && k.is_cuda() && v.is_cuda());
+  TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4, "q/k/v must be [B, L, H, D]");
+  TORCH_CHECK(q.size(3) == 64 && k.size(3) == 64 && v.size(3) == 64, "head_dim must be 64");
+  TORCH_CHECK(q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1, "last dim must be contiguous");
+  TORCH_CHECK(q.scalar_type() == at::kHalf || q.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(k.scalar_type() == q.scalar_type() && v.scalar_type() == q.scalar_type());
+  TORCH_CHECK(k.size(0) == q.size(0) && v.size(0) == q.size(0) && k.size(2) == q.size(2) && v.size(2) == q.size(2));
+  TORCH_CHECK(k.size(1) == v.size(1));
+  TORCH_CHECK(q.size(1) % 8 == 0 && k.size(1) % 8 == 0, "sequence lengths must be multiples of 8");
+  for (const Tensor* t : {&q, &k, &v}) {
+    TORCH_CHECK(t->stride(0) % 8 == 0 && t->stride(1) % 8 == 0 && t->stride(2) % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(t->data_ptr()) & 15) == 0,
+                "q/k/v must be 16-byte aligned with strides that are multiples of 8 elements");
+  }
+  p.q = q.data_ptr();
+  p.k = k.data_ptr();
+  p.v = v.data_ptr();
+  p.q_sb = q.stride(0); p.q_sl = q.stride(1); p.q_sh = q.stride(2);
+  p.k_sb = k.stride(0); p.k_sl = k.stride(1); p.k_sh = k.stride(2);
+  p.v_sb = v.stride(0); p.v_sl = v.stride(1); p.v_sh = v.stride(2);
+  p.B = (int)q.size(0);
+  p.Lq = (int)q.size(1);
+  p.H = (int)q.size(2);
+  p.Lk = (int)k.size(1);
+  p.is_bf16 = q.scalar_type() == at::kBFloat16 ? 1 : 0;
+  p.bias = nullptr;
+  p.bias_batch = 1;
+  p.bias_is_f32 = 0;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->is_cuda() && bias->is_contiguous() && bias->dim() == 4);
+    TORCH_CHECK((bias->size(0) == 1 || bias->size(0) == p.B) && bias->size(1) == p.H && bias->size(2) == p.Lq &&
+                bias->size(3) == p.Lk, "bias must be [1|B, H, Lq, Lk]");
+    TORCH_CHECK(bias->scalar_type() == at::kFloat || bias->scalar_type() == q.scalar_type());
+    p.bias = bias->data_ptr();
+    p.bias_batch = (int)bias->size(0);
+    p.bias_is_f32 = bias->scalar_type() == at::kFloat ? 1 : 0;
+  }
+  p.kpm = nullptr;
+  if (kpm.has_value() && kpm->defined()) {
+    TORCH_CHECK(kpm->is_cuda() && kpm->is_contiguous() && kpm->scalar_type() == at::kBool && kpm->dim() == 2 &&
+                kpm->size(0) == p.B && kpm->size(1) == p.Lk, "key_padding_mask must be bool [B, Lk]");
+    p.kpm = reinterpret_cast<const uint8_t*>(kpm->data_ptr());
+  }
+  p.p_drop = (float)p_drop;
+  p.scale = (float)scale;
+}
+
+std::tuple<Tensor, Tensor, int64_t, int64_t> fmha_fwd(const Tensor& q, const Tensor& k, const Tensor& v,
+                                                      const OptTensor& bias, const OptTensor& kpm, double p_drop,
+                                                      double scale) {
+  const c10::cuda::CUDAGuard guard(q.device());
+  ub::FmhaFwdParams p{};
+  fill_common(p, q, k, v, bias, kpm, p_drop, scale);
+  Tensor out = torch::empty({p.B, p.Lq, p.H, 64}, q.options());
+  Tensor lse = torch::empty({p.B, p.H, p.Lq}, q.options().dtype(at::kFloat));
+  p.out = out.data_ptr();
+  p.lse = lse.data_ptr<float>();
+  p.seed = p.offset = 0;
+  if (p_drop > 0.0) {
+    auto so = reserve_philox(4);
+    p.seed = so.first;
+    p.offset = so.second;
+  }
+  ub::launch_fmha_fwd(p, at::cuda::getCurrentCUDAStream().stream());
+  cudaError_t err = cudaGetLastError();
+  TORCH_CHECK(err == cudaSuccess, "fmha_fwd launch failed: ", cudaGetErrorString(err));
+  return {out, lse, (int64_t)p.seed, (int64_t)p.offset};
+}
+
+std::tuple<Tensor, Tensor, Tensor, OptTensor> fmha_bwd(const Tensor& dout, const Tensor& q, const Tensor& k,
+                                                       const Tensor& v, const Tensor& out, const Tensor& lse,
+                                                       const OptTensor& bias, const OptTensor& kpm, double p_drop,
+                                                       double scale, int64_t seed, int64_t offset, bool need_dbias) {
+  const c10::cuda::CUDAGuard guard(q.device());
+  ub::FmhaBwdParams p{};
+  fill_common(p.f, q, k, v, bias, kpm, p_drop, scale);
+  TORCH_CHECK(dout.is_contiguous() && out.is_contiguous() && lse.is_contiguous());
+  p.f.out = out.data_ptr();
+  p.f.lse = lse.data_ptr<float>();
+  p.f.seed = (uint64_t)seed;
+  p.f.offset = (uint64_t)offset;
+  p.dout = dout.data_ptr();
+  Tensor delta = torch::empty({p.f.B, p.f.H, p.f.Lq}, q.options().dtype(at::kFloat));
+  Tensor dq_acc = torch::zeros({p.f.B, p.f.Lq, p.f.H, 64}, q.options().dtype(at::kFloat));
+  Tensor dq = torch::empty({p.f.B, p.f.Lq, p.f.H, 64}, q.options());
+  Tensor dk = torch::empty({p.f.B, p.f.Lk, p.f.H, 64}, q.options());
+  Tensor dv = torch::empty({p.f.B, p.f.Lk, p.f.H, 64}, q.options());
+  OptTensor dbias;
+  p.dbias = nullptr;
+  if (need_dbias && p.f.bias != nullptr) {
+    dbias = torch::zeros({p.f.bias_batch, p.f.H, p.f.Lq, p.f.Lk}, q.options().dtype(at::kFloat));
+    p.dbias = dbias->data_ptr<float>();
+  }
+  p.delta = delta.data_ptr<float>();
+  p.dq_acc = dq_acc.data_ptr<float>();
+  p.dq = dq.data_ptr();
+  p.dk = dk.data_ptr();
+  p.dv = dv.data_ptr();
+  ub::launch_fmha_bwd(p, at::cuda::getCurrentCUDAStream().stream());
+  cudaError_t err = cudaGetLastError();
+  TORCH_CHECK(err == cudaSuccess, "fmha_bwd launch failed: ", cudaGetErrorString(err));
+  return {dq, dk, dv, dbias};
+}
+}  // namespace
+
+void register_fmha(pybind11::module_& m) {
+  m.def("fmha_fwd", &fmha_fwd);
+  m.def("fmha_bwd", &fmha_bwd);
+}

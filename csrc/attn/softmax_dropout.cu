@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
 
 template <typename T, int VPT>
 __global__ void __launch_bounds__(kSmThreads) softmax_dropout_bwd_kernel(
-    T* __restrict__ dy, const T* __restrict__ probs, SmGeom g, float p, float keep_scale, unsigned long long seed,
+    const T* dy, T* dx, const T* __restrict__ probs, SmGeom g, float p, float keep_scale, unsigned long long seed,
     unsigned long long offset) {
   constexpr int EPV = VecTraits<T>::kElems;
   __shared__ float scratch[8];
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_bwd_kernel(
           float o[EPV];
 #pragma unroll
           for (int e = 0; e < EPV; ++e) o[e] = d[k][e] - y[k][e] * dot;
-          st_global_v4(dy + row * g.K + (long long)vi * EPV, pack<T>(o));
+          st_global_v4(dx + row * g.K + (long long)vi * EPV, pack<T>(o));
         }
       }
     }
@@ -221,7 +221,7 @@ __global__ void softmax_dropout_fwd_scalar(T* x, T* out, const T* mask, const T*
 }
 
 template <typename T>
-__global__ void softmax_dropout_bwd_scalar(T* dy, const T* probs, SmGeom g, float p, float keep_scale,
+__global__ void softmax_dropout_bwd_scalar(const T* dy, T* dx, const T* probs, SmGeom g, float p, float keep_scale,
                                            unsigned long long seed, unsigned long long offset) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -247,7 +247,7 @@ __global__ void softmax_dropout_bwd_scalar(T* dy, const T* probs, SmGeom g, floa
         d = ((keep >> (idx & 7)) & 1u) ? d * keep_scale : 0.f;
       }
       const float y = to_f32<T>(probs[idx]);
-      dy[idx] = from_f32<T>((d - dot) * y);
+      dx[idx] = from_f32<T>((d - dot) * y);
     }
   }
 }
@@ -322,12 +322,12 @@ static void run_sm_fwd(void* x, void* out, const void* mask, const void* bias, l
 }
 
 template <typename T>
-static void run_sm_bwd(void* dy, const void* probs, long long rows, int K, float p, unsigned long long seed,
+static void run_sm_bwd(const void* dy, void* dx, const void* probs, long long rows, int K, float p, unsigned long long seed,
                        unsigned long long offset, cudaStream_t stream) {
   SmGeom g;
   int vpt = 0;
   const bool vec = make_sm_geom(g, rows, K, VecTraits<T>::kElems, vpt) &&
-                   ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(probs)) & 15) == 0;
+                   ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(probs)) & 15) == 0;
   g.mask_div = 1;
   g.bias_rows = 1;
   const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
@@ -336,13 +336,13 @@ static void run_sm_bwd(void* dy, const void* probs, long long rows, int K, float
     long long need = (rows + rows_per_cta - 1) / rows_per_cta;
     const long long cap = (long long)sm_count2() * 8;
     const int grid = (int)(need < cap ? need : cap);
-    UB_SM_VPT(vpt, (softmax_dropout_bwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>((T*)dy, (const T*)probs, g, p,
+    UB_SM_VPT(vpt, (softmax_dropout_bwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>((const T*)dy, (T*)dx, (const T*)probs, g, p,
                                                                                          keep_scale, seed, offset)));
   } else {
     long long need = (rows + 7) / 8;
     const long long cap = (long long)sm_count2() * 8;
     const int grid = (int)(need < cap ? need : cap);
-    softmax_dropout_bwd_scalar<T><<<grid, 256, 0, stream>>>((T*)dy, (const T*)probs, g, p, keep_scale, seed, offset);
+    softmax_dropout_bwd_scalar<T><<<grid, 256, 0, stream>>>((const T*)dy, (T*)dx, (const T*)probs, g, p, keep_scale, seed, offset);
   }
 }
 
@@ -355,12 +355,12 @@ void launch_softmax_dropout_fwd(void* x, void* out, const void* mask, const void
   else run_sm_fwd<__nv_bfloat16>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, stream);
 }
 
-void launch_softmax_dropout_bwd(void* dy, const void* probs, long long rows, int K, float p, unsigned long long seed,
+void launch_softmax_dropout_bwd(const void* dy, void* dx, const void* probs, long long rows, int K, float p, unsigned long long seed,
                                 unsigned long long offset, int dtype, cudaStream_t stream) {
   if (rows <= 0 || K <= 0) return;
-  if (dtype == kF32) run_sm_bwd<float>(dy, probs, rows, K, p, seed, offset, stream);
-  else if (dtype == kF16) run_sm_bwd<__half>(dy, probs, rows, K, p, seed, offset, stream);
-  else run_sm_bwd<__nv_bfloat16>(dy, probs, rows, K, p, seed, offset, stream);
+  if (dtype == kF32) run_sm_bwd<float>(dy, dx, probs, rows, K, p, seed, offset, stream);
+  else if (dtype == kF16) run_sm_bwd<__half>(dy, dx, probs, rows, K, p, seed, offset, stream);
+  else run_sm_bwd<__nv_bfloat16>(dy, dx, probs, rows, K, p, seed, offset, stream);
 }
 
 }  // namespace ub

@@ -1,0 +1,135 @@
+// Thin inline-PTX wrappers for the Blackwell (sm_100a) tensor-core path used by the fused attention
+// kernels: tensor-memory allocation, tcgen05.mma (kind::f16, cta_group::1), tcgen05.commit ->
+// mbarrier, tcgen05.ld/st (32x32b: one TMEM lane == one thread), fences and UMMA descriptors.
+//
+// Shared-memory operand layout used throughout (SWIZZLE_NONE "interleaved" canonical layout):
+// a tile of R rows x C 16-bit columns is stored as 8x8 core matrices of 128 contiguous bytes
+// (8 rows x 16 bytes).  The same bytes can be presented to the tensor core either as a K-major
+// operand (rows = M/N, columns = K) or as an MN-major operand (rows = K, columns = M/N) by swapping
+// the leading/stride byte offsets of the descriptor - no transposes are ever materialised.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ub {
+namespace tc {
+
+#define TC_DEVICE __device__ __forceinline__
+
+TC_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- tensor memory -------------------------------------------------------------------------------
+TC_DEVICE void tmem_alloc(uint32_t dst_smem_addr, uint32_t ncols) {  // whole warp, ncols = pow2 >= 32
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem_addr), "r"(ncols)
+               : "memory");
+}
+TC_DEVICE void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+TC_DEVICE void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp (the allocating one)
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- fences -----------------------------------------------------------------------------------------
+TC_DEVICE void fence_before_thread_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+TC_DEVICE void fence_after_thread_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// make generic-proxy st.shared visible to the async proxy (tensor core operand reads)
+TC_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+TC_DEVICE void fence_mbarrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------------
+TC_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+TC_DEVICE bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Spin with a wall-clock bound: a lost arrive must abort the kernel (trap) instead of hanging the GPU.
+TC_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      __trap();
+    }
+  }
+}
+// all previously issued tcgen05.mma of this thread arrive on `bar` when complete
+TC_DEVICE void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ---- descriptors ------------------------------------------------------------------------------------
+// 64-bit shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (Blackwell).
+// K-major operand : lbo = bytes between core matrices adjacent along K, sbo = bytes between
+//                   8-row groups along M/N.
+// MN-major operand: lbo = bytes between 8-deep groups along K, sbo = bytes between 8-element groups
+//                   along M/N.
+TC_DEVICE uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version
+  return d;
+}
+
+// 32-bit instruction descriptor for kind::f16: D fp32, A/B fp16 (fmt 0) or bf16 (fmt 1).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int ab_fmt, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)ab_fmt << 7) | ((uint32_t)ab_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; one thread issues on behalf of the CTA.
+TC_DEVICE void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+
+// ---- TMEM <-> registers (32x32b: thread i of the warp <-> lane base+i; N consecutive columns) ------------------
+TC_DEVICE void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+TC_DEVICE void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+TC_DEVICE void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+TC_DEVICE void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// byte offset of the 16-byte chunk (row, chunk) inside a [rows x 64 halfs] tile: 8x8 core matrices,
+// [row/8][chunk][row%8] order => 1024 bytes per 8-row group.
+TC_DEVICE uint32_t tile64_off(int row, int chunk) { return (uint32_t)((row >> 3) * 1024 + chunk * 128 + (row & 7) * 16); }
+// same for a [rows x 128 halfs] tile (16 chunks per row) => 2048 bytes per 8-row group.
+TC_DEVICE uint32_t tile128_off(int row, int chunk) { return (uint32_t)((row >> 3) * 2048 + chunk * 128 + (row & 7) * 16); }
+
+}  // namespace tc
+}  // namespace ub

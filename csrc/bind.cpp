@@ -310,10 +310,13 @@ Tensor softmax_dropout_bwd(Tensor dy, const Tensor& probs, double p, int64_t see
   check_cuda_contig(probs, "softmax_results");
   TORCH_CHECK(dy.dim() == 3 && dy.sizes() == probs.sizes() && dy.scalar_type() == probs.scalar_type());
   const c10::cuda::CUDAGuard guard(dy.device());
-  ub::launch_softmax_dropout_bwd(dy.data_ptr(), probs.data_ptr(), dy.size(0) * dy.size(1), (int)dy.size(2), (float)p,
-                                 (uint64_t)seed, (uint64_t)offset, dtype_tag(dy), cur_stream());
+  // out of place: autograd may hand the same grad tensor to several consumers
+  Tensor dx = torch::empty_like(dy);
+  ub::launch_softmax_dropout_bwd(dy.data_ptr(), dx.data_ptr(), probs.data_ptr(), dy.size(0) * dy.size(1),
+                                 (int)dy.size(2), (float)p, (uint64_t)seed, (uint64_t)offset, dtype_tag(dy),
+                                 cur_stream());
   check_launch("softmax_dropout_bwd");
-  return dy;
+  return dx;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -80,7 +80,7 @@ def test_fused_adam(gdtype, n):
                  bias_correction=True, weight_decay=0.01)]
     ops.fused_adam(work, grad_scale=torch.tensor(8.0, device="cuda"), zero_grad=True)
     assert maxdiff(p, rp) < 1e-5 and maxdiff(m, rm) < 1e-5 and maxdiff(v, rv) < 1e-4
-    assert maxdiff(half, rp) < 1e-2
+    assert maxdiff(half, rp) <= rp.abs().max().item() * 2 ** -7  # one 16-bit rounding of the fp32 result
     assert g.abs().max().item() == 0.0
 
 

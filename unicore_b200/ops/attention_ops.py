@@ -61,8 +61,13 @@ class _FusedAttentionFn(torch.autograd.Function):
 
 
 def fused_attention_supported(q, k, v, bias=None, key_padding_mask=None) -> bool:
-    if not use_native(q, k, v, bias, key_padding_mask):
+    if not use_native(q, k, v, bias, key_padding_mask) or not hasattr(native(), "fmha_fwd"):
         return False
+    if key_padding_mask is not None and key_padding_mask.dtype != torch.bool:
+        return False
+    for t in (q, k, v):
+        if t.data_ptr() % 16 != 0 or any(s % 8 != 0 for s in t.stride()[:3]):
+            return False
     if q.dtype not in (torch.float16, torch.bfloat16) or k.dtype != q.dtype or v.dtype != q.dtype:
         return False
     if q.dim() != 4 or q.shape[-1] != 64 or k.shape[-1] != 64:

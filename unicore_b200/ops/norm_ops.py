@@ -49,13 +49,12 @@ class _RMSNormFn(torch.autograd.Function):
 
 
 def _norm_supported(x: torch.Tensor, weight: Optional[torch.Tensor]) -> bool:
-    return (
-        weight is not None
-        and x.dtype in (torch.float16, torch.bfloat16, torch.float32)
-        and x.numel() > 0
-        and x.shape[-1] == weight.numel()
-        and x.shape[-1] <= 16384
-    )
+    if weight is None or x.dtype not in (torch.float16, torch.bfloat16, torch.float32) or x.numel() == 0:
+        return False
+    cols = x.shape[-1]
+    epv = 16 // x.element_size()  # elements per 128-bit vector
+    # a row is held in registers by <= 256 threads x 4 vectors
+    return cols == weight.numel() and cols % epv == 0 and cols // epv <= 1024
 
 
 def layer_norm(x, normalized_shape, weight, bias, eps=1e-5):
