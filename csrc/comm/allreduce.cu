@@ -1,0 +1,202 @@
+// Gradient all-reduce over NVLink 5 / NVSwitch peer memory (sm_100a), replacing the NCCL all-reduce
+// issued by DDP in the reference (unicore/models/distributed_unicore_model.py:37-46) on the
+// gradient path.  The flat 16-bit gradient arena lives in symmetric memory (every rank maps every
+// peer's buffer + an NVLS multicast alias), so the kernels below read/write peers with plain
+// ld/st.global or multimem.* and synchronise with flags in a symmetric signal buffer:
+//
+//   one-shot : every rank reads the range from all peers and reduces locally (latency optimal,
+//              used for small ranges / statistics vectors)
+//   two-shot : rank r reduces its 1/N slice from all peers (reduce-scatter by peer loads) and
+//              writes the result into every peer (all-gather by peer stores)
+//   nvls     : rank r issues multimem.ld_reduce on its slice (reduction inside the NVSwitch, fp32
+//              accumulate) and multimem.st to broadcast it - each byte crosses each link once
+//
+// Reduction order is the fixed rank order 0..N-1 with fp32 accumulation, so every replica ends up
+// with bit-identical gradients.  An optional scale (1/world) is applied before the 16-bit store.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "../common.cuh"
+#include "comm_api.h"
+
+namespace ub {
+
+constexpr int kCommThreads = 512;
+
+// ---- cross-GPU flag barrier (CAS put / CAS take: self-resetting, safe for back-to-back use) -----------------
+UB_DEVICE void flag_put(uint32_t* addr) {
+  while (atomicCAS_system(addr, 0u, 1u) != 0u) {
+  }
+}
+UB_DEVICE void flag_take(uint32_t* addr) {
+  const long long t0 = clock64();
+  while (atomicCAS_system(addr, 1u, 0u) != 1u) {
+    if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a peer died; do not hang the GPU forever
+  }
+}
+
+// All ranks' CTA `blockIdx.x` meet. Slot layout in every rank's flag buffer: [block][sender rank].
+UB_DEVICE void block_barrier(const CommPeers& peers, bool release_first) {
+  if (release_first) __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < (unsigned)peers.world) {
+    const int t = threadIdx.x;
+    uint32_t* remote = reinterpret_cast<uint32_t*>(peers.flags[t]) + blockIdx.x * peers.world + peers.rank;
+    uint32_t* mine = reinterpret_cast<uint32_t*>(peers.flags[peers.rank]) + blockIdx.x * peers.world + t;
+    flag_put(remote);
+    flag_take(mine);
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
+template <typename T>
+UB_DEVICE void acc_add(float (&acc)[16 / sizeof(T)], const Vec16& v) {
+  float t[16 / sizeof(T)];
+  unpack<T>(v, t);
+#pragma unroll
+  for (int e = 0; e < (int)(16 / sizeof(T)); ++e) acc[e] += t[e];
+}
+
+// ---- one-shot / two-shot ------------------------------------------------------------------------------------------
+// Range = [begin_vec, end_vec) in 16-byte vectors relative to each buffer base.
+template <typename T, bool kTwoShot>
+__global__ void __launch_bounds__(kCommThreads) allreduce_p2p_kernel(CommPeers peers, long long begin_vec,
+                                                                       long long end_vec, float scale) {
+  constexpr int EPV = 16 / sizeof(T);
+  block_barrier(peers, /*release_first=*/false);  // every rank's producer kernels have finished
+
+  long long lo = begin_vec, hi = end_vec;
+  if (kTwoShot) {
+    const long long n = end_vec - begin_vec;
+    const long long per = (n + peers.world - 1) / peers.world;
+    lo = begin_vec + per * peers.rank;
+    hi = lo + per < end_vec ? lo + per : end_vec;
+    if (lo > end_vec) lo = end_vec;
+  }
+  const long long stride = (long long)gridDim.x * kCommThreads;
+  for (long long v = lo + (long long)blockIdx.x * kCommThreads + threadIdx.x; v < hi; v += stride) {
+    Vec16 in[kMaxPeers];
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) {
+      if (p < peers.world) in[p] = ld_global_v4(reinterpret_cast<const uint8_t*>(peers.buf[p]) + v * 16);
+    }
+    float acc[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) {
+      if (p < peers.world) acc_add<T>(acc, in[p]);
+    }
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) acc[e] *= scale;
+    const Vec16 out = pack<T>(acc);
+    if (kTwoShot) {
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p) {
+        if (p < peers.world) st_global_v4(reinterpret_cast<uint8_t*>(peers.buf[p]) + v * 16, out);
+      }
+    } else {
+      st_global_v4(reinterpret_cast<uint8_t*>(peers.buf[peers.rank]) + v * 16, out);
+    }
+  }
+  // two-shot: my stores must be visible at the peers; one-shot: nobody may overwrite its buffer
+  // (next backward) while a peer is still reading it
+  block_barrier(peers, /*release_first=*/true);
+}
+
+// ---- NVLS (multimem) --------------------------------------------------------------------------------------------------
+template <typename T>
+UB_DEVICE Vec16 multimem_ld_reduce(const void* mc_addr);
+template <>
+UB_DEVICE Vec16 multimem_ld_reduce<__half>(const void* a) {
+  Vec16 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3])
+               : "l"(a)
+               : "memory");
+  return v;
+}
+template <>
+UB_DEVICE Vec16 multimem_ld_reduce<__nv_bfloat16>(const void* a) {
+  Vec16 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3])
+               : "l"(a)
+               : "memory");
+  return v;
+}
+template <>
+UB_DEVICE Vec16 multimem_ld_reduce<float>(const void* a) {
+  Vec16 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3])
+               : "l"(a)
+               : "memory");
+  return v;
+}
+UB_DEVICE void multimem_st(void* mc_addr, const Vec16& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_addr), "r"(v.w[0]), "r"(v.w[1]),
+               "r"(v.w[2]), "r"(v.w[3])
+               : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCommThreads) allreduce_nvls_kernel(CommPeers peers, long long begin_vec,
+                                                                        long long end_vec, float scale) {
+  constexpr int EPV = 16 / sizeof(T);
+  block_barrier(peers, false);
+  const long long n = end_vec - begin_vec;
+  const long long per = (n + peers.world - 1) / peers.world;
+  long long lo = begin_vec + per * peers.rank;
+  long long hi = lo + per < end_vec ? lo + per : end_vec;
+  if (lo > end_vec) lo = end_vec;
+  uint8_t* mc = reinterpret_cast<uint8_t*>(peers.multicast);
+  const long long stride = (long long)gridDim.x * kCommThreads;
+  for (long long v = lo + (long long)blockIdx.x * kCommThreads + threadIdx.x; v < hi; v += stride) {
+    Vec16 r = multimem_ld_reduce<T>(mc + v * 16);
+    if (scale != 1.f) {
+      float acc[EPV];
+      unpack<T>(r, acc);
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) acc[e] *= scale;
+      r = pack<T>(acc);
+    }
+    multimem_st(mc + v * 16, r);
+  }
+  block_barrier(peers, true);
+}
+
+// ---- host --------------------------------------------------------------------------------------------------------------
+template <typename T>
+static void run_allreduce(const CommPeers& peers, long long begin_vec, long long end_vec, float scale, int algo,
+                          int blocks, cudaStream_t stream) {
+  if (algo == kAlgoNvls) {
+    allreduce_nvls_kernel<T><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
+  } else if (algo == kAlgoTwoShot) {
+    allreduce_p2p_kernel<T, true><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
+  } else {
+    allreduce_p2p_kernel<T, false><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
+  }
+}
+
+int pick_allreduce_algo(long long bytes, int world, bool has_multicast) {
+  if (bytes <= 256 * 1024) return kAlgoOneShot;
+  if (has_multicast && world > 2) return kAlgoNvls;
+  return kAlgoTwoShot;
+}
+
+void launch_allreduce(const CommPeers& peers, long long byte_offset, long long bytes, int dtype, float scale, int algo,
+                      int blocks, cudaStream_t stream) {
+  const long long begin_vec = byte_offset / 16, end_vec = (byte_offset + bytes) / 16;
+  if (end_vec <= begin_vec) return;
+  if (algo == kAlgoAuto) algo = pick_allreduce_algo(bytes, peers.world, peers.multicast != nullptr);
+  if (algo == kAlgoNvls && peers.multicast == nullptr) algo = kAlgoTwoShot;
+  if (blocks <= 0) blocks = (algo == kAlgoOneShot && bytes <= 64 * 1024) ? 4 : 32;
+  if (blocks > kMaxCommBlocks) blocks = kMaxCommBlocks;
+  if (dtype == kF32) run_allreduce<float>(peers, begin_vec, end_vec, scale, algo, blocks, stream);
+  else if (dtype == kF16) run_allreduce<__half>(peers, begin_vec, end_vec, scale, algo, blocks, stream);
+  else run_allreduce<__nv_bfloat16>(peers, begin_vec, end_vec, scale, algo, blocks, stream);
+}
+
+}  // namespace ub

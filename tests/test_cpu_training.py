@@ -1,0 +1,140 @@
+"""End-to-end CPU tests: CLI training, checkpoint schema + resume, fp16/bf16 optimizer semantics,
+and 2-process gloo data parallelism (c10d and legacy engines, object collectives)."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PY = sys.executable
+
+COMMON = [
+    "--user-dir", os.path.join(ROOT, "examples", "bert"), "--task", "synthetic_mlm", "--loss", "masked_lm",
+    "--arch", "bert_base", "--encoder-layers", "2", "--encoder-embed-dim", "32", "--encoder-ffn-embed-dim", "64",
+    "--encoder-attention-heads", "4", "--synthetic-vocab-size", "120", "--synthetic-seq-len", "16",
+    "--synthetic-num-samples", "64", "--max-seq-len", "32", "--optimizer", "adam", "--adam-betas", "(0.9, 0.98)",
+    "--clip-norm", "1.0", "--lr-scheduler", "polynomial_decay", "--lr", "1e-3", "--warmup-updates", "2",
+    "--total-num-update", "40", "--batch-size", "8", "--log-format", "simple", "--log-interval", "1",
+    "--num-workers", "0", "--cpu", "--weight-decay", "0.01", "--seed", "3",
+]
+
+
+def run_cli(extra, nproc=1, timeout=600):
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="1")
+    script = os.path.join(ROOT, "unicore_cli", "train.py")
+    if nproc == 1:
+        cmd = [PY, script] + COMMON + ["--distributed-world-size", "1"] + extra
+    else:
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        cmd = [PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
+               "127.0.0.1", "--master-port", str(port), script] + COMMON + ["--distributed-backend", "gloo"] + extra
+    out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    assert out.returncode == 0, out.stdout[-4000:]
+    return out.stdout
+
+
+def losses_of(log):
+    vals = []
+    for line in log.splitlines():
+        if "train_inner" in line and "loss=" in line:
+            vals.append(float(line.split("loss=")[1].split(",")[0]))
+    return vals
+
+
+def test_train_checkpoint_schema_and_resume(tmp_path):
+    save = str(tmp_path / "ck")
+    base = ["--save-dir", save, "--tmp-save-dir", save, "--ema-decay", "0.99", "--update-freq", "2",
+            "--validate-interval-updates", "4", "--save-interval-updates", "4", "--synthetic-num-samples", "128"]
+    log_a = run_cli(base + ["--max-update", "4"])
+    assert len(losses_of(log_a)) == 4
+    ck = torch.load(os.path.join(save, "checkpoint_last.pt"), map_location="cpu", weights_only=False)
+    assert set(ck) == {"args", "model", "loss", "optimizer_history", "task_state", "extra_state",
+                       "last_optimizer_state", "ema"}
+    hist = ck["optimizer_history"][-1]
+    assert hist["loss_name"] == "MaskedLMLoss" and hist["optimizer_name"] == "UnicoreAdam" and hist["num_updates"] == 4
+    it = ck["extra_state"]["train_iterator"]
+    assert it["epoch"] == 1 and it["iterations_in_epoch"] == 8 and it["shuffle"] is True  # counts micro-batches
+    assert set(ck["ema"]) == {"params", "decay"} and all(v.dtype == torch.float32 for v in ck["model"].values())
+    assert os.path.exists(os.path.join(save, "checkpoint_1_4.pt")) and os.path.exists(os.path.join(save, "checkpoint_best.pt"))
+    # resume: continues from update 4 with the saved iterator position
+    log_b = run_cli(base + ["--max-update", "6"])
+    assert "Loaded checkpoint" in log_b and "@ 4 updates" in log_b
+    resumed = losses_of(log_b)
+    # uninterrupted run for comparison (fp32 on CPU is deterministic)
+    save2 = str(tmp_path / "ck2")
+    log_c = run_cli(["--save-dir", save2, "--tmp-save-dir", save2, "--ema-decay", "0.99", "--update-freq", "2",
+                     "--disable-validation", "--no-save", "--max-update", "6", "--synthetic-num-samples", "128"])
+    straight = losses_of(log_c)
+    assert len(resumed) == 2 and resumed == pytest.approx(straight[4:6], abs=2e-3)
+
+
+@pytest.mark.parametrize("precision", [["--fp16", "--fp16-init-scale", "4"], ["--bf16"], ["--bf16", "--bf16-sr"]])
+def test_mixed_precision_checkpoint_layout(tmp_path, precision):
+    save = str(tmp_path / "ck")
+    log = run_cli(["--save-dir", save, "--tmp-save-dir", save, "--disable-validation", "--max-update", "3"] + precision)
+    assert len(losses_of(log)) == 3
+    ck = torch.load(os.path.join(save, "checkpoint_last.pt"), map_location="cpu", weights_only=False)
+    assert ck["optimizer_history"][-1]["optimizer_name"] == "FP16Optimizer"
+    opt = ck["last_optimizer_state"]
+    # one flat fp32 state vector per weight-decay group (decay, no-decay)
+    assert sorted(opt["state"].keys()) == [0, 1] and len(opt["param_groups"]) == 2
+    assert opt["param_groups"][1]["weight_decay"] == 0.0 and opt["param_groups"][0]["weight_decay"] == 0.01
+    n_model = sum(v.numel() for k, v in ck["model"].items() if k != "lm_head.weight")
+    flat = sum(opt["state"][i]["exp_avg"].numel() for i in (0, 1))
+    assert flat >= n_model and flat - n_model < 200  # = sum of per-tensor pad-to-2
+    assert ("loss_scale" in opt) == ("--fp16" in precision)
+
+
+@pytest.mark.parametrize("backend", ["c10d", "no_c10d"])
+def test_two_rank_gloo_matches_single_process(tmp_path, backend):
+    """2 ranks x batch 8 == 1 rank x batch 8 x update-freq 2 is NOT generally true (different
+    shuffles), so compare the invariant instead: both ranks log identical global stats, training
+    runs, and the global batch size is the sum over ranks."""
+    log = run_cli(["--ddp-backend", backend, "--disable-validation", "--no-save", "--max-update", "4", "--bf16"], nproc=2)
+    assert "training on 2 devices" in log
+    lines = [l for l in log.splitlines() if "train_inner" in l]
+    assert len(lines) == 4 and all("bsz=16" in l for l in lines)
+    assert all(v == v for v in losses_of(log))
+
+
+def _object_collectives_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    from unicore.distributed import utils as du
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    got = du.all_gather_list({"rank": rank, "t": torch.ones(2) * rank}, max_size=4096)
+    assert [g["rank"] for g in got] == list(range(world)) and got[1]["t"].sum() == 2
+    red = du.all_reduce_dict({"a": 1.5, "b": torch.tensor([1.0, 2.0])}, device=torch.device("cpu"))
+    assert float(red["a"]) == 1.5 * world and red["b"].tolist() == [world * 1.0, world * 2.0]
+    obj = {"w": torch.arange(6).float().view(2, 3), "h": torch.ones(3, dtype=torch.half), "n": 3, "s": "x"} if rank == 0 else None
+    obj = du.broadcast_object(obj, src_rank=0)
+    assert obj["n"] == 3 and obj["w"].shape == (2, 3) and obj["h"].dtype == torch.half and obj["w"][1, 2] == 5
+    # legacy engine: averaged grads are identical on all ranks
+    from unicore.distributed import LegacyDistributedDataParallel
+
+    torch.manual_seed(0)
+    model = LegacyDistributedDataParallel(torch.nn.Linear(4, 3), None)
+    model(torch.full((2, 4), float(rank + 1))).sum().backward()
+    model.all_reduce_grads()
+    g = model.module.weight.grad.clone()
+    gathered = du.all_gather_list(g)
+    assert torch.equal(gathered[0], gathered[1]) and torch.allclose(g, torch.full_like(g, 3.0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_object_collectives_and_legacy_ddp_gloo():
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_object_collectives_worker, args=(2, port), nprocs=2, join=True)

@@ -253,6 +253,10 @@ class LRUCacheDataset(BaseWrapperDataset):
         super().__init__(dataset)
         self._memo = _Memo()
 
+    def set_epoch(self, epoch):
+        super().set_epoch(epoch)
+        self._memo.store.clear()  # items may be epoch dependent (e.g. masking noise)
+
     def __getitem__(self, index):
         return self._memo.get(index, lambda i: self.dataset[i])
 

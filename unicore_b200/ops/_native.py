@@ -93,6 +93,22 @@ def native():
     return _PROXY
 
 
+def aligned_param(t, dtype=None):
+    """Return ``t`` (cast to ``dtype``) as a 16-byte aligned, contiguous tensor.
+
+    Parameters are views into flat arenas whose per-tensor padding is 2 elements (checkpoint layout
+    contract), so a small 1-D parameter can start at a 4-byte boundary; the vectorised kernels need
+    16-byte alignment.  The (differentiable) copy only happens for such misaligned vectors.
+    """
+    if t is None:
+        return None
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if not t.is_contiguous() or t.data_ptr() % 16 != 0:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
 def use_native(*tensors) -> bool:
     """True when the native kernels should handle these tensors."""
     if not USE_NATIVE:

@@ -19,7 +19,7 @@ from typing import Optional
 import torch
 import torch.nn.functional as F
 
-from ._native import native, use_native
+from ._native import aligned_param, native, use_native
 
 
 # ------------------------------------------------------------------------------------------------
@@ -41,7 +41,7 @@ class _BiasGeluFn(torch.autograd.Function):
 
 def bias_gelu(x: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     if use_native(x, bias) and x.dtype in (torch.float16, torch.bfloat16) and x.is_contiguous() and x.shape[-1] % 8 == 0:
-        return _BiasGeluFn.apply(x, bias)
+        return _BiasGeluFn.apply(x, aligned_param(bias, x.dtype))
     return F.gelu(x + bias if bias is not None else x)
 
 
@@ -84,9 +84,9 @@ def bias_dropout_add_layer_norm(x, bias, residual, ln_weight, ln_bias, p, eps, t
         and ln_weight is not None and ln_bias is not None
         and hasattr(native(), "bias_dropout_add_ln_fwd")
     ):
-        w = ln_weight if ln_weight.dtype == x.dtype else ln_weight.to(x.dtype)
-        b = ln_bias if ln_bias.dtype == x.dtype else ln_bias.to(x.dtype)
-        bb = bias if bias is None or bias.dtype == x.dtype else bias.to(x.dtype)
+        w = aligned_param(ln_weight, x.dtype)
+        b = aligned_param(ln_bias, x.dtype)
+        bb = aligned_param(bias, x.dtype)
         return _BiasDropoutAddLNFn.apply(x, bb, residual, w, b, p, eps, training)
     from .norm_ops import layer_norm
 

@@ -10,7 +10,7 @@ from typing import Optional
 import torch
 import torch.nn.functional as F
 
-from ._native import native, use_native
+from ._native import aligned_param, native, use_native
 
 
 class _LayerNormFn(torch.autograd.Function):
@@ -60,8 +60,8 @@ def _norm_supported(x: torch.Tensor, weight: Optional[torch.Tensor]) -> bool:
 def layer_norm(x, normalized_shape, weight, bias, eps=1e-5):
     """LayerNorm over the last dimension (biased variance, ``rsqrt(var + eps)``)."""
     if use_native(x, weight, bias) and len(normalized_shape) == 1 and _norm_supported(x, weight):
-        w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
-        b = bias if bias is None or bias.dtype == x.dtype else bias.to(x.dtype)
+        w = aligned_param(weight, x.dtype)
+        b = aligned_param(bias, x.dtype)
         return _LayerNormFn.apply(x, w, b, eps)
     return F.layer_norm(
         x, normalized_shape,
@@ -74,7 +74,7 @@ def layer_norm(x, normalized_shape, weight, bias, eps=1e-5):
 def rms_norm(x, normalized_shape, weight, eps=1e-5):
     """``y = x * rsqrt(mean(x^2) + eps) * weight`` over the last dimension."""
     if use_native(x, weight) and len(normalized_shape) == 1 and _norm_supported(x, weight):
-        w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
+        w = aligned_param(weight, x.dtype)
         return _RMSNormFn.apply(x, w, eps)
     if hasattr(F, "rms_norm"):
         return F.rms_norm(x, normalized_shape, weight.to(x.dtype) if weight is not None else None, eps)

@@ -1,12 +1,233 @@
-"""Placeholder; replaced below in the build."""
+"""Symmetric-memory data parallelism for one NVSwitch domain (``--ddp-backend b200``).
+
+Instead of handing gradients to NCCL (reference: torch DDP reducer,
+``unicore/models/distributed_unicore_model.py:37-46``), the flat 16-bit gradient arena that the
+mixed-precision optimizer builds (``unicore/optim/fp16_optimizer.py``) is *allocated in symmetric
+memory*: every rank maps every peer's arena (and an NVLS multicast alias) into its address space.
+Autograd therefore writes gradients directly where the hand-written reduction kernels
+(``csrc/comm/allreduce.cu``: one-shot / two-shot peer loads+stores, or ``multimem.ld_reduce`` /
+``multimem.st`` through the switch) read them - no bucket copies, no NCCL call on the gradient path.
+
+Overlap with backward: parameters are grouped into contiguous buckets of the arena (reverse
+registration order ~ gradient-ready order); per-parameter ``post_accumulate_grad`` hooks count a
+bucket down and, when it is complete, launch its reduction on a high-priority side stream.
+``all_reduce_grads()`` (called by the trainer after backward) flushes whatever is left and joins
+the streams.  ``no_sync()`` disables communication for gradient-accumulation micro-batches.
+
+Rendezvous uses ``torch.distributed._symmetric_memory`` (CUDA VMM handles exchanged over the
+process group's store); NCCL remains only for bootstrap and cold paths (parameter broadcast,
+checkpoints, tiny statistics).
+"""
+import contextlib
+import logging
+from typing import Dict, List, Optional
+
 import torch
+import torch.distributed as dist
+from torch import nn
+
+logger = logging.getLogger(__name__)
+
+
+def _symm_module():
+    import torch.distributed._symmetric_memory as symm_mem
+
+    return symm_mem
 
 
 def symm_available() -> bool:
-    return False
+    """CUDA + initialised NCCL group + symmetric memory importable + native kernels loaded."""
+    try:
+        from unicore_b200.ops import _native
+
+        if not (_native.USE_NATIVE and hasattr(_native.native(), "symm_allreduce")):
+            return False
+        if not (torch.cuda.is_available() and dist.is_available() and dist.is_initialized()):
+            return False
+        if dist.get_world_size() < 2 or dist.get_world_size() > _native.native().SYMM_MAX_PEERS:
+            return False
+        _symm_module()
+        return True
+    except Exception:  # noqa: BLE001
+        return False
 
 
-class SymmDataParallel(torch.nn.Module):
-    def __init__(self, module, process_group, bucket_cap_mb=25):
+class SymmBuffer:
+    """One symmetric allocation: local tensor + peer addresses (+ multicast alias)."""
+
+    def __init__(self, numel: int, dtype: torch.dtype, device: torch.device, group):
+        symm_mem = _symm_module()
+        self.tensor = symm_mem.empty(numel, dtype=dtype, device=device)
+        self.handle = symm_mem.rendezvous(self.tensor, group)
+        self.rank = self.handle.rank
+        self.world = self.handle.world_size
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        mc = 0
+        try:
+            if getattr(self.handle, "has_multicast_support", False):
+                mc = int(self.handle.multicast_ptr)
+        except Exception:  # noqa: BLE001
+            mc = 0
+        self.multicast_ptr = mc
+
+
+class SymmAllReduce:
+    """Launches the peer-memory all-reduce kernels on ranges of a symmetric buffer."""
+
+    def __init__(self, group=None):
+        from unicore_b200.ops._native import native
+
+        self.native = native()
+        self.group = group if group is not None else dist.group.WORLD
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        n_flags = int(self.native.SYMM_MAX_BLOCKS) * int(self.native.SYMM_MAX_PEERS)
+        self.flags = SymmBuffer(n_flags, torch.int32, self.device, self.group)
+        self.flags.tensor.zero_()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # flags are zero everywhere before the first kernel spins on them
+        self.rank = self.flags.rank
+        self.world = self.flags.world
+
+    def allocate(self, numel: int, dtype: torch.dtype) -> SymmBuffer:
+        return SymmBuffer(numel, dtype, self.device, self.group)
+
+    def __call__(self, buf: SymmBuffer, elem_offset: int = 0, numel: Optional[int] = None, scale: float = 1.0,
+                 algo: int = 0, blocks: int = 0):
+        """In-place sum over ranks of ``buf.tensor[elem_offset : elem_offset + numel]`` (x ``scale``)."""
+        t = buf.tensor
+        numel = t.numel() - elem_offset if numel is None else numel
+        esz = t.element_size()
+        byte_off, nbytes = elem_offset * esz, numel * esz
+        if byte_off % 16 or nbytes % 16:
+            raise ValueError("symmetric all-reduce ranges must be 16-byte aligned")
+        tag = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[t.dtype]
+        self.native.symm_allreduce(
+            buf.ptrs, self.flags.ptrs, buf.multicast_ptr, self.rank, byte_off, nbytes, tag, float(scale), int(algo),
+            int(blocks),
+        )
+
+
+class _Bucket:
+    __slots__ = ("buffer", "lo", "hi", "pending", "total", "launched")
+
+    def __init__(self, buffer, lo, hi):
+        self.buffer, self.lo, self.hi = buffer, lo, hi
+        self.pending = self.total = 0
+        self.launched = False
+
+
+class SymmDataParallel(nn.Module):
+    """Data-parallel wrapper whose gradient reduction runs on hand-written NVLink kernels."""
+
+    def __init__(self, module: nn.Module, process_group=None, bucket_cap_mb: int = 25):
         super().__init__()
-        raise RuntimeError("symmetric-memory engine not built yet")
+        self.module = module
+        self.process_group = process_group if process_group is not None else dist.group.WORLD
+        self.world_size = dist.get_world_size(self.process_group)
+        self.reducer = SymmAllReduce(self.process_group)
+        self.bucket_bytes = max(1, int(bucket_cap_mb)) * 1024 * 1024
+        self.accumulate_grads = False
+        self._buffers: List[SymmBuffer] = []
+        self._buckets: List[_Bucket] = []
+        self._param_bucket: Dict[nn.Parameter, _Bucket] = {}
+        self._hooks = []
+        self._comm_stream = torch.cuda.Stream(priority=-1)
+        self._started = False
+        # replicas must start identical (reference: DDP broadcasts from rank 0 at construction)
+        with torch.no_grad():
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t.data, src=0, group=self.process_group)
+
+    def forward(self, *inputs, **kwargs):
+        return self.module(*inputs, **kwargs)
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        previous, self.accumulate_grads = self.accumulate_grads, True
+        try:
+            yield
+        finally:
+            self.accumulate_grads = previous
+
+    # -- optimizer integration ----------------------------------------------------------------------------
+    def alloc_grad_buffer(self, numel: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+        """Called by ``flatten_parameters``: the flat gradient arena lives in symmetric memory."""
+        padded = -(-numel // 8) * 8  # whole 16-byte vectors
+        buf = self.reducer.allocate(padded, dtype)
+        buf.tensor.zero_()
+        self._buffers.append(buf)
+        return buf.tensor[:numel]
+
+    def attach_optimizer(self, optimizer) -> None:
+        """Build buckets over the flat gradient arenas and install gradient-ready hooks."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks, self._buckets, self._param_bucket = [], [], {}
+        by_ptr = {buf.tensor.data_ptr(): buf for buf in self._buffers}
+        for group in optimizer.fp16_params:
+            for flat in group["params"]:
+                buf = by_ptr.get(flat.grad.data_ptr())
+                if buf is None:
+                    continue
+                esz = flat.grad.element_size()
+                per_bucket = max(8, (self.bucket_bytes // esz) // 8 * 8)
+                total = buf.tensor.numel()
+                edges = list(range(0, total, per_bucket)) + [total]
+                buckets = [_Bucket(buf, lo, hi) for lo, hi in zip(edges[:-1], edges[1:])]
+                self._buckets.extend(buckets)
+                base = flat.grad.data_ptr()
+                for p in self.module.parameters():
+                    if p.grad is None or not p.requires_grad:
+                        continue
+                    off = (p.grad.data_ptr() - base) // esz
+                    if not (0 <= off < flat.grad.numel()) or p.grad.dtype != flat.grad.dtype:
+                        continue
+                    # every bucket the parameter overlaps has to wait for its gradient
+                    last = min(off + p.grad.numel() - 1, total - 1)
+                    first_b = off // per_bucket
+                    last_b = min(last // per_bucket, len(buckets) - 1)
+                    touched = buckets[first_b:last_b + 1]
+                    for b in touched:
+                        b.total += 1
+                    self._param_bucket[p] = touched
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
+        self._reset_counters()
+
+    def _reset_counters(self):
+        for b in self._buckets:
+            b.pending = b.total
+            b.launched = False
+        self._started = False
+
+    def _on_grad_ready(self, param):
+        if self.accumulate_grads:
+            return
+        for b in self._param_bucket.get(param, ()):
+            b.pending -= 1
+            if b.pending == 0 and not b.launched:
+                self._launch(b)
+
+    def _launch(self, b: _Bucket):
+        if not self._started:
+            self._started = True
+        # the bucket's gradients were produced on the current (compute) stream
+        self._comm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._comm_stream):
+            self.reducer(b.buffer, b.lo, b.hi - b.lo, scale=1.0 / self.world_size)
+        b.launched = True
+
+    def all_reduce_grads(self):
+        """Flush unreduced buckets (unused params, no hooks fired) and join the comm stream."""
+        if self.accumulate_grads:
+            return
+        if not self._buckets:  # optimizer without flat arenas: fall back to NCCL per tensor
+            for p in self.module.parameters():
+                if p.grad is not None:
+                    p.grad.div_(self.world_size)
+                    dist.all_reduce(p.grad, group=self.process_group)
+            return
+        for b in self._buckets:
+            if not b.launched:
+                self._launch(b)
+        torch.cuda.current_stream().wait_stream(self._comm_stream)
+        self._reset_counters()
