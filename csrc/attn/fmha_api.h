@@ -11,8 +11,9 @@ struct FmhaFwdParams {
   const void* v;
   void* out;       // [B, Lq, H, 64] contiguous
   float* lse;      // [B, H, Lq]
-  const void* bias;        // [bias_batch (1 or B), H, Lq, Lk] contiguous, fp32 or same 16-bit type; may be null
+  const void* bias;        // [bias_batch (1 or B), H, Lq, Lk] contiguous, same 16-bit type as q; may be null
   const uint8_t* kpm;      // [B, Lk] bool, nonzero = masked; may be null
+  uint32_t* drop_bits;     // [B, H, Lq, ceil(Lk/32)] dropout keep bits (written by fwd, read by bwd); null if p == 0
   long long q_sb, q_sl, q_sh, k_sb, k_sl, k_sh, v_sb, v_sl, v_sh;
   int B, H, Lq, Lk;
   int bias_batch, bias_is_f32, is_bf16;
@@ -26,10 +27,12 @@ struct FmhaBwdParams {
   const void* dout;  // [B, Lq, H, 64] contiguous
   float* delta;      // [B, H, Lq] scratch: rowsum(dO * O)
   float* dq_acc;     // [B, Lq, H, 64] fp32, zero-initialised (atomically accumulated)
-  void* dq;          // [B, Lq, H, 64] 16-bit result
-  void* dk;          // [B, Lk, H, 64]
+  void* dq;          // [B, Lq, H, 64] 16-bit results, addressed through (batch, seq, head) element strides so
+  void* dk;          // that they can be slices of one packed [B, L, 3, H, 64] gradient tensor
   void* dv;
+  long long dq_sb, dq_sl, dq_sh, dk_sb, dk_sl, dk_sh, dv_sb, dv_sl, dv_sh;
   float* dbias;      // [bias_batch, H, Lq, Lk] fp32, zero-initialised; null when not needed
+  int debug_flags;   // profiling only: 1 = skip dBias reductions, 2 = skip dQ reductions, 4 = skip exp/dS math
 };
 void launch_fmha_bwd(const FmhaBwdParams& p, cudaStream_t stream);
 

@@ -4,6 +4,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <optional>
 
@@ -56,11 +57,12 @@ void fill_common(ub::FmhaFwdParams& p, const Tensor& q, const Tensor& k, const T
     TORCH_CHECK(bias->is_cuda() && bias->is_contiguous() && bias->dim() == 4);
     TORCH_CHECK((bias->size(0) == 1 || bias->size(0) == p.B) && bias->size(1) == p.H && bias->size(2) == p.Lq &&
                 bias->size(3) == p.Lk, "bias must be [1|B, H, Lq, Lk]");
-    TORCH_CHECK(bias->scalar_type() == at::kFloat || bias->scalar_type() == q.scalar_type());
+    TORCH_CHECK(bias->scalar_type() == q.scalar_type(), "bias must have the dtype of q");
+    TORCH_CHECK((reinterpret_cast<uintptr_t>(bias->data_ptr()) & 15) == 0, "bias must be 16-byte aligned");
     p.bias = bias->data_ptr();
     p.bias_batch = (int)bias->size(0);
-    p.bias_is_f32 = bias->scalar_type() == at::kFloat ? 1 : 0;
   }
+  p.drop_bits = nullptr;
   p.kpm = nullptr;
   if (kpm.has_value() && kpm->defined()) {
     TORCH_CHECK(kpm->is_cuda() && kpm->is_contiguous() && kpm->scalar_type() == at::kBool && kpm->dim() == 2 &&
@@ -71,7 +73,7 @@ void fill_common(ub::FmhaFwdParams& p, const Tensor& q, const Tensor& k, const T
   p.scale = (float)scale;
 }
 
-std::tuple<Tensor, Tensor, int64_t, int64_t> fmha_fwd(const Tensor& q, const Tensor& k, const Tensor& v,
+std::tuple<Tensor, Tensor, OptTensor> fmha_fwd(const Tensor& q, const Tensor& k, const Tensor& v,
                                                       const OptTensor& bias, const OptTensor& kpm, double p_drop,
                                                       double scale) {
   const c10::cuda::CUDAGuard guard(q.device());
@@ -82,35 +84,61 @@ std::tuple<Tensor, Tensor, int64_t, int64_t> fmha_fwd(const Tensor& q, const Ten
   p.out = out.data_ptr();
   p.lse = lse.data_ptr<float>();
   p.seed = p.offset = 0;
+  OptTensor bits;
   if (p_drop > 0.0) {
     auto so = reserve_philox(4);
     p.seed = so.first;
     p.offset = so.second;
+    // 1 keep-bit per (query, key): 1/16 of the size of a 16-bit score tensor
+    bits = torch::empty({p.B, p.H, p.Lq, (p.Lk + 31) / 32}, q.options().dtype(at::kInt));
+    p.drop_bits = reinterpret_cast<uint32_t*>(bits->data_ptr());
   }
   ub::launch_fmha_fwd(p, at::cuda::getCurrentCUDAStream().stream());
   cudaError_t err = cudaGetLastError();
   TORCH_CHECK(err == cudaSuccess, "fmha_fwd launch failed: ", cudaGetErrorString(err));
-  return {out, lse, (int64_t)p.seed, (int64_t)p.offset};
+  return {out, lse, bits};
 }
 
 std::tuple<Tensor, Tensor, Tensor, OptTensor> fmha_bwd(const Tensor& dout, const Tensor& q, const Tensor& k,
                                                        const Tensor& v, const Tensor& out, const Tensor& lse,
                                                        const OptTensor& bias, const OptTensor& kpm, double p_drop,
-                                                       double scale, int64_t seed, int64_t offset, bool need_dbias) {
+                                                       double scale, const OptTensor& drop_bits, bool need_dbias,
+                                                       bool packed_grad) {
+  // packed_grad: q/k/v are slices [:, :, i] of one [B, L, 3, H, 64] tensor; the gradients are then
+  // written straight into one packed [B, L, 3, H, 64] tensor (returned three times as views), which
+  // spares autograd three zero-filled select-backward tensors and two full-size adds per layer.
   const c10::cuda::CUDAGuard guard(q.device());
   ub::FmhaBwdParams p{};
   fill_common(p.f, q, k, v, bias, kpm, p_drop, scale);
   TORCH_CHECK(dout.is_contiguous() && out.is_contiguous() && lse.is_contiguous());
   p.f.out = out.data_ptr();
   p.f.lse = lse.data_ptr<float>();
-  p.f.seed = (uint64_t)seed;
-  p.f.offset = (uint64_t)offset;
+  if (p_drop > 0.0) {
+    TORCH_CHECK(drop_bits.has_value() && drop_bits->defined() && drop_bits->is_contiguous(), "dropout bits missing");
+    p.f.drop_bits = reinterpret_cast<uint32_t*>(drop_bits->data_ptr());
+  }
   p.dout = dout.data_ptr();
+  {
+    const char* dbg = std::getenv("UNICORE_FMHA_DEBUG");
+    p.debug_flags = dbg ? std::atoi(dbg) : 0;
+  }
   Tensor delta = torch::empty({p.f.B, p.f.H, p.f.Lq}, q.options().dtype(at::kFloat));
   Tensor dq_acc = torch::zeros({p.f.B, p.f.Lq, p.f.H, 64}, q.options().dtype(at::kFloat));
-  Tensor dq = torch::empty({p.f.B, p.f.Lq, p.f.H, 64}, q.options());
-  Tensor dk = torch::empty({p.f.B, p.f.Lk, p.f.H, 64}, q.options());
-  Tensor dv = torch::empty({p.f.B, p.f.Lk, p.f.H, 64}, q.options());
+  Tensor dq, dk, dv;
+  if (packed_grad) {
+    TORCH_CHECK(p.f.Lq == p.f.Lk, "packed gradients need self-attention shapes");
+    Tensor dqkv = torch::empty({p.f.B, p.f.Lq, 3, p.f.H, 64}, q.options());
+    dq = dqkv.select(2, 0);
+    dk = dqkv.select(2, 1);
+    dv = dqkv.select(2, 2);
+  } else {
+    dq = torch::empty({p.f.B, p.f.Lq, p.f.H, 64}, q.options());
+    dk = torch::empty({p.f.B, p.f.Lk, p.f.H, 64}, q.options());
+    dv = torch::empty({p.f.B, p.f.Lk, p.f.H, 64}, q.options());
+  }
+  p.dq_sb = dq.stride(0); p.dq_sl = dq.stride(1); p.dq_sh = dq.stride(2);
+  p.dk_sb = dk.stride(0); p.dk_sl = dk.stride(1); p.dk_sh = dk.stride(2);
+  p.dv_sb = dv.stride(0); p.dv_sl = dv.stride(1); p.dv_sh = dv.stride(2);
   OptTensor dbias;
   p.dbias = nullptr;
   if (need_dbias && p.f.bias != nullptr) {

@@ -1,17 +1,21 @@
 // Fused multi-head attention backward for sm_100a (head_dim 64, fp16/bf16), flash-attention style:
-// probabilities are recomputed from the saved log-sum-exp, the dropout mask from the Philox counters.
+// probabilities are recomputed from the saved log-sum-exp; the dropout keep bits come from the
+// forward pass (1 bit / element).
 //
-//   grid = (key tiles, H, B); one CTA owns K_j, V_j (128 keys) and walks the query tiles i:
+//   grid = (key tiles, H, B); one CTA (512 threads) owns K_j, V_j (128 keys) and walks the query tiles i:
 //     S   = Q_i K_j^T                      tcgen05.mma  -> TMEM [  0,128)
 //     dP  = dO_i V_j^T                     tcgen05.mma  -> TMEM [128,256)
-//     P   = exp(scale*S + bias - LSE_i) ;  dS = P o (dropout(dP) - delta_i)        (256 threads:
-//           thread = (query row, column half); no cross-thread reductions are needed)
-//     dV_j += dropout(P)^T dO_i            tcgen05.mma  -> TMEM [256,320)   (A and B MN-major views)
+//     P   = exp2(S*scale*log2e + bias*log2e + kmask - LSE_i*log2e) ;  dS = P o (drop(dP) - delta_i)
+//           thread = (query row, 32-column quarter): no cross-thread reductions; 16 warps hide latency
+//     dV_j += drop(P)^T dO_i               tcgen05.mma  -> TMEM [256,320)   (A and B MN-major views)
 //     dK_j += scale * dS^T Q_i             tcgen05.mma  -> TMEM [320,384)
 //     dQ_i  = scale * dS K_j               tcgen05.mma  -> TMEM [384,448) -> red.global.add.v4.f32
 //     dBias += dS                          red.global.add.v4.f32 (bias broadcast over the batch)
-//   Every shared-memory tile is written once in the 8x8 core-matrix layout and presented to the
-//   tensor core as K-major or MN-major by swapping descriptor strides (no transposes).
+//   Software pipeline: Q_{i+1}, dO_{i+1} and the bias tile of (i+1, j) are fetched with cp.async
+//   into the alternate buffers while tile i is being processed; the bias tile is staged in the
+//   buffer that later receives dS (same core-matrix layout => in-place overwrite, chunk by chunk).
+//   Every operand tile is written once and presented to the tensor core as K-major or MN-major by
+//   swapping descriptor strides (no transposes).
 // Pre-pass:  delta = rowsum(dO o O).   Post-pass: dq = cast(dq_acc).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -29,38 +33,20 @@ namespace {
 using namespace tc;
 
 constexpr int kBM = 128, kBN = 128, kD = 64;
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 512;
 constexpr uint32_t kBwdTmemCols = 512;
 constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
 
-constexpr uint32_t kOffQ = 0, kOffDO = 16384, kOffK = 32768, kOffV = 49152, kOffP = 65536, kOffDS = 98304;
-constexpr uint32_t kOffBar = 131072;
-constexpr uint32_t kBwdSmemBytes = 131072 + 64;
-
-template <typename T>
-UB_DEVICE void bwd_load_tile64(uint8_t* smem_tile, const T* gbase, long long row_stride, int valid_rows) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps
-  const int r_in8 = lane & 7, c_lo = lane >> 3;
-  Vec16 regs[4];
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int u = it * 8 + warp;
-    const int row = (u >> 1) * 8 + r_in8;
-    const int c = (u & 1) * 4 + c_lo;
-    if (row < valid_rows) {
-      regs[it] = ld_global_nc_v4(gbase + (long long)row * row_stride + c * 8);
-    } else {
-      regs[it].w[0] = regs[it].w[1] = regs[it].w[2] = regs[it].w[3] = 0u;
-    }
-  }
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int u = it * 8 + warp;
-    const int row = (u >> 1) * 8 + r_in8;
-    const int c = (u & 1) * 4 + c_lo;
-    *reinterpret_cast<Vec16*>(smem_tile + tile64_off(row, c)) = regs[it];
-  }
-}
+// shared memory map (bytes)
+constexpr uint32_t kOffQ = 0;          // 2 x 16 KB
+constexpr uint32_t kOffDO = 32768;     // 2 x 16 KB
+constexpr uint32_t kOffK = 65536;
+constexpr uint32_t kOffV = 81920;
+constexpr uint32_t kOffP = 98304;      // 32 KB
+constexpr uint32_t kOffDS = 131072;    // 2 x 32 KB: bias tile, then dS (in place)
+constexpr uint32_t kOffKAdd = 196608;  // float[128]
+constexpr uint32_t kOffBar = 196608 + 512;
+constexpr uint32_t kBwdSmemBytes = kOffBar + 64;
 
 template <typename T>
 UB_DEVICE uint32_t bwd_pack2(float a, float b);
@@ -77,56 +63,6 @@ UB_DEVICE uint32_t bwd_pack2<__nv_bfloat16>(float a, float b) {
 
 UB_DEVICE void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-// s = acc*scale + bias, -inf for masked / out-of-range keys (same rule as the forward kernel)
-template <typename T, bool kBiasF32>
-UB_DEVICE void bwd_logits32(const uint32_t (&acc)[32], float (&s)[32], float scale, const void* bias_row, int key0,
-                            const uint8_t* kpm_row, int Lk) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(acc[i]) * scale;
-  if (bias_row != nullptr) {
-    if (kBiasF32) {
-      const float* bp = reinterpret_cast<const float*>(bias_row) + key0;
-#pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        if (key0 + v * 4 < Lk) {
-          const Vec16 b = ld_global_v4(bp + v * 4);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) s[v * 4 + e] += __uint_as_float(b.w[e]);
-        }
-      }
-    } else {
-      const T* bp = reinterpret_cast<const T*>(bias_row) + key0;
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        if (key0 + v * 8 < Lk) {
-          float t[8];
-          unpack<T>(ld_global_v4(bp + v * 8), t);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) s[v * 8 + e] += t[e];
-        }
-      }
-    }
-  }
-  if (kpm_row != nullptr) {
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      if (key0 + v * 8 < Lk) {
-        const uint2 m = *reinterpret_cast<const uint2*>(kpm_row + key0 + v * 8);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if ((m.x >> (8 * e)) & 0xffu) s[v * 8 + e] = -CUDART_INF_F;
-          if ((m.y >> (8 * e)) & 0xffu) s[v * 8 + 4 + e] = -CUDART_INF_F;
-        }
-      }
-    }
-  }
-  if (key0 + 32 > Lk) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (key0 + i >= Lk) s[i] = -CUDART_INF_F;
-  }
 }
 
 // ---- pre-pass: delta[b,h,q] = sum_d dO * O -----------------------------------------------------------------
@@ -159,27 +95,36 @@ __global__ void __launch_bounds__(256) fmha_delta_kernel(const T* __restrict__ d
 
 // ---- post-pass: fp32 accumulator -> 16-bit ------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) fmha_cast_kernel(const float* __restrict__ in, T* __restrict__ out, long long nvec) {
+__global__ void __launch_bounds__(256) fmha_cast_kernel(const float* __restrict__ in, T* __restrict__ out, long long nvec,
+                                                          int H, int Lq, long long sb, long long sl, long long sh) {
+  // in: contiguous [B, Lq, H, 64] fp32; out: 16-bit with (batch, seq, head) element strides
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
     float x[8];
     unpack<float>(ld_global_nc_v4(in + v * 8), x);
     unpack<float>(ld_global_nc_v4(in + v * 8 + 4), x + 4);
-    st_global_v4(out + v * 8, pack<T>(x));
+    const long long rowi = v >> 3;  // (b, q, h) row of 64 elements = 8 vectors
+    const int part = (int)(v & 7);
+    const int hh = (int)(rowi % H);
+    const long long bq = rowi / H;
+    const long long qq = bq % Lq, bb = bq / Lq;
+    st_global_v4(out + bb * sb + qq * sl + (long long)hh * sh + part * 8, pack<T>(x));
   }
 }
 
 // ---- main kernel ----------------------------------------------------------------------------------------------
-template <typename T, bool kBiasF32>
+template <typename T>
 __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams bp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const FmhaFwdParams& p = bp.f;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int r = tid & 127, half = tid >> 7;  // thread = (tile row, 64-column half)
+  const int r = tid & 127, quarter = tid >> 7;  // thread = (tile row, 32-column quarter)
+  const int col0 = quarter * 32;                // my columns inside the key tile
   const int key_tile0 = blockIdx.x * kBN, h = blockIdx.y, b = blockIdx.z;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_a = smem_base + kOffBar, bar_b = smem_base + kOffBar + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 16);
+  float* kadd = reinterpret_cast<float*>(smem + kOffKAdd);
 
   if (warp == 0) {
     tmem_alloc(smem_u32(tmem_slot), kBwdTmemCols);
@@ -196,101 +141,122 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
   const long long o_sl = (long long)p.H * kD;  // contiguous [B, L, H, 64] tensors
   const T* dog = reinterpret_cast<const T*>(bp.dout) + ((long long)b * p.Lq * p.H + h) * kD;
   const int k_valid = min(kBN, p.Lk - key_tile0);
-  bwd_load_tile64<T>(smem + kOffK, kg + (long long)key_tile0 * p.k_sl, p.k_sl, k_valid);
-  bwd_load_tile64<T>(smem + kOffV, vg + (long long)key_tile0 * p.v_sl, p.v_sl, k_valid);
-  fence_before_thread_sync();
-  __syncthreads();
-  fence_after_thread_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  const int bb = p.bias_batch > 1 ? b : 0;
+  const bool has_bias = p.bias != nullptr;
+  const T* bias_base = has_bias ? reinterpret_cast<const T*>(p.bias) + (((long long)bb * p.H + h) * p.Lq) * p.Lk + key_tile0
+                                : nullptr;
+  const int n_qtiles = (p.Lq + kBM - 1) / kBM;
+
+  auto issue_tile = [&](int i) {  // asynchronous copies of everything tile i needs
+    const int q0 = i * kBM;
+    const int q_valid = min(kBM, p.Lq - q0);
+    const uint32_t buf = (uint32_t)(i & 1);
+    cp_async_tile64<kBwdThreads, T>(smem_base + kOffQ + buf * 16384, qg + (long long)q0 * p.q_sl, p.q_sl, q_valid);
+    cp_async_tile64<kBwdThreads, T>(smem_base + kOffDO + buf * 16384, dog + (long long)q0 * o_sl, o_sl, q_valid);
+    if (has_bias)
+      cp_async_tile128<kBwdThreads, T>(smem_base + kOffDS + buf * 32768, bias_base + (long long)q0 * p.Lk, p.Lk,
+                                       q_valid, k_valid);
+  };
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t idesc_s = make_idesc_f16(kBM, kBN, kFmt, 0, 0);    // S, dP: both operands K-major
   constexpr uint32_t idesc_t = make_idesc_f16(kBN, kD, kFmt, 1, 1);     // dV, dK: both operands MN-major
   constexpr uint32_t idesc_q = make_idesc_f16(kBM, kD, kFmt, 0, 1);     // dQ: A K-major, B MN-major
 
-  const uint8_t* kpm_row = p.kpm != nullptr ? p.kpm + (long long)b * p.Lk : nullptr;
-  const bool drop = p.p_drop > 0.f;
-  const uint32_t thresh = dropout_thresh16(p.p_drop);
-  const float keep_scale = drop ? 1.f / (1.f - p.p_drop) : 1.f;
+  cp_async_tile64<kBwdThreads, T>(smem_base + kOffK, kg + (long long)key_tile0 * p.k_sl, p.k_sl, k_valid);
+  cp_async_tile64<kBwdThreads, T>(smem_base + kOffV, vg + (long long)key_tile0 * p.v_sl, p.v_sl, k_valid);
+  issue_tile(0);
+  cp_async_commit();
+  if (tid < kBN) {
+    const int key = key_tile0 + tid;
+    const bool masked = key >= p.Lk || (p.kpm != nullptr && p.kpm[(long long)b * p.Lk + key] != 0);
+    kadd[tid] = masked ? -CUDART_INF_F : 0.f;
+  }
+  cp_async_wait<0>();
+  fence_proxy_async_smem();
+  fence_before_thread_sync();
+  __syncthreads();
+  fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+
+  // S_i = Q_i K^T and dP_i = dO_i V^T (issued one tile ahead of the softmax that consumes them)
+  auto issue_s_dp = [&](int i) {
+    const uint32_t buf = (uint32_t)(i & 1);
+    const uint32_t sQ = smem_base + kOffQ + buf * 16384, sDO = smem_base + kOffDO + buf * 16384;
+#pragma unroll
+    for (int kk = 0; kk < kD / 16; ++kk) {
+      const uint64_t dq_ = make_smem_desc(sQ + kk * 256, 128, 1024);
+      const uint64_t dk_ = make_smem_desc(smem_base + kOffK + kk * 256, 128, 1024);
+      umma_f16_ss(tmem_base + kColS, dq_, dk_, idesc_s, kk > 0 ? 1u : 0u);
+    }
+#pragma unroll
+    for (int kk = 0; kk < kD / 16; ++kk) {
+      const uint64_t ddo = make_smem_desc(sDO + kk * 256, 128, 1024);
+      const uint64_t dv_ = make_smem_desc(smem_base + kOffV + kk * 256, 128, 1024);
+      umma_f16_ss(tmem_base + kColDP, ddo, dv_, idesc_s, kk > 0 ? 1u : 0u);
+    }
+    umma_commit(bar_a);
+  };
+  if (tid == 0) issue_s_dp(0);
+
+  const bool drop = p.p_drop > 0.f && p.drop_bits != nullptr;
+  const float keep_scale = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   constexpr float kLog2e = 1.4426950408889634f;
-  const int bb = p.bias_batch > 1 ? b : 0;
+  const float scale2 = p.scale * kLog2e;
+  const int words_per_row = (p.Lk + 31) / 32;
   uint32_t phase_a = 0, phase_b = 0;
-  const int n_qtiles = (p.Lq + kBM - 1) / kBM;
 
   for (int i = 0; i < n_qtiles; ++i) {
     const int q0 = i * kBM;
-    const int q_valid = min(kBM, p.Lq - q0);
-    // Q_i, dO_i -> shared memory (previous iteration's MMAs were drained via bar_b below)
-    bwd_load_tile64<T>(smem + kOffQ, qg + (long long)q0 * p.q_sl, p.q_sl, q_valid);
-    bwd_load_tile64<T>(smem + kOffDO, dog + (long long)q0 * o_sl, o_sl, q_valid);
-    fence_proxy_async_smem();
-    fence_before_thread_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_thread_sync();
-#pragma unroll
-      for (int kk = 0; kk < kD / 16; ++kk) {
-        const uint64_t dq_ = make_smem_desc(smem_base + kOffQ + kk * 256, 128, 1024);
-        const uint64_t dk_ = make_smem_desc(smem_base + kOffK + kk * 256, 128, 1024);
-        umma_f16_ss(tmem_base + kColS, dq_, dk_, idesc_s, kk > 0 ? 1u : 0u);
-      }
-#pragma unroll
-      for (int kk = 0; kk < kD / 16; ++kk) {
-        const uint64_t ddo = make_smem_desc(smem_base + kOffDO + kk * 256, 128, 1024);
-        const uint64_t dv_ = make_smem_desc(smem_base + kOffV + kk * 256, 128, 1024);
-        umma_f16_ss(tmem_base + kColDP, ddo, dv_, idesc_s, kk > 0 ? 1u : 0u);
-      }
-      umma_commit(bar_a);
-    }
+    const uint32_t buf = (uint32_t)(i & 1);
+    const uint32_t sQ = smem_base + kOffQ + buf * 16384, sDO = smem_base + kOffDO + buf * 16384;
+    const uint32_t offDS = kOffDS + buf * 32768;
+    if (i + 1 < n_qtiles) issue_tile(i + 1);  // prefetch under the softmax of tile i
+    cp_async_commit();
+
     const int row = q0 + r;
     const bool row_valid = row < p.Lq;
     const long long stat_idx = ((long long)b * p.H + h) * p.Lq + (row_valid ? row : 0);
     const float lse = row_valid ? p.lse[stat_idx] : CUDART_INF_F;
     const float delta = row_valid ? bp.delta[stat_idx] : 0.f;
-    const float lse_use = (lse == -CUDART_INF_F) ? CUDART_INF_F : lse;  // fully masked row -> p = 0
-    const void* bias_row = nullptr;
-    if (p.bias != nullptr && row_valid) {
-      const long long boff = (((long long)bb * p.H + h) * p.Lq + row) * p.Lk;
-      bias_row = kBiasF32 ? (const void*)(reinterpret_cast<const float*>(p.bias) + boff)
-                          : (const void*)(reinterpret_cast<const T*>(p.bias) + boff);
-    }
+    // fully masked row (lse = -inf) or padding row -> p = 0
+    const float lse2 = (lse == -CUDART_INF_F || !row_valid) ? CUDART_INF_F : lse * kLog2e;
+    uint32_t keep_word = 0xffffffffu;
+    if (drop && row_valid && key_tile0 + col0 < p.Lk)
+      keep_word = p.drop_bits[stat_idx * words_per_row + ((key_tile0 + col0) >> 5)];
     float* dbias_row = (bp.dbias != nullptr && row_valid)
-                           ? bp.dbias + (((long long)bb * p.H + h) * p.Lq + row) * p.Lk
+                           ? bp.dbias + (((long long)bb * p.H + h) * p.Lq + row) * p.Lk + key_tile0
                            : nullptr;
-    const unsigned long long drop_row_base = (((unsigned long long)b * p.H + h) * p.Lq + (row_valid ? row : 0)) * p.Lk;
 
     mbar_wait(bar_a, phase_a);
     phase_a ^= 1;
     fence_after_thread_sync();
-
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      const int col0 = half * 64 + c * 32;      // column inside the key tile
-      const int key0 = key_tile0 + col0;
+    {
       uint32_t acc[32], dpr[32];
-      float s[32];
       tmem_ld32(lane_base + kColS + col0, acc);
       tmem_ld32(lane_base + kColDP + col0, dpr);
       tmem_wait_ld();
-      bwd_logits32<T, kBiasF32>(acc, s, p.scale, bias_row, key0, kpm_row, p.Lk);
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        uint32_t keep = 0xffu;
-        if (drop) {
-          const unsigned long long idx = drop_row_base + (unsigned long long)(key0 + v * 8);
-          keep = dropout_keep8(p.seed, p.offset, idx >> 3, thresh);
-        }
+        const uint32_t off = tile128_off(r, (col0 >> 3) + v);
+        float bf[8];
+        if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(smem + offDS + off), bf);
+        const float4 ka = *reinterpret_cast<const float4*>(kadd + col0 + v * 8);
+        const float4 kb = *reinterpret_cast<const float4*>(kadd + col0 + v * 8 + 4);
+        const float kk8[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
         float pd[8], ds[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float pr = row_valid ? exp2f((s[v * 8 + e] - lse_use) * kLog2e) : 0.f;
-          const float km = ((keep >> e) & 1u) ? keep_scale : 0.f;
+          const float add = has_bias ? fmaf(bf[e], kLog2e, kk8[e]) : kk8[e];
+          const float s2 = fmaf(__uint_as_float(acc[v * 8 + e]), scale2, add);
+          const float pr = exp2f(s2 - lse2);
+          const float km = ((keep_word >> (v * 8 + e)) & 1u) ? keep_scale : 0.f;
           pd[e] = pr * km;
-          ds[e] = pr * (__uint_as_float(dpr[v * 8 + e]) * km - delta);
+          ds[e] = pr * fmaf(__uint_as_float(dpr[v * 8 + e]), km, -delta);
         }
-        if (dbias_row != nullptr && key0 + v * 8 < p.Lk) {
-          red_add_v4(dbias_row + key0 + v * 8, ds[0], ds[1], ds[2], ds[3]);
-          red_add_v4(dbias_row + key0 + v * 8 + 4, ds[4], ds[5], ds[6], ds[7]);
+        if (dbias_row != nullptr && key_tile0 + col0 + v * 8 < p.Lk && !(bp.debug_flags & 1)) {
+          red_add_v4(dbias_row + col0 + v * 8, ds[0], ds[1], ds[2], ds[3]);
+          red_add_v4(dbias_row + col0 + v * 8 + 4, ds[4], ds[5], ds[6], ds[7]);
         }
         Vec16 op, od;
 #pragma unroll
@@ -298,66 +264,70 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
           op.w[e] = bwd_pack2<T>(pd[2 * e], pd[2 * e + 1]);
           od.w[e] = bwd_pack2<T>(ds[2 * e] * p.scale, ds[2 * e + 1] * p.scale);
         }
-        const uint32_t off = tile128_off(r, (col0 >> 3) + v);
         *reinterpret_cast<Vec16*>(smem + kOffP + off) = op;
-        *reinterpret_cast<Vec16*>(smem + kOffDS + off) = od;
+        *reinterpret_cast<Vec16*>(smem + offDS + off) = od;   // in place over the consumed bias chunk
       }
     }
+    cp_async_wait<0>();   // my share of tile i+1 has landed; the barrier below publishes it
     fence_proxy_async_smem();
     fence_before_thread_sync();
     __syncthreads();
     if (tid == 0) {
       fence_after_thread_sync();
+      const uint32_t sDS = smem_base + offDS;
 #pragma unroll
       for (int kk = 0; kk < kBM / 16; ++kk) {  // reduction over the 128 query rows, 16 per step
         const uint64_t a_p = make_smem_desc(smem_base + kOffP + kk * 4096, 2048, 128);    // P^T  (MN-major)
-        const uint64_t b_do = make_smem_desc(smem_base + kOffDO + kk * 2048, 1024, 128);  // dO   (MN-major)
+        const uint64_t b_do = make_smem_desc(sDO + kk * 2048, 1024, 128);                 // dO   (MN-major)
         umma_f16_ss(tmem_base + kColDV, a_p, b_do, idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
       }
 #pragma unroll
       for (int kk = 0; kk < kBM / 16; ++kk) {
-        const uint64_t a_ds = make_smem_desc(smem_base + kOffDS + kk * 4096, 2048, 128);  // dS^T (MN-major)
-        const uint64_t b_q = make_smem_desc(smem_base + kOffQ + kk * 2048, 1024, 128);    // Q    (MN-major)
+        const uint64_t a_ds = make_smem_desc(sDS + kk * 4096, 2048, 128);                 // dS^T (MN-major)
+        const uint64_t b_q = make_smem_desc(sQ + kk * 2048, 1024, 128);                   // Q    (MN-major)
         umma_f16_ss(tmem_base + kColDK, a_ds, b_q, idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
       }
 #pragma unroll
       for (int kk = 0; kk < kBN / 16; ++kk) {  // reduction over the 128 keys
-        const uint64_t a_ds = make_smem_desc(smem_base + kOffDS + kk * 256, 128, 2048);   // dS   (K-major)
+        const uint64_t a_ds = make_smem_desc(sDS + kk * 256, 128, 2048);                  // dS   (K-major)
         const uint64_t b_k = make_smem_desc(smem_base + kOffK + kk * 2048, 1024, 128);    // K    (MN-major)
         umma_f16_ss(tmem_base + kColDQ, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
       }
       umma_commit(bar_b);
+      // next tile's S / dP run on the tensor core while the dQ read-out and the atomics proceed
+      if (i + 1 < n_qtiles) issue_s_dp(i + 1);
     }
     mbar_wait(bar_b, phase_b);
     phase_b ^= 1;
     fence_after_thread_sync();
-    {  // dQ_i partial -> global fp32 accumulator
-      uint32_t acc[32];
-      tmem_ld32(lane_base + kColDQ + half * 32, acc);
+    {  // dQ_i partial -> global fp32 accumulator (16 of the 64 columns per thread)
+      uint32_t acc[16];
+      tmem_ld16(lane_base + kColDQ + quarter * 16, acc);
       tmem_wait_ld();
-      if (row_valid) {
-        float* dst = bp.dq_acc + (((long long)b * p.Lq + row) * p.H + h) * kD + half * 32;
+      if (row_valid && !(bp.debug_flags & 2)) {
+        float* dst = bp.dq_acc + (((long long)b * p.Lq + row) * p.H + h) * kD + quarter * 16;
 #pragma unroll
-        for (int v = 0; v < 8; ++v)
+        for (int v = 0; v < 4; ++v)
           red_add_v4(dst + v * 4, __uint_as_float(acc[v * 4]), __uint_as_float(acc[v * 4 + 1]),
                      __uint_as_float(acc[v * 4 + 2]), __uint_as_float(acc[v * 4 + 3]));
       }
     }
-    fence_before_thread_sync();  // TMEM reads done before the next iteration's MMAs overwrite S/dP/dQ
   }
 
-  // ---- epilogue: dK_j, dV_j -------------------------------------------------------------------------------------
+  // ---- epilogue: dK_j, dV_j (16 of the 64 columns per thread) ---------------------------------------------------
   {
     const int key = key_tile0 + r;
-    uint32_t accv[32], acck[32];
-    tmem_ld32(lane_base + kColDV + half * 32, accv);
-    tmem_ld32(lane_base + kColDK + half * 32, acck);
+    uint32_t accv[16], acck[16];
+    tmem_ld16(lane_base + kColDV + quarter * 16, accv);
+    tmem_ld16(lane_base + kColDK + quarter * 16, acck);
     tmem_wait_ld();
     if (key < p.Lk) {
-      T* dvg = reinterpret_cast<T*>(bp.dv) + (((long long)b * p.Lk + key) * p.H + h) * kD + half * 32;
-      T* dkg = reinterpret_cast<T*>(bp.dk) + (((long long)b * p.Lk + key) * p.H + h) * kD + half * 32;
+      T* dvg = reinterpret_cast<T*>(bp.dv) + (long long)b * bp.dv_sb + (long long)key * bp.dv_sl + (long long)h * bp.dv_sh +
+               quarter * 16;
+      T* dkg = reinterpret_cast<T*>(bp.dk) + (long long)b * bp.dk_sb + (long long)key * bp.dk_sl + (long long)h * bp.dk_sh +
+               quarter * 16;
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
+      for (int v = 0; v < 2; ++v) {
         Vec16 ov, ok;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -381,19 +351,14 @@ void run_bwd(const FmhaBwdParams& bp, cudaStream_t stream) {
   fmha_delta_kernel<T><<<(unsigned)((nrows * 8 + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const T*>(bp.dout), reinterpret_cast<const T*>(p.out), bp.delta, p.B, p.H, p.Lq);
   dim3 grid((p.Lk + kBN - 1) / kBN, p.H, p.B);
-  if (p.bias_is_f32) {
-    auto kern = fmha_bwd_kernel<T, true>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes);
-    kern<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(bp);
-  } else {
-    auto kern = fmha_bwd_kernel<T, false>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes);
-    kern<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(bp);
-  }
+  auto kern = fmha_bwd_kernel<T>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes);
+  kern<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(bp);
   const long long nvec = nrows * 64 / 8;
   long long blocks = (nvec + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  fmha_cast_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(bp.dq_acc, reinterpret_cast<T*>(bp.dq), nvec);
+  fmha_cast_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(bp.dq_acc, reinterpret_cast<T*>(bp.dq), nvec, p.H, p.Lq,
+                                                            bp.dq_sb, bp.dq_sl, bp.dq_sh);
 }
 
 }  // namespace

@@ -3,16 +3,21 @@
 //
 // Tensor-core path: tcgen05.mma (cta_group::1, M=128) with fp32 accumulators in tensor memory.
 //   S (128 x 128 fp32) lives in TMEM columns [0,128), O (128 x 64 fp32) in columns [128,192).
-//   One CTA = one 128-row query tile of one (batch, head); it walks the key tiles (128 keys each):
-//     1. K_j, V_j -> shared memory (8x8 core-matrix layout, see tcgen05.cuh)
+//   One CTA (256 threads) = one 128-row query tile of one (batch, head); it walks the key tiles:
+//     1. cp.async: bias tile (staged *into the P buffer*, same core-matrix layout, so each thread
+//        later overwrites exactly the bias chunks it consumed) and V_j; K_j was prefetched while the
+//        previous tile's softmax ran
 //     2. S  = Q K_j^T          4 x tcgen05.mma (K=16 each), commit -> mbarrier
-//     3. softmax: thread t owns query row t (TMEM lane t): tcgen05.ld the row, add bias / masks,
-//        online max/sum, Philox dropout, write P (16-bit) to shared memory, rescale O in TMEM
-//     4. O += P V_j            8 x tcgen05.mma (V presented MN-major from the same row-major bytes)
+//     3. softmax in ONE pass over registers: thread = (query row, 64-key half); TMEM lane = row.
+//        tcgen05.ld, fused scale/bias/key-mask FMA (log2 domain), row max exchanged between the two
+//        halves through shared memory, exp2, Philox dropout (keep bits are stored for backward),
+//        P -> shared memory, O rescaled in TMEM (32 columns per thread)
+//     4. O += P V_j            8 x tcgen05.mma (V presented MN-major from the same row-major bytes);
+//        V_j is only waited for here, so its latency hides behind the softmax
 //   q/k/v are read through strides straight out of the packed in_proj output; O is written as
 //   [B, Lq, H, 64] so that out_proj consumes it without a transpose.
-// Two CTAs are resident per SM (80 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps
-// the other's loads and MMAs.
+// Two CTAs are resident per SM (82 KB smem, 256 TMEM columns, <= 128 registers/thread) so one CTA's
+// softmax overlaps the other's copies and MMAs; 16 warps per SM hide the ALU/MUFU latencies.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
@@ -24,49 +29,25 @@
 #include "tcgen05.cuh"
 
 namespace ub {
+namespace {
 
 using namespace tc;
 
 constexpr int kBlockM = 128;   // query rows per CTA
 constexpr int kBlockN = 128;   // keys per tile
 constexpr int kHeadDim = 64;
-constexpr int kFwdThreads = 128;
+constexpr int kFwdThreads = 256;
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kTmemColS = 0, kTmemColO = 128;
 
 constexpr uint32_t kSmemQ = 0;
 constexpr uint32_t kSmemK = 16384;
 constexpr uint32_t kSmemV = 32768;
-constexpr uint32_t kSmemP = 49152;            // 128 x 128 x 2 = 32768 bytes
-constexpr uint32_t kSmemBar = 81920;          // 2 mbarriers + tmem base
-constexpr uint32_t kFwdSmemBytes = 81920 + 64;
-
-// copy a [128 rows x 64] 16-bit tile (row stride `row_stride` elements) into core-matrix layout.
-// Rows >= valid_rows are zero filled.
-template <typename T>
-UB_DEVICE void load_tile64(uint8_t* smem_tile, const T* gbase, long long row_stride, int valid_rows) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r_in8 = lane & 7, c_lo = lane >> 3;
-  Vec16 regs[8];
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int u = it * 4 + warp;
-    const int row = (u >> 1) * 8 + r_in8;
-    const int c = (u & 1) * 4 + c_lo;
-    if (row < valid_rows) {
-      regs[it] = ld_global_nc_v4(gbase + (long long)row * row_stride + c * 8);
-    } else {
-      regs[it].w[0] = regs[it].w[1] = regs[it].w[2] = regs[it].w[3] = 0u;
-    }
-  }
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int u = it * 4 + warp;
-    const int row = (u >> 1) * 8 + r_in8;
-    const int c = (u & 1) * 4 + c_lo;
-    *reinterpret_cast<Vec16*>(smem_tile + tile64_off(row, c)) = regs[it];
-  }
-}
+constexpr uint32_t kSmemP = 49152;            // 128 x 128 x 2 = 32768 bytes: bias tile, then P
+constexpr uint32_t kSmemKAdd = 81920;         // float[128]: 0 or -inf per key of the tile
+constexpr uint32_t kSmemXchg = 81920 + 512;   // float[256]: row max / row sum exchange between halves
+constexpr uint32_t kSmemBar = 81920 + 512 + 1024;
+constexpr uint32_t kFwdSmemBytes = kSmemBar + 64;
 
 template <typename T>
 UB_DEVICE uint32_t pack2(float a, float b);
@@ -81,64 +62,17 @@ UB_DEVICE uint32_t pack2<__nv_bfloat16>(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// logits of 32 consecutive keys of this thread's row: s = acc * scale + bias, -inf where masked
-template <typename T, bool kBiasF32>
-UB_DEVICE void logits32(const uint32_t (&acc)[32], float (&s)[32], float scale, const void* bias_row, int key0,
-                        const uint8_t* kpm_row, int Lk, bool row_valid) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(acc[i]) * scale;
-  if (bias_row != nullptr && row_valid) {
-    if (kBiasF32) {
-      const float* bp = reinterpret_cast<const float*>(bias_row) + key0;
-#pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        if (key0 + v * 4 < Lk) {
-          const Vec16 b = ld_global_v4(bp + v * 4);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) s[v * 4 + e] += __uint_as_float(b.w[e]);
-        }
-      }
-    } else {
-      const T* bp = reinterpret_cast<const T*>(bias_row) + key0;
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        if (key0 + v * 8 < Lk) {
-          float t[8];
-          unpack<T>(ld_global_v4(bp + v * 8), t);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) s[v * 8 + e] += t[e];
-        }
-      }
-    }
-  }
-  if (kpm_row != nullptr) {
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      if (key0 + v * 8 < Lk) {
-        const uint2 m = *reinterpret_cast<const uint2*>(kpm_row + key0 + v * 8);  // 8 bool bytes
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if ((m.x >> (8 * e)) & 0xffu) s[v * 8 + e] = -CUDART_INF_F;
-          if ((m.y >> (8 * e)) & 0xffu) s[v * 8 + 4 + e] = -CUDART_INF_F;
-        }
-      }
-    }
-  }
-  if (key0 + 32 > Lk) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (key0 + i >= Lk) s[i] = -CUDART_INF_F;
-  }
-}
-
-template <typename T, bool kBiasF32>
+template <typename T>
 __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & 127, half = tid >> 7;   // thread = (tile row, 64-key half)
   const int q0 = blockIdx.x * kBlockM, h = blockIdx.y, b = blockIdx.z;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_s = smem_base + kSmemBar, bar_o = smem_base + kSmemBar + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemBar + 16);
+  float* kadd = reinterpret_cast<float*>(smem + kSmemKAdd);
+  float* xchg = reinterpret_cast<float*>(smem + kSmemXchg);
 
   if (warp == 0) {
     tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -153,45 +87,59 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
   const T* kg = reinterpret_cast<const T*>(p.k) + (long long)b * p.k_sb + (long long)h * p.k_sh;
   const T* vg = reinterpret_cast<const T*>(p.v) + (long long)b * p.v_sb + (long long)h * p.v_sh;
   const int q_valid = min(kBlockM, p.Lq - q0);
-  load_tile64<T>(smem + kSmemQ, qg, p.q_sl, q_valid);
+  const bool has_bias = p.bias != nullptr;
+  const T* bias_tile = has_bias ? reinterpret_cast<const T*>(p.bias) +
+                                      (((long long)(p.bias_batch > 1 ? b : 0) * p.H + h) * p.Lq + q0) * p.Lk
+                                : nullptr;
+  // prologue copies: Q and K_0 (one group)
+  cp_async_tile64<kFwdThreads, T>(smem_base + kSmemQ, qg, p.q_sl, q_valid);
+  cp_async_tile64<kFwdThreads, T>(smem_base + kSmemK, kg, p.k_sl, min(kBlockN, p.Lk));
+  cp_async_commit();
   fence_before_thread_sync();
   __syncthreads();
   fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's TMEM lanes
+  const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's TMEM lanes
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t idesc_qk = make_idesc_f16(kBlockM, kBlockN, kFmt, 0, 0);
   constexpr uint32_t idesc_pv = make_idesc_f16(kBlockM, kHeadDim, kFmt, 0, 1);
 
-  const int row = q0 + tid;
+  const int row = q0 + r;
   const bool row_valid = row < p.Lq;
-  const void* bias_row = nullptr;
-  if (p.bias != nullptr) {
-    const long long boff = ((long long)(p.bias_batch > 1 ? b : 0) * p.H + h) * p.Lq + (row_valid ? row : 0);
-    bias_row = kBiasF32 ? (const void*)(reinterpret_cast<const float*>(p.bias) + boff * p.Lk)
-                        : (const void*)(reinterpret_cast<const T*>(p.bias) + boff * p.Lk);
-  }
   const uint8_t* kpm_row = p.kpm != nullptr ? p.kpm + (long long)b * p.Lk : nullptr;
   const bool drop = p.p_drop > 0.f;
   const uint32_t thresh = dropout_thresh16(p.p_drop);
   const float keep_scale = drop ? 1.f / (1.f - p.p_drop) : 1.f;
-  const unsigned long long drop_row_base = (((unsigned long long)b * p.H + h) * p.Lq + (row_valid ? row : 0)) * p.Lk;
+  const unsigned long long row_lin = ((unsigned long long)b * p.H + h) * p.Lq + (row_valid ? row : 0);
+  const unsigned long long drop_row_base = row_lin * p.Lk;
+  uint32_t* bits_row = (drop && p.drop_bits != nullptr) ? p.drop_bits + row_lin * ((p.Lk + 31) / 32) : nullptr;
 
   constexpr float kLog2e = 1.4426950408889634f;
-  float m_run = -CUDART_INF_F, l_run = 0.f;
+  const float scale2 = p.scale * kLog2e;
+  float m_run = -CUDART_INF_F, l_run = 0.f;   // running max (log2 domain, common to both halves), partial sum
   uint32_t phase_s = 0, phase_o = 0;
   const int n_tiles = (p.Lk + kBlockN - 1) / kBlockN;
 
   for (int j = 0; j < n_tiles; ++j) {
     const int key_tile0 = j * kBlockN;
-    if (j > 0) {  // previous P V must be done before K/V/P shared memory is overwritten
+    const int k_valid = min(kBlockN, p.Lk - key_tile0);
+    if (j > 0) {  // previous P V must be done before V / P shared memory is overwritten
       mbar_wait(bar_o, phase_o);
       phase_o ^= 1;
       fence_after_thread_sync();
     }
-    const int k_valid = min(kBlockN, p.Lk - key_tile0);
-    load_tile64<T>(smem + kSmemK, kg + (long long)key_tile0 * p.k_sl, p.k_sl, k_valid);
-    load_tile64<T>(smem + kSmemV, vg + (long long)key_tile0 * p.v_sl, p.v_sl, k_valid);
+    // group "bias_j" (into the P buffer), then group "V_j"; K_j is the older group already in flight
+    if (has_bias)
+      cp_async_tile128<kFwdThreads, T>(smem_base + kSmemP, bias_tile + key_tile0, p.Lk, q_valid, k_valid);
+    cp_async_commit();
+    cp_async_tile64<kFwdThreads, T>(smem_base + kSmemV, vg + (long long)key_tile0 * p.v_sl, p.v_sl, k_valid);
+    cp_async_commit();
+    if (tid < kBlockN) {  // additive key mask of this tile
+      const int key = key_tile0 + tid;
+      const bool masked = key >= p.Lk || (kpm_row != nullptr && kpm_row[key] != 0);
+      kadd[tid] = masked ? -CUDART_INF_F : 0.f;
+    }
+    cp_async_wait<2>();            // all but {bias_j, V_j}: Q (first tile) and K_j have landed
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -204,71 +152,93 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
       }
       umma_commit(bar_s);
     }
+    cp_async_wait<1>();            // my share of the bias tile has landed (V_j may still be in flight)
     mbar_wait(bar_s, phase_s);
     phase_s ^= 1;
     fence_after_thread_sync();
+    __syncthreads();               // everyone's bias chunks are visible; K buffer is free (S is complete)
+    if (j + 1 < n_tiles)           // prefetch K_{j+1} under the softmax
+      cp_async_tile64<kFwdThreads, T>(smem_base + kSmemK, kg + (long long)(key_tile0 + kBlockN) * p.k_sl, p.k_sl,
+                                      min(kBlockN, p.Lk - key_tile0 - kBlockN));
+    cp_async_commit();             // (possibly empty) group "K_{j+1}": keeps the group arithmetic uniform
 
-    // ---- pass 1: row maximum -------------------------------------------------------------------
-    float m_tile = -CUDART_INF_F;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t acc[32];
-      float s[32];
-      tmem_ld32(lane_base + kTmemColS + c * 32, acc);
-      tmem_wait_ld();
-      logits32<T, kBiasF32>(acc, s, p.scale, bias_row, key_tile0 + c * 32, kpm_row, p.Lk, row_valid);
+    // ---- logits of my 64 columns in registers (log2 domain): s2 = acc*scale*log2e + bias*log2e + kadd ----
+    float s2[64];
+    float m_part = -CUDART_INF_F;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, s[i]);
+    for (int c = 0; c < 2; ++c) {
+      const int col0 = half * 64 + c * 32;
+      uint32_t acc[32];
+      tmem_ld32(lane_base + kTmemColS + col0, acc);
+      tmem_wait_ld();
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float bf[8];
+        if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(smem + kSmemP + tile128_off(r, (col0 >> 3) + v)), bf);
+        const float4 ka = *reinterpret_cast<const float4*>(kadd + col0 + v * 8);
+        const float4 kb = *reinterpret_cast<const float4*>(kadd + col0 + v * 8 + 4);
+        const float kk8[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int i = c * 32 + v * 8 + e;
+          const float add = has_bias ? fmaf(bf[e], kLog2e, kk8[e]) : kk8[e];
+          s2[i] = fmaf(__uint_as_float(acc[v * 8 + e]), scale2, add);
+          m_part = fmaxf(m_part, s2[i]);
+        }
+      }
     }
+    xchg[tid] = m_part;
+    __syncthreads();
+    const float m_tile = fmaxf(m_part, xchg[tid ^ 128]);
     const float m_new = fmaxf(m_run, m_tile);
     const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-    const float alpha = exp2f((m_run - m_use) * kLog2e);  // m_run = -inf -> 0
+    const float alpha = exp2f(m_run - m_use);  // m_run = -inf -> 0
     l_run *= alpha;
     m_run = m_new;
 
-    // ---- pass 2: probabilities, dropout, P -> shared memory ---------------------------------------
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t acc[32];
-      float s[32];
-      tmem_ld32(lane_base + kTmemColS + c * 32, acc);
-      tmem_wait_ld();
-      logits32<T, kBiasF32>(acc, s, p.scale, bias_row, key_tile0 + c * 32, kpm_row, p.Lk, row_valid);
-      float psum = 0.f;
+    // ---- probabilities, dropout, P -> shared memory (in place over the bias chunks) ---------------------
+    float psum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        s[i] = exp2f((s[i] - m_use) * kLog2e);
-        psum += s[i];
+    for (int c = 0; c < 2; ++c) {
+      const int col0 = half * 64 + c * 32;
+      uint32_t keep_word = 0xffffffffu;
+      if (drop) {
+        keep_word = 0u;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const unsigned long long idx = drop_row_base + (unsigned long long)(key_tile0 + col0 + v * 8);
+          keep_word |= dropout_keep8(p.seed, p.offset, idx >> 3, thresh) << (8 * v);
+        }
+        if (bits_row != nullptr && row_valid && key_tile0 + col0 < p.Lk) bits_row[(key_tile0 + col0) >> 5] = keep_word;
       }
-      l_run += psum;
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        if (drop) {
-          const unsigned long long idx = drop_row_base + (unsigned long long)(key_tile0 + c * 32 + v * 8);
-          const uint32_t keep = dropout_keep8(p.seed, p.offset, idx >> 3, thresh);
+        float pr[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) s[v * 8 + e] = ((keep >> e) & 1u) ? s[v * 8 + e] * keep_scale : 0.f;
+        for (int e = 0; e < 8; ++e) {
+          pr[e] = exp2f(s2[c * 32 + v * 8 + e] - m_use);
+          psum += pr[e];
+          if (drop) pr[e] = ((keep_word >> (v * 8 + e)) & 1u) ? pr[e] * keep_scale : 0.f;
         }
         Vec16 o;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o.w[e] = pack2<T>(s[v * 8 + 2 * e], s[v * 8 + 2 * e + 1]);
-        *reinterpret_cast<Vec16*>(smem + kSmemP + tile128_off(tid, c * 4 + v)) = o;
+        for (int e = 0; e < 4; ++e) o.w[e] = pack2<T>(pr[2 * e], pr[2 * e + 1]);
+        *reinterpret_cast<Vec16*>(smem + kSmemP + tile128_off(r, (col0 >> 3) + v)) = o;
       }
     }
+    l_run += psum;
 
-    // ---- rescale the running output accumulator ------------------------------------------------------
+    // ---- rescale the running output accumulator (32 of the 64 columns per thread) ------------------------
     if (j > 0) {
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t acc[32];
-        tmem_ld32(lane_base + kTmemColO + c * 32, acc);
-        tmem_wait_ld();
+      uint32_t acc[32];
+      tmem_ld32(lane_base + kTmemColO + half * 32, acc);
+      tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) * alpha);
-        tmem_st32(lane_base + kTmemColO + c * 32, acc);
-      }
+      for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) * alpha);
+      tmem_st32(lane_base + kTmemColO + half * 32, acc);
       tmem_wait_st();
     }
+    cp_async_wait<1>();            // V_j has landed (K_{j+1} may still be in flight)
     fence_proxy_async_smem();
     fence_before_thread_sync();
     __syncthreads();
@@ -287,50 +257,50 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
   }
 
   // ---- epilogue ---------------------------------------------------------------------------------------
+  xchg[tid] = l_run;
   mbar_wait(bar_o, phase_o);
   fence_after_thread_sync();
-  const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
-  T* og = reinterpret_cast<T*>(p.out) + (((long long)b * p.Lq + row) * p.H + h) * kHeadDim;
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
+  __syncthreads();
+  const float l_tot = l_run + xchg[tid ^ 128];
+  const float inv_l = l_tot > 0.f ? 1.f / l_tot : 0.f;
+  {
     uint32_t acc[32];
-    tmem_ld32(lane_base + kTmemColO + c * 32, acc);
+    tmem_ld32(lane_base + kTmemColO + half * 32, acc);
     tmem_wait_ld();
     if (row_valid) {
+      T* og = reinterpret_cast<T*>(p.out) + (((long long)b * p.Lq + row) * p.H + h) * kHeadDim + half * 32;
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         Vec16 o;
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           o.w[e] = pack2<T>(__uint_as_float(acc[v * 8 + 2 * e]) * inv_l, __uint_as_float(acc[v * 8 + 2 * e + 1]) * inv_l);
-        st_global_v4(og + c * 32 + v * 8, o);
+        st_global_v4(og + v * 8, o);
       }
     }
   }
-  if (row_valid) {
-    p.lse[((long long)b * p.H + h) * p.Lq + row] = (l_run > 0.f) ? m_run + __logf(l_run) : -CUDART_INF_F;
+  if (row_valid && half == 0) {
+    // natural-log LSE of the logits: (m2 + log2(l)) / log2(e)
+    p.lse[row_lin] = (l_tot > 0.f) ? (m_run + log2f(l_tot)) * 0.6931471805599453f : -CUDART_INF_F;
   }
   fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+}  // namespace
+
 void launch_fmha_fwd(const FmhaFwdParams& p, cudaStream_t stream) {
   dim3 grid((p.Lq + kBlockM - 1) / kBlockM, p.H, p.B);
-#define UB_FMHA_FWD_LAUNCH(T, BF32)                                                                            \
-  do {                                                                                                         \
-    auto kern = fmha_fwd_kernel<T, BF32>;                                                                      \
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes);               \
-    kern<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(p);                                                     \
-  } while (0)
   if (p.is_bf16) {
-    if (p.bias_is_f32) UB_FMHA_FWD_LAUNCH(__nv_bfloat16, true);
-    else UB_FMHA_FWD_LAUNCH(__nv_bfloat16, false);
+    auto kern = fmha_fwd_kernel<__nv_bfloat16>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes);
+    kern<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(p);
   } else {
-    if (p.bias_is_f32) UB_FMHA_FWD_LAUNCH(__half, true);
-    else UB_FMHA_FWD_LAUNCH(__half, false);
+    auto kern = fmha_fwd_kernel<__half>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes);
+    kern<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(p);
   }
-#undef UB_FMHA_FWD_LAUNCH
 }
 
 }  // namespace ub

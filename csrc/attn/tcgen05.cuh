@@ -122,6 +122,15 @@ TC_DEVICE void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+TC_DEVICE void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 TC_DEVICE void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 TC_DEVICE void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -130,6 +139,51 @@ TC_DEVICE void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::
 TC_DEVICE uint32_t tile64_off(int row, int chunk) { return (uint32_t)((row >> 3) * 1024 + chunk * 128 + (row & 7) * 16); }
 // same for a [rows x 128 halfs] tile (16 chunks per row) => 2048 bytes per 8-row group.
 TC_DEVICE uint32_t tile128_off(int row, int chunk) { return (uint32_t)((row >> 3) * 2048 + chunk * 128 + (row & 7) * 16); }
+
+// ---- asynchronous global -> shared copies (LDGSTS); src_bytes = 0 zero-fills the 16 destination bytes --------
+TC_DEVICE void cp_async16(uint32_t smem_addr, const void* gptr, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
+}
+TC_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+TC_DEVICE void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Asynchronously stage a [128 rows x 64] 16-bit tile (row stride in elements) into the core-matrix
+// layout with NT threads. Rows >= valid_rows are zero-filled. 8 lanes cover one 128-byte core-matrix
+// column (conflict-free shared-memory writes), 4 such groups cover 64 contiguous bytes of each row.
+template <int NT, typename T>
+TC_DEVICE void cp_async_tile64(uint32_t smem_tile, const T* gbase, long long row_stride, int valid_rows) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r_in8 = lane & 7, c_lo = lane >> 3;
+  constexpr int kWarps = NT / 32;
+#pragma unroll
+  for (int it = 0; it < 32 / kWarps; ++it) {
+    const int u = it * kWarps + warp;          // 0..31: (row group, chunk half)
+    const int row = (u >> 1) * 8 + r_in8;
+    const int c = (u & 1) * 4 + c_lo;
+    const bool ok = row < valid_rows;
+    cp_async16(smem_tile + tile64_off(row, c), gbase + (ok ? (long long)row * row_stride + c * 8 : 0), ok ? 16u : 0u);
+  }
+}
+
+// Same for a [128 x 128] 16-bit tile (bias): columns >= valid_cols and rows >= valid_rows zero-filled.
+template <int NT, typename T>
+TC_DEVICE void cp_async_tile128(uint32_t smem_tile, const T* gbase, long long row_stride, int valid_rows,
+                                int valid_cols) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r_in8 = lane & 7, c_lo = lane >> 3;
+  constexpr int kWarps = NT / 32;
+#pragma unroll
+  for (int it = 0; it < 64 / kWarps; ++it) {
+    const int u = it * kWarps + warp;          // 0..63: (row group, chunk quarter)
+    const int row = (u >> 2) * 8 + r_in8;
+    const int c = (u & 3) * 4 + c_lo;
+    const bool ok = row < valid_rows && c * 8 < valid_cols;
+    cp_async16(smem_tile + tile128_off(row, c), gbase + (ok ? (long long)row * row_stride + c * 8 : 0), ok ? 16u : 0u);
+  }
+}
 
 }  // namespace tc
 }  // namespace ub

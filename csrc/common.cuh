@@ -166,11 +166,12 @@ struct Philox4 {
   uint32_t x, y, z, w;
 };
 
-UB_DEVICE Philox4 philox4x32_10(uint64_t seed, uint64_t offset, uint64_t ctr) {
+template <int kRounds>
+UB_DEVICE Philox4 philox4x32(uint64_t seed, uint64_t offset, uint64_t ctr) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = (uint32_t)offset, c3 = (uint32_t)(offset >> 32);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kRounds; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
@@ -180,12 +181,17 @@ UB_DEVICE Philox4 philox4x32_10(uint64_t seed, uint64_t offset, uint64_t ctr) {
   }
   return Philox4{c0, c1, c2, c3};
 }
+// full-strength variant (stochastic rounding of the weights)
+UB_DEVICE Philox4 philox4x32_10(uint64_t seed, uint64_t offset, uint64_t ctr) {
+  return philox4x32<10>(seed, offset, ctr);
+}
 
 // Dropout decisions for 8 consecutive elements whose first linear index is `idx8*8`:
 // one Philox call gives 8 x 16-bit uniforms; keep iff u16 >= thresh16 (thresh16 = round(p*65536)).
 // Returns an 8-bit keep mask (bit i = element i kept).
 UB_DEVICE uint32_t dropout_keep8(uint64_t seed, uint64_t offset, uint64_t idx8, uint32_t thresh16) {
-  const Philox4 r = philox4x32_10(seed, offset, idx8);
+  // 7 rounds: Philox4x32-7 already passes BigCrush and dropout only needs decorrelated bits
+  const Philox4 r = philox4x32<7>(seed, offset, idx8);
   uint32_t m = 0;
   const uint32_t ws[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll

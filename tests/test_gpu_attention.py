@@ -89,6 +89,29 @@ def test_fmha_backward(dtype, bias_batch):
     assert berr < tol * max(1.0, bias_r.grad.abs().max().item()), berr
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_fmha_qkvpacked_backward(dtype):
+    """Packed entry point: gradients land in one [B, L, 3, H, D] tensor written by the kernels."""
+    ops = _ops()
+    B, H, L = 2, 4, 384
+    qkv, _, _, _ = _make(B, H, L, L, dtype, seed=4)
+    bias = torch.randn(1, H, L, L, device="cuda").to(dtype).requires_grad_(True)
+    kpm = torch.zeros(B, L, dtype=torch.bool, device="cuda")
+    kpm[0, 300:] = True
+    out = ops.fused_attention_qkvpacked(qkv, bias=bias, key_padding_mask=kpm, dropout_p=0.0, training=True, scale=0.125)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    assert qkv.grad.shape == qkv.shape and qkv.grad.is_contiguous()
+    qkv_r = qkv.detach().float().requires_grad_(True)
+    bias_r = bias.detach().float().requires_grad_(True)
+    ref, _ = _ref(qkv_r[:, :, 0], qkv_r[:, :, 1], qkv_r[:, :, 2], bias_r, kpm, 0.125)
+    ref.backward(dout.float())
+    tol = 1e-2 if dtype == torch.float16 else 6e-2
+    assert (out.float() - ref).abs().max().item() < tol
+    assert (qkv.grad.float() - qkv_r.grad).abs().max().item() < tol * max(1.0, qkv_r.grad.abs().max().item())
+    assert (bias.grad.float() - bias_r.grad).abs().max().item() < tol * max(1.0, bias_r.grad.abs().max().item())
+
+
 def test_fmha_dropout_consistency():
     """Dropout: keep-rate, and backward uses exactly the forward's mask (checked via a linear probe)."""
     ops = _ops()

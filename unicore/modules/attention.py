@@ -88,8 +88,8 @@ class SelfMultiheadAttention(nn.Module):
         q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]  # strided views [B, L, H, D]
         bias4 = _bias_as_4d(attn_bias, bsz, self.num_heads, tgt_len, tgt_len)
         if not return_attn and ops.fused_attention_supported(q, k, v, bias4, key_padding_mask):
-            o = ops.fused_attention(
-                q, k, v, bias=bias4, key_padding_mask=key_padding_mask,
+            o = ops.fused_attention_qkvpacked(
+                qkv, bias=bias4, key_padding_mask=key_padding_mask,
                 dropout_p=self.dropout, training=self.training, scale=self.scaling,
             ).reshape(bsz, tgt_len, embed_dim)
             return o, None, None

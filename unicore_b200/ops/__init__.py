@@ -1,6 +1,11 @@
 """Python surface of the hand-written sm_100a kernels (+ PyTorch fallbacks for CPU runs)."""
 from ._native import HAS_CUDA_EXT, USE_NATIVE, native, use_native  # noqa: F401
-from .attention_ops import attention_reference, fused_attention, fused_attention_supported  # noqa: F401
+from .attention_ops import (  # noqa: F401
+    attention_reference,
+    fused_attention,
+    fused_attention_qkvpacked,
+    fused_attention_supported,
+)
 from .fused_ops import bias_dropout_add_layer_norm, bias_gelu, softmax_cross_entropy  # noqa: F401
 from .norm_ops import layer_norm, rms_norm  # noqa: F401
 from .optim_ops import (  # noqa: F401

@@ -41,23 +41,50 @@ class _FusedAttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, bias, key_padding_mask, dropout_p, training, scale):
         p = float(dropout_p) if training else 0.0
-        out, lse, seed, offset = native().fmha_fwd(q, k, v, bias, key_padding_mask, p, float(scale))
-        ctx.save_for_backward(q, k, v, out, lse, bias, key_padding_mask)
+        out, lse, bits = native().fmha_fwd(q, k, v, bias, key_padding_mask, p, float(scale))
+        ctx.save_for_backward(q, k, v, out, lse, bias, key_padding_mask, bits)
         ctx.p = p
         ctx.scale = float(scale)
-        ctx.rng = (seed, offset)
         ctx.need_dbias = bias is not None and bias.requires_grad
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, out, lse, bias, kpm = ctx.saved_tensors
+        q, k, v, out, lse, bias, kpm, bits = ctx.saved_tensors
         dq, dk, dv, dbias = native().fmha_bwd(
-            dout.contiguous(), q, k, v, out, lse, bias, kpm, ctx.p, ctx.scale, ctx.rng[0], ctx.rng[1], ctx.need_dbias
+            dout.contiguous(), q, k, v, out, lse, bias, kpm, ctx.p, ctx.scale, bits, ctx.need_dbias, False
         )
         if dbias is not None and dbias.dtype != bias.dtype:
             dbias = dbias.to(bias.dtype)
         return dq, dk, dv, dbias, None, None, None, None
+
+
+class _FusedAttentionPackedFn(torch.autograd.Function):
+    """Self-attention on a packed ``[B, L, 3, H, 64]`` projection: q/k/v are strided slices on the way
+    in, and the backward kernels write dq/dk/dv directly into ONE packed gradient tensor."""
+
+    @staticmethod
+    def forward(ctx, qkv, bias, key_padding_mask, dropout_p, training, scale):
+        p = float(dropout_p) if training else 0.0
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+        out, lse, bits = native().fmha_fwd(q, k, v, bias, key_padding_mask, p, float(scale))
+        ctx.save_for_backward(qkv, out, lse, bias, key_padding_mask, bits)
+        ctx.p = p
+        ctx.scale = float(scale)
+        ctx.need_dbias = bias is not None and bias.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse, bias, kpm, bits = ctx.saved_tensors
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+        dq, _dk, _dv, dbias = native().fmha_bwd(
+            dout.contiguous(), q, k, v, out, lse, bias, kpm, ctx.p, ctx.scale, bits, ctx.need_dbias, True
+        )
+        dqkv = dq._base  # the packed [B, L, 3, H, 64] tensor the three gradients are views of
+        if dbias is not None and dbias.dtype != bias.dtype:
+            dbias = dbias.to(bias.dtype)
+        return dqkv, dbias, None, None, None, None
 
 
 def fused_attention_supported(q, k, v, bias=None, key_padding_mask=None) -> bool:
@@ -83,6 +110,8 @@ def fused_attention_supported(q, k, v, bias=None, key_padding_mask=None) -> bool
             return False
         if bias.dtype not in (q.dtype, torch.float32):
             return False
+        if bias.dtype == q.dtype and bias.is_contiguous() and bias.data_ptr() % 16 != 0:
+            return False
     return True
 
 
@@ -92,8 +121,23 @@ def fused_attention(q, k, v, bias=None, key_padding_mask=None, dropout_p=0.0, tr
         scale = 1.0 / math.sqrt(q.shape[-1])
     if fused_attention_supported(q, k, v, bias, key_padding_mask):
         if bias is not None:
-            bias = bias.contiguous()
+            # the kernel stages the bias tile next to P in shared memory in the compute dtype
+            bias = bias.to(q.dtype).contiguous()
         if key_padding_mask is not None:
             key_padding_mask = key_padding_mask.to(torch.bool).contiguous()
         return _FusedAttentionFn.apply(q, k, v, bias, key_padding_mask, dropout_p, training, scale)
     return attention_reference(q, k, v, bias, key_padding_mask, dropout_p, training, scale)
+
+
+def fused_attention_qkvpacked(qkv, bias=None, key_padding_mask=None, dropout_p=0.0, training=True, scale=None):
+    """Self-attention on the packed in_proj output ``qkv [B, L, 3, H, D]`` (returns ``[B, L, H, D]``)."""
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    if scale is None:
+        scale = 1.0 / math.sqrt(q.shape[-1])
+    if qkv.is_contiguous() and fused_attention_supported(q, k, v, bias, key_padding_mask):
+        if bias is not None:
+            bias = bias.to(q.dtype).contiguous()
+        if key_padding_mask is not None:
+            key_padding_mask = key_padding_mask.to(torch.bool).contiguous()
+        return _FusedAttentionPackedFn.apply(qkv, bias, key_padding_mask, dropout_p, training, scale)
+    return fused_attention(q, k, v, bias, key_padding_mask, dropout_p, training, scale)
