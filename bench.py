@@ -237,7 +237,6 @@ def build_trainer(a, impl, world, rank, local_rank):
     model = task.build_model(args)
     loss = task.build_loss(args)
     trainer = Trainer(args, task, model, loss)
-    trainer.init_total_train_steps_ = None
     trainer._total_train_steps = args.max_update  # what init_total_train_steps() would set
     return args, task, trainer
 

@@ -67,15 +67,16 @@ void launch_ema(float* ema, const float* p, long long n, float decay, cudaStream
 // ---- LayerNorm / RMSNorm -----------------------------------------------------------------------------------
 void launch_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
                           int rows, int cols, float eps, int dtype, cudaStream_t stream);
-// dgamma_part/dbeta_part: float[parts * cols] scratch; counter zeroed; dgamma/dbeta in `dtype`
-int norm_bwd_parts(int rows, int cols);
+// part: float[3 * norm_bwd_parts(...) * cols] scratch (per-CTA partial column sums); dgamma/dbeta in `dtype`
+int norm_bwd_parts(int rows, int cols, int dtype);
+bool norm_v2_supported(int cols, int dtype);  // geometries for which the fused op can also emit dbias
 void launch_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
-                          void* dx, void* dgamma, void* dbeta, float* dgamma_part, float* dbeta_part,
-                          unsigned* counter, int rows, int cols, int dtype, cudaStream_t stream);
+                          void* dx, void* dgamma, void* dbeta, float* part, int rows, int cols, int dtype,
+                          cudaStream_t stream);
 void launch_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int rows, int cols, float eps,
                         int dtype, cudaStream_t stream);
 void launch_rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* gamma, void* dx, void* dgamma,
-                        float* dgamma_part, unsigned* counter, int rows, int cols, int dtype, cudaStream_t stream);
+                        float* part, int rows, int cols, int dtype, cudaStream_t stream);
 
 // ---- softmax + dropout ---------------------------------------------------------------------------------------
 // x: [rows, K] overwritten with softmax probabilities; out: dropout result (may alias x when p == 0)
@@ -90,25 +91,26 @@ void launch_softmax_dropout_bwd(const void* dy, void* dx, const void* probs, lon
 // ---- fused element-wise ---------------------------------------------------------------------------------------
 void launch_bias_gelu_fwd(const void* x, const void* bias, void* y, long long rows, int cols, int dtype,
                           cudaStream_t stream);
-void launch_bias_gelu_bwd(const void* dy, const void* x, const void* bias, void* dx, long long rows, int cols,
-                          int dtype, cudaStream_t stream);
+// dbias (nullable) = column sums of dx; part = float[bias_gelu_parts(rows, cols) * cols] scratch
+int bias_gelu_parts(long long rows, int cols);
+void launch_bias_gelu_bwd(const void* dy, const void* x, const void* bias, void* dx, void* dbias, float* part,
+                          long long rows, int cols, int dtype, cudaStream_t stream);
 // y = LN(residual + dropout(x + bias)); summed = residual + dropout(x + bias) (saved for backward)
 void launch_bias_dropout_add_ln_fwd(const void* x, const void* bias, const void* residual, const void* gamma,
                                     const void* beta, void* y, void* summed, float* mean, float* rstd, int rows,
                                     int cols, float p, float eps, unsigned long long seed, unsigned long long offset,
                                     int dtype, cudaStream_t stream);
-// dsum = dLN(dy); dx = dropout_mask * dsum / (1-p)
+// dsum = dLN(dy); dx = dropout_mask * dsum / (1-p); dbias (nullable) = column sums of dx
 void launch_bias_dropout_add_ln_bwd(const void* dy, const void* summed, const float* mean, const float* rstd,
                                     const void* gamma, void* dsum, void* dx, void* dgamma, void* dbeta,
-                                    float* dgamma_part, float* dbeta_part, unsigned* counter, int rows, int cols,
-                                    float p, unsigned long long seed, unsigned long long offset, int dtype,
-                                    cudaStream_t stream);
+                                    void* dbias, float* part, int rows, int cols, float p, unsigned long long seed,
+                                    unsigned long long offset, int dtype, cudaStream_t stream);
 // loss_rows[i] = lse_i - logit_i[target_i] (0 when target == ignore_index); lse saved for backward
 void launch_softmax_xent_fwd(const void* logits, const long long* target, float* loss_rows, float* lse, int rows,
-                             int cols, long long ignore_index, int dtype, cudaStream_t stream);
+                             int cols, int stride, long long ignore_index, int dtype, cudaStream_t stream);
 // dlogits = (softmax - onehot) * dloss (0 for ignored rows), written in `dtype`
 void launch_softmax_xent_bwd(const void* logits, const long long* target, const float* lse, const float* dloss,
-                             void* dlogits, int rows, int cols, long long ignore_index, int dtype,
+                             void* dlogits, int rows, int cols, int stride, long long ignore_index, int dtype,
                              cudaStream_t stream);
 
 }  // namespace ub

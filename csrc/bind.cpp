@@ -227,12 +227,11 @@ std::tuple<Tensor, Tensor, Tensor> layernorm_bwd(const Tensor& dy, const Tensor&
   const int rows = (int)x.size(0), cols = (int)x.size(1);
   Tensor dx = torch::empty_like(x);
   Tensor dgamma = torch::empty_like(gamma), dbeta = torch::empty_like(gamma);
-  const int parts = ub::norm_bwd_parts(rows, cols);
-  Tensor part = torch::empty({2, parts, cols}, x.options().dtype(at::kFloat));
+  const int parts = ub::norm_bwd_parts(rows, cols, dtype_tag(x));
+  Tensor part = torch::empty({3, parts, cols}, x.options().dtype(at::kFloat));
   ub::launch_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
                            gamma.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                           part.data_ptr<float>(), part.data_ptr<float>() + (size_t)parts * cols, nullptr, rows, cols,
-                           dtype_tag(x), cur_stream());
+                           part.data_ptr<float>(), rows, cols, dtype_tag(x), cur_stream());
   check_launch("layernorm_bwd");
   return {dx, dgamma, dbeta};
 }
@@ -258,10 +257,10 @@ std::tuple<Tensor, Tensor> rmsnorm_bwd(const Tensor& dy, const Tensor& x, const 
   const int rows = (int)x.size(0), cols = (int)x.size(1);
   Tensor dx = torch::empty_like(x);
   Tensor dgamma = torch::empty_like(gamma);
-  const int parts = ub::norm_bwd_parts(rows, cols);
-  Tensor part = torch::empty({parts, cols}, x.options().dtype(at::kFloat));
+  const int parts = ub::norm_bwd_parts(rows, cols, dtype_tag(x));
+  Tensor part = torch::empty({3, parts, cols}, x.options().dtype(at::kFloat));
   ub::launch_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), rstd.data_ptr<float>(), gamma.data_ptr(), dx.data_ptr(),
-                         dgamma.data_ptr(), part.data_ptr<float>(), nullptr, rows, cols, dtype_tag(x), cur_stream());
+                         dgamma.data_ptr(), part.data_ptr<float>(), rows, cols, dtype_tag(x), cur_stream());
   check_launch("rmsnorm_bwd");
   return {dx, dgamma};
 }
@@ -334,16 +333,26 @@ Tensor bias_gelu_fwd(const Tensor& x, const OptTensor& bias) {
   return y;
 }
 
-Tensor bias_gelu_bwd(const Tensor& dy, const Tensor& x, const OptTensor& bias) {
+// returns (dx, dbias); dbias (column sums of dx, produced by the same pass) only when a bias was given
+std::tuple<Tensor, OptTensor> bias_gelu_bwd(const Tensor& dy, const Tensor& x, const OptTensor& bias) {
   check_cuda_contig(dy, "dy");
   check_cuda_contig(x, "x");
   const c10::cuda::CUDAGuard guard(x.device());
   const int cols = (int)x.size(-1);
+  const long long rows = x.numel() / cols;
   Tensor dx = torch::empty_like(x);
-  ub::launch_bias_gelu_bwd(dy.data_ptr(), x.data_ptr(), opt_ptr(bias), dx.data_ptr(), x.numel() / cols, cols,
-                           dtype_tag(x), cur_stream());
+  OptTensor dbias;
+  Tensor part;
+  const bool has_bias = bias.has_value() && bias->defined();
+  if (has_bias) {
+    dbias = torch::empty_like(*bias);
+    part = torch::empty({ub::bias_gelu_parts(rows, cols), cols}, x.options().dtype(at::kFloat));
+  }
+  ub::launch_bias_gelu_bwd(dy.data_ptr(), x.data_ptr(), opt_ptr(bias), dx.data_ptr(),
+                           has_bias ? dbias->data_ptr() : nullptr, has_bias ? part.data_ptr<float>() : nullptr, rows,
+                           cols, dtype_tag(x), cur_stream());
   check_launch("bias_gelu_bwd");
-  return dx;
+  return {dx, dbias};
 }
 
 std::tuple<Tensor, Tensor, Tensor, Tensor, int64_t, int64_t> bias_dropout_add_ln_fwd(
@@ -372,10 +381,13 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, int64_t, int64_t> bias_dropout_add_ln
   return {y, mean, rstd, summed, (int64_t)seed, (int64_t)offset};
 }
 
-std::tuple<Tensor, Tensor, Tensor, Tensor> bias_dropout_add_ln_bwd(const Tensor& dy, const Tensor& summed,
-                                                                   const Tensor& mean, const Tensor& rstd,
-                                                                   const Tensor& gamma, double p, int64_t seed,
-                                                                   int64_t offset) {
+// returns (dsum, dx, dgamma, dbeta, dbias); dbias is undefined unless `need_dbias` and the geometry allows
+// the in-kernel column sums (the caller then reduces dx itself)
+std::tuple<Tensor, Tensor, Tensor, Tensor, OptTensor> bias_dropout_add_ln_bwd(const Tensor& dy, const Tensor& summed,
+                                                                              const Tensor& mean, const Tensor& rstd,
+                                                                              const Tensor& gamma, double p,
+                                                                              int64_t seed, int64_t offset,
+                                                                              bool need_dbias) {
   check_cuda_contig(dy, "dy");
   check_cuda_contig(summed, "summed");
   const c10::cuda::CUDAGuard guard(dy.device());
@@ -383,41 +395,49 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> bias_dropout_add_ln_bwd(const Tensor&
   Tensor dsum = torch::empty_like(summed);
   Tensor dx = p > 0.0 ? torch::empty_like(summed) : dsum;
   Tensor dgamma = torch::empty_like(gamma), dbeta = torch::empty_like(gamma);
-  const int parts = ub::norm_bwd_parts(rows, cols);
-  Tensor part = torch::empty({2, parts, cols}, summed.options().dtype(at::kFloat));
+  const int parts = ub::norm_bwd_parts(rows, cols, dtype_tag(summed));
+  Tensor part = torch::empty({3, parts, cols}, summed.options().dtype(at::kFloat));
+  OptTensor dbias;
+  if (need_dbias && ub::norm_v2_supported(cols, dtype_tag(summed))) dbias = torch::empty_like(gamma);
   ub::launch_bias_dropout_add_ln_bwd(dy.data_ptr(), summed.data_ptr(), mean.data_ptr<float>(),
                                      rstd.data_ptr<float>(), gamma.data_ptr(), dsum.data_ptr(), dx.data_ptr(),
-                                     dgamma.data_ptr(), dbeta.data_ptr(), part.data_ptr<float>(),
-                                     part.data_ptr<float>() + (size_t)parts * cols, nullptr, rows, cols, (float)p,
-                                     (uint64_t)seed, (uint64_t)offset, dtype_tag(summed), cur_stream());
+                                     dgamma.data_ptr(), dbeta.data_ptr(), dbias.has_value() ? dbias->data_ptr() : nullptr,
+                                     part.data_ptr<float>(), rows, cols, (float)p, (uint64_t)seed, (uint64_t)offset,
+                                     dtype_tag(summed), cur_stream());
   check_launch("bias_dropout_add_ln_bwd");
-  return {dsum, dx, dgamma, dbeta};
+  return {dsum, dx, dgamma, dbeta, dbias};
 }
 
-std::tuple<Tensor, Tensor> softmax_xent_fwd(const Tensor& logits, const Tensor& target, int64_t ignore_index) {
+// `logits` is [rows, stride] contiguous of which the first `valid_cols` columns are the vocabulary (the
+// rest is GEMM-alignment padding); valid_cols <= 0 means all columns.
+std::tuple<Tensor, Tensor> softmax_xent_fwd(const Tensor& logits, const Tensor& target, int64_t ignore_index,
+                                            int64_t valid_cols) {
   check_cuda_contig(logits, "logits");
   check_cuda_contig(target, "target");
   TORCH_CHECK(logits.dim() == 2 && target.dim() == 1 && target.size(0) == logits.size(0));
   TORCH_CHECK(target.scalar_type() == at::kLong);
+  TORCH_CHECK(valid_cols <= logits.size(1));
   const c10::cuda::CUDAGuard guard(logits.device());
-  const int rows = (int)logits.size(0), cols = (int)logits.size(1);
+  const int rows = (int)logits.size(0), stride = (int)logits.size(1);
+  const int cols = valid_cols > 0 ? (int)valid_cols : stride;
   Tensor loss = torch::empty({rows}, logits.options().dtype(at::kFloat));
   Tensor lse = torch::empty({rows}, logits.options().dtype(at::kFloat));
   ub::launch_softmax_xent_fwd(logits.data_ptr(), (const long long*)target.data_ptr<int64_t>(), loss.data_ptr<float>(),
-                              lse.data_ptr<float>(), rows, cols, ignore_index, dtype_tag(logits), cur_stream());
+                              lse.data_ptr<float>(), rows, cols, stride, ignore_index, dtype_tag(logits), cur_stream());
   check_launch("softmax_xent_fwd");
   return {loss, lse};
 }
 
 Tensor softmax_xent_bwd(const Tensor& logits, const Tensor& target, const Tensor& lse, const Tensor& dloss,
-                        int64_t ignore_index) {
+                        int64_t ignore_index, int64_t valid_cols) {
   check_cuda_contig(logits, "logits");
   TORCH_CHECK(dloss.is_cuda() && dloss.scalar_type() == at::kFloat && dloss.numel() == 1);
   const c10::cuda::CUDAGuard guard(logits.device());
-  const int rows = (int)logits.size(0), cols = (int)logits.size(1);
+  const int rows = (int)logits.size(0), stride = (int)logits.size(1);
+  const int cols = valid_cols > 0 ? (int)valid_cols : stride;
   Tensor dlogits = torch::empty_like(logits);
   ub::launch_softmax_xent_bwd(logits.data_ptr(), (const long long*)target.data_ptr<int64_t>(), lse.data_ptr<float>(),
-                              dloss.data_ptr<float>(), dlogits.data_ptr(), rows, cols, ignore_index,
+                              dloss.data_ptr<float>(), dlogits.data_ptr(), rows, cols, stride, ignore_index,
                               dtype_tag(logits), cur_stream());
   check_launch("softmax_xent_bwd");
   return dlogits;

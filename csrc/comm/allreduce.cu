@@ -25,29 +25,41 @@ constexpr int kCommThreads = 512;
 
 // ---- cross-GPU flag barrier (CAS put / CAS take: self-resetting, safe for back-to-back use) -----------------
 UB_DEVICE void flag_put(uint32_t* addr) {
-  while (atomicCAS_system(addr, 0u, 1u) != 0u) {
-  }
+  while (atomicCAS_system(addr, 0u, 1u) != 0u) __nanosleep(32);
 }
 UB_DEVICE void flag_take(uint32_t* addr) {
   const long long t0 = clock64();
   while (atomicCAS_system(addr, 1u, 0u) != 1u) {
+    __nanosleep(32);  // keep the polling traffic off the links the data kernels of other buckets use
     if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a peer died; do not hang the GPU forever
   }
 }
 
-// All ranks' CTA `blockIdx.x` meet. Slot layout in every rank's flag buffer: [block][sender rank].
-UB_DEVICE void block_barrier(const CommPeers& peers, bool release_first) {
+// All ranks' CTAs that use flag slot `slot` meet. Slot layout in every rank's flag buffer: [slot][sender].
+UB_DEVICE void slot_barrier(const CommPeers& peers, int slot, bool release_first) {
   if (release_first) __threadfence_system();
   __syncthreads();
   if (threadIdx.x < (unsigned)peers.world) {
     const int t = threadIdx.x;
-    uint32_t* remote = reinterpret_cast<uint32_t*>(peers.flags[t]) + blockIdx.x * peers.world + peers.rank;
-    uint32_t* mine = reinterpret_cast<uint32_t*>(peers.flags[peers.rank]) + blockIdx.x * peers.world + t;
+    uint32_t* remote = reinterpret_cast<uint32_t*>(peers.flags[t]) + slot * peers.world + peers.rank;
+    uint32_t* mine = reinterpret_cast<uint32_t*>(peers.flags[peers.rank]) + slot * peers.world + t;
     flag_put(remote);
     flag_take(mine);
   }
   __syncthreads();
   __threadfence_system();
+}
+UB_DEVICE void block_barrier(const CommPeers& peers, bool release_first) {
+  slot_barrier(peers, blockIdx.x, release_first);
+}
+
+// Rendezvous of the ranks before a data kernel: ONE warp per GPU waits until every peer's stream has
+// reached the same point (i.e. its producer kernels have finished).  Ranks are skewed by up to a few
+// hundred microseconds inside a backward pass; parking that wait in a 32-thread kernel instead of in
+// the data kernel's CTAs leaves the SMs to the compute kernels the reduction overlaps with.
+constexpr int kHandshakeSlot = kMaxCommBlocks - 1;
+__global__ void __launch_bounds__(32) symm_handshake_kernel(CommPeers peers) {
+  slot_barrier(peers, kHandshakeSlot, /*release_first=*/false);
 }
 
 template <typename T>
@@ -60,49 +72,85 @@ UB_DEVICE void acc_add(float (&acc)[16 / sizeof(T)], const Vec16& v) {
 
 // ---- one-shot / two-shot ------------------------------------------------------------------------------------------
 // Range = [begin_vec, end_vec) in 16-byte vectors relative to each buffer base.
-template <typename T, bool kTwoShot>
-__global__ void __launch_bounds__(kCommThreads) allreduce_p2p_kernel(CommPeers peers, long long begin_vec,
-                                                                       long long end_vec, float scale) {
-  constexpr int EPV = 16 / sizeof(T);
-  block_barrier(peers, /*release_first=*/false);  // every rank's producer kernels have finished
+constexpr int kCommUnroll = 4;  // vectors per thread in flight per peer (NVLink latency ~2-3 us)
 
-  long long lo = begin_vec, hi = end_vec;
-  if (kTwoShot) {
-    const long long n = end_vec - begin_vec;
-    const long long per = (n + peers.world - 1) / peers.world;
-    lo = begin_vec + per * peers.rank;
-    hi = lo + per < end_vec ? lo + per : end_vec;
-    if (lo > end_vec) lo = end_vec;
-  }
-  const long long stride = (long long)gridDim.x * kCommThreads;
-  for (long long v = lo + (long long)blockIdx.x * kCommThreads + threadIdx.x; v < hi; v += stride) {
+// One-shot, in place: every rank reads the whole range from every peer, so nobody may store its result
+// before all peers have finished reading - the grid covers the range with ONE vector per thread, the
+// reduced value waits in registers across a second barrier.  (Host guarantees grid * 512 >= vectors.)
+template <typename T>
+__global__ void __launch_bounds__(kCommThreads) allreduce_oneshot_kernel(CommPeers peers, long long begin_vec,
+                                                                          long long end_vec, float scale) {
+  constexpr int EPV = 16 / sizeof(T);
+  // (the handshake kernel ahead of us in the stream established that every rank's producers finished)
+  const long long v = begin_vec + (long long)blockIdx.x * kCommThreads + threadIdx.x;
+  const bool active = v < end_vec;
+  float acc[EPV];
+#pragma unroll
+  for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
+  if (active) {
     Vec16 in[kMaxPeers];
 #pragma unroll
     for (int p = 0; p < kMaxPeers; ++p) {
       if (p < peers.world) in[p] = ld_global_v4(reinterpret_cast<const uint8_t*>(peers.buf[p]) + v * 16);
     }
-    float acc[EPV];
-#pragma unroll
-    for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
 #pragma unroll
     for (int p = 0; p < kMaxPeers; ++p) {
       if (p < peers.world) acc_add<T>(acc, in[p]);
     }
+  }
+  block_barrier(peers, /*release_first=*/false);  // all peers hold their sums in registers
+  if (active) {
 #pragma unroll
     for (int e = 0; e < EPV; ++e) acc[e] *= scale;
-    const Vec16 out = pack<T>(acc);
-    if (kTwoShot) {
+    st_global_v4(reinterpret_cast<uint8_t*>(peers.buf[peers.rank]) + v * 16, pack<T>(acc));
+  }
+}
+
+// Two-shot: rank r owns slice r: reduce-scatter by peer loads, all-gather by peer stores.
+// W = compile-time bound on the world size (2 / 4 / 8); W * kU = 16 peer vectors in flight per thread.
+template <typename T, int W>
+__global__ void __launch_bounds__(kCommThreads) allreduce_twoshot_kernel(CommPeers peers, long long begin_vec,
+                                                                          long long end_vec, float scale) {
+  constexpr int EPV = 16 / sizeof(T);
+  constexpr int kU = 16 / W;
+  const long long n = end_vec - begin_vec;
+  const long long per = (n + peers.world - 1) / peers.world;
+  long long lo = begin_vec + per * peers.rank;
+  const long long hi = lo + per < end_vec ? lo + per : end_vec;
+  if (lo > end_vec) lo = end_vec;
+  const long long stride = (long long)gridDim.x * kCommThreads;
+  for (long long v0 = lo + (long long)blockIdx.x * kCommThreads + threadIdx.x; v0 < hi; v0 += stride * kU) {
+    Vec16 in[kU][W];
 #pragma unroll
-      for (int p = 0; p < kMaxPeers; ++p) {
-        if (p < peers.world) st_global_v4(reinterpret_cast<uint8_t*>(peers.buf[p]) + v * 16, out);
+    for (int u = 0; u < kU; ++u) {
+      const long long v = v0 + u * stride;
+#pragma unroll
+      for (int p = 0; p < W; ++p) {
+        if (p < peers.world && v < hi) in[u][p] = ld_global_v4(reinterpret_cast<const uint8_t*>(peers.buf[p]) + v * 16);
       }
-    } else {
-      st_global_v4(reinterpret_cast<uint8_t*>(peers.buf[peers.rank]) + v * 16, out);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long v = v0 + u * stride;
+      if (v < hi) {
+        float acc[EPV];
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int p = 0; p < W; ++p) {
+          if (p < peers.world) acc_add<T>(acc, in[u][p]);
+        }
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[e] *= scale;
+        const Vec16 out = pack<T>(acc);
+#pragma unroll
+        for (int p = 0; p < W; ++p) {
+          if (p < peers.world) st_global_v4(reinterpret_cast<uint8_t*>(peers.buf[p]) + v * 16, out);
+        }
+      }
     }
   }
-  // two-shot: my stores must be visible at the peers; one-shot: nobody may overwrite its buffer
-  // (next backward) while a peer is still reading it
-  block_barrier(peers, /*release_first=*/true);
+  block_barrier(peers, /*release_first=*/true);  // my stores are visible at the peers before anyone proceeds
 }
 
 // ---- NVLS (multimem) --------------------------------------------------------------------------------------------------
@@ -145,7 +193,6 @@ template <typename T>
 __global__ void __launch_bounds__(kCommThreads) allreduce_nvls_kernel(CommPeers peers, long long begin_vec,
                                                                         long long end_vec, float scale) {
   constexpr int EPV = 16 / sizeof(T);
-  block_barrier(peers, false);
   const long long n = end_vec - begin_vec;
   const long long per = (n + peers.world - 1) / peers.world;
   long long lo = begin_vec + per * peers.rank;
@@ -153,16 +200,27 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_nvls_kernel(CommPeers 
   if (lo > end_vec) lo = end_vec;
   uint8_t* mc = reinterpret_cast<uint8_t*>(peers.multicast);
   const long long stride = (long long)gridDim.x * kCommThreads;
-  for (long long v = lo + (long long)blockIdx.x * kCommThreads + threadIdx.x; v < hi; v += stride) {
-    Vec16 r = multimem_ld_reduce<T>(mc + v * 16);
-    if (scale != 1.f) {
-      float acc[EPV];
-      unpack<T>(r, acc);
+  for (long long v0 = lo + (long long)blockIdx.x * kCommThreads + threadIdx.x; v0 < hi; v0 += stride * kCommUnroll) {
+    Vec16 r[kCommUnroll];
 #pragma unroll
-      for (int e = 0; e < EPV; ++e) acc[e] *= scale;
-      r = pack<T>(acc);
+    for (int u = 0; u < kCommUnroll; ++u) {
+      const long long v = v0 + u * stride;
+      if (v < hi) r[u] = multimem_ld_reduce<T>(mc + v * 16);
     }
-    multimem_st(mc + v * 16, r);
+#pragma unroll
+    for (int u = 0; u < kCommUnroll; ++u) {
+      const long long v = v0 + u * stride;
+      if (v < hi) {
+        if (scale != 1.f) {
+          float acc[EPV];
+          unpack<T>(r[u], acc);
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) acc[e] *= scale;
+          r[u] = pack<T>(acc);
+        }
+        multimem_st(mc + v * 16, r[u]);
+      }
+    }
   }
   block_barrier(peers, true);
 }
@@ -171,12 +229,18 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_nvls_kernel(CommPeers 
 template <typename T>
 static void run_allreduce(const CommPeers& peers, long long begin_vec, long long end_vec, float scale, int algo,
                           int blocks, cudaStream_t stream) {
+  symm_handshake_kernel<<<1, 32, 0, stream>>>(peers);
   if (algo == kAlgoNvls) {
     allreduce_nvls_kernel<T><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
   } else if (algo == kAlgoTwoShot) {
-    allreduce_p2p_kernel<T, true><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
+    if (peers.world <= 2)
+      allreduce_twoshot_kernel<T, 2><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
+    else if (peers.world <= 4)
+      allreduce_twoshot_kernel<T, 4><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
+    else
+      allreduce_twoshot_kernel<T, 8><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
   } else {
-    allreduce_p2p_kernel<T, false><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
+    allreduce_oneshot_kernel<T><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
   }
 }
 
@@ -192,8 +256,14 @@ void launch_allreduce(const CommPeers& peers, long long byte_offset, long long b
   if (end_vec <= begin_vec) return;
   if (algo == kAlgoAuto) algo = pick_allreduce_algo(bytes, peers.world, peers.multicast != nullptr);
   if (algo == kAlgoNvls && peers.multicast == nullptr) algo = kAlgoTwoShot;
-  if (blocks <= 0) blocks = (algo == kAlgoOneShot && bytes <= 64 * 1024) ? 4 : 32;
-  if (blocks > kMaxCommBlocks) blocks = kMaxCommBlocks;
+  const long long one_shot_blocks = (end_vec - begin_vec + kCommThreads - 1) / kCommThreads;
+  if (algo == kAlgoOneShot && one_shot_blocks > kMaxCommBlocks - 1) algo = kAlgoTwoShot;  // range too large
+  if (algo == kAlgoOneShot) {
+    blocks = (int)one_shot_blocks;  // exactly one vector per thread (see kernel)
+  } else {
+    if (blocks <= 0) blocks = 24;
+    if (blocks > kMaxCommBlocks - 1) blocks = kMaxCommBlocks - 1;  // the last slot belongs to the handshake
+  }
   if (dtype == kF32) run_allreduce<float>(peers, begin_vec, end_vec, scale, algo, blocks, stream);
   else if (dtype == kF16) run_allreduce<__half>(peers, begin_vec, end_vec, scale, algo, blocks, stream);
   else run_allreduce<__nv_bfloat16>(peers, begin_vec, end_vec, scale, algo, blocks, stream);

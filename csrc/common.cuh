@@ -132,6 +132,42 @@ UB_DEVICE Vec16 pack<__nv_bfloat16>(const float* in) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 - two fp32 lanes per issued instruction);
+// used where a kernel is issue-bound rather than bandwidth-bound (GELU, softmax statistics).
+// ------------------------------------------------------------------------------------------------
+struct alignas(8) F2 {
+  float x, y;
+};
+UB_DEVICE unsigned long long f2_bits(F2 a) { return *reinterpret_cast<unsigned long long*>(&a); }
+UB_DEVICE F2 f2_from_bits(unsigned long long b) { return *reinterpret_cast<F2*>(&b); }
+UB_DEVICE F2 f2(float a) { return F2{a, a}; }
+UB_DEVICE F2 fma2(F2 a, F2 b, F2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return f2_from_bits(d);
+}
+UB_DEVICE F2 mul2(F2 a, F2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from_bits(d);
+}
+UB_DEVICE F2 add2(F2 a, F2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from_bits(d);
+}
+UB_DEVICE float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+UB_DEVICE float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ------------------------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------------------------
 UB_DEVICE float warp_sum(float v) {

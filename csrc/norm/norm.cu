@@ -9,6 +9,8 @@
 //   * backward reads x and dy ONCE and emits dx plus per-CTA partial dgamma/dbeta (fp32), which a
 //     small second kernel reduces deterministically (reference: x, dy read twice + 2 extra kernels);
 //   * fp32 statistics, biased variance, rstd = rsqrt(var + eps).
+#include <type_traits>
+
 #include "../api.h"
 #include "../common.cuh"
 
@@ -294,6 +296,321 @@ __global__ void __launch_bounds__(256) norm_param_grad_kernel(const float* __res
   }
 }
 
+// ================================================================================================
+// v2 kernels (rows of up to 384 16-byte vectors, i.e. every hidden size in practice).
+//
+// The v1 kernels above keep VPT vectors per thread, which for hidden = 768 costs 170 registers in
+// the backward (dgamma/dbeta accumulators scale with VPT) -> 8 warps per SM and stop-and-go loads;
+// ncu showed them at ~30 % of HBM bandwidth.  Here a thread owns exactly ONE vector column (so the
+// accumulators are 8 floats each), a row is owned by ceil32(nvec) threads, and memory-level
+// parallelism comes from R consecutive rows kept in flight per thread instead.
+// ================================================================================================
+constexpr int kNormV2Threads = 384;
+constexpr int kNormV2Warps = kNormV2Threads / 32;
+
+struct NormGeom2 {
+  int rows, cols, tpr, nvec, groups;  // blockDim.x = tpr * groups
+};
+
+template <int NVAL>
+UB_DEVICE void group_sum2(float (&v)[NVAL], int tpr, float* scratch) {
+  const int lim = tpr < 32 ? tpr : 32;
+#pragma unroll
+  for (int k = 0; k < NVAL; ++k) {
+    for (int o = lim >> 1; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  }
+  if (tpr > 32) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpg = tpr >> 5;
+    const int gfirst = (warp / wpg) * wpg;
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < NVAL; ++k) scratch[k * kNormV2Warps + warp] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NVAL; ++k) {
+      float s = 0.f;
+      for (int w = 0; w < wpg; ++w) s += scratch[k * kNormV2Warps + gfirst + w];
+      v[k] = s;
+    }
+  }
+}
+
+template <typename T, int R, bool kRMS, bool kFused>
+__global__ void __launch_bounds__(kNormV2Threads, 2) norm_fwd_v2_kernel(
+    const T* __restrict__ x, const T* __restrict__ gamma, const T* __restrict__ beta, T* __restrict__ y,
+    float* __restrict__ mean_out, float* __restrict__ rstd_out, NormGeom2 g, float eps,
+    const T* __restrict__ bias, const T* __restrict__ residual, T* __restrict__ summed, float p, float keep_scale,
+    unsigned long long seed, unsigned long long offset) {
+  constexpr int EPV = VecTraits<T>::kElems;
+  __shared__ float scratch[R * kNormV2Warps];
+  const int tpr = g.tpr;
+  const int grp = threadIdx.x / tpr, j = threadIdx.x - grp * tpr;
+  const bool col_ok = j < g.nvec;
+  const float inv_cols = 1.f / (float)g.cols;
+  const uint32_t thresh = kFused ? dropout_thresh16(p) : 0u;
+
+  float gam[EPV], bet[EPV], bia[EPV];
+#pragma unroll
+  for (int e = 0; e < EPV; ++e) gam[e] = bet[e] = bia[e] = 0.f;
+  if (col_ok) {
+    unpack<T>(ldv(gamma + j * EPV), gam);
+    if (!kRMS) unpack<T>(ldv(beta + j * EPV), bet);
+    if (kFused && bias != nullptr) unpack<T>(ldv(bias + j * EPV), bia);
+  }
+
+  const int rows_per_iter = gridDim.x * g.groups * R;
+  const int n_iters = (g.rows + rows_per_iter - 1) / rows_per_iter;
+  for (int it = 0; it < n_iters; ++it) {
+    const int row0 = ((it * gridDim.x + blockIdx.x) * g.groups + grp) * R;
+    Vec16 xv[R], rv[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      if (col_ok && row0 + i < g.rows) {
+        const size_t off = (size_t)(row0 + i) * g.cols + (size_t)j * EPV;
+        xv[i] = ld_global_nc_v4(x + off);
+        if (kFused) rv[i] = ld_global_nc_v4(residual + off);
+      }
+    }
+    float xs[R][EPV];
+    float acc[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      acc[i] = 0.f;
+      if (col_ok && row0 + i < g.rows) {
+        unpack<T>(xv[i], xs[i]);
+        if (kFused) {
+          const size_t off = (size_t)(row0 + i) * g.cols + (size_t)j * EPV;
+          float res[EPV];
+          unpack<T>(rv[i], res);
+          uint32_t keep = 0xffu;
+          if (p > 0.f) keep = dropout_keep8(seed, offset, off / 8, thresh);
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) {
+            const float h = (xs[i][e] + bia[e]) * (((keep >> e) & 1u) ? keep_scale : 0.f);
+            // round the sum to T first: backward and the pre-LN consumer see exactly this value
+            xs[i][e] = to_f32<T>(from_f32<T>(res[e] + h));
+          }
+          st_global_v4(summed + off, pack<T>(xs[i]));
+        }
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[i] += kRMS ? xs[i][e] * xs[i][e] : xs[i][e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) xs[i][e] = 0.f;
+      }
+    }
+    group_sum2<R>(acc, tpr, scratch);
+    float mu[R], rs[R];
+    if (kRMS) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        mu[i] = 0.f;
+        rs[i] = rsqrtf(acc[i] * inv_cols + eps);
+      }
+    } else {
+      float var[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        mu[i] = acc[i] * inv_cols;
+        var[i] = 0.f;
+        if (col_ok) {
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) {
+            const float d = xs[i][e] - mu[i];
+            var[i] += d * d;
+          }
+        }
+      }
+      group_sum2<R>(var, tpr, scratch);
+#pragma unroll
+      for (int i = 0; i < R; ++i) rs[i] = rsqrtf(var[i] * inv_cols + eps);
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int row = row0 + i;
+      if (row < g.rows) {
+        if (j == 0) {
+          if (!kRMS) mean_out[row] = mu[i];
+          rstd_out[row] = rs[i];
+        }
+        if (col_ok) {
+          float o[EPV];
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) {
+            const float xh = (xs[i][e] - mu[i]) * rs[i];
+            o[e] = kRMS ? xh * gam[e] : xh * gam[e] + bet[e];
+          }
+          st_global_v4(y + (size_t)row * g.cols + (size_t)j * EPV, pack<T>(o));
+        }
+      }
+    }
+  }
+}
+
+// Backward.  part = [3][gridDim.x][cols] fp32 partial column sums: dgamma, dbeta, and (fused op with a
+// bias) dbias = column sums of the dropout-masked gradient, which saves a separate reduction pass.
+template <typename T, int R, bool kRMS, bool kFused>
+__global__ void __launch_bounds__(kNormV2Threads, 2) norm_bwd_v2_kernel(
+    const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const T* __restrict__ gamma, T* __restrict__ dx, float* __restrict__ part,
+    NormGeom2 g, T* __restrict__ dx_drop, int want_dbias, float p, float keep_scale, unsigned long long seed,
+    unsigned long long offset) {
+  constexpr int EPV = VecTraits<T>::kElems;
+  extern __shared__ float sm_acc[];  // [3][cols]
+  __shared__ float scratch[2 * R * kNormV2Warps];
+  const int tpr = g.tpr;
+  const int grp = threadIdx.x / tpr, j = threadIdx.x - grp * tpr;
+  const bool col_ok = j < g.nvec;
+  const float inv_cols = 1.f / (float)g.cols;
+  const uint32_t thresh = kFused ? dropout_thresh16(p) : 0u;
+
+  float gam[EPV], dg[EPV], db[EPV], dbi[EPV];
+#pragma unroll
+  for (int e = 0; e < EPV; ++e) gam[e] = dg[e] = db[e] = dbi[e] = 0.f;
+  if (col_ok) unpack<T>(ldv(gamma + j * EPV), gam);
+
+  const int rows_per_iter = gridDim.x * g.groups * R;
+  const int n_iters = (g.rows + rows_per_iter - 1) / rows_per_iter;
+  for (int it = 0; it < n_iters; ++it) {
+    const int row0 = ((it * gridDim.x + blockIdx.x) * g.groups + grp) * R;
+    Vec16 xq[R], dq[R];
+    float mu[R], rs[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const bool ok = row0 + i < g.rows;
+      mu[i] = (ok && !kRMS) ? mean[row0 + i] : 0.f;
+      rs[i] = ok ? rstd[row0 + i] : 0.f;
+      if (ok && col_ok) {
+        const size_t off = (size_t)(row0 + i) * g.cols + (size_t)j * EPV;
+        xq[i] = ld_global_nc_v4(x + off);
+        dq[i] = ld_global_nc_v4(dy + off);
+      } else {
+        xq[i].w[0] = xq[i].w[1] = xq[i].w[2] = xq[i].w[3] = 0u;
+        dq[i] = xq[i];
+      }
+    }
+    float s[2 * R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float xv[EPV], dv[EPV];
+      unpack<T>(xq[i], xv);
+      unpack<T>(dq[i], dv);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) {
+        const float xh = (xv[e] - mu[i]) * rs[i];
+        const float gy = dv[e] * gam[e];
+        s0 += gy;
+        s1 += gy * xh;
+        dg[e] += dv[e] * xh;
+        if (!kRMS) db[e] += dv[e];
+      }
+      s[2 * i] = s0;
+      s[2 * i + 1] = s1;
+    }
+    group_sum2<2 * R>(s, tpr, scratch);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      if (col_ok && row0 + i < g.rows) {
+        const float m1 = kRMS ? 0.f : s[2 * i] * inv_cols, m2 = s[2 * i + 1] * inv_cols;
+        const size_t off = (size_t)(row0 + i) * g.cols + (size_t)j * EPV;
+        float xv[EPV], dv[EPV], o[EPV];
+        unpack<T>(xq[i], xv);
+        unpack<T>(dq[i], dv);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+          const float xh = (xv[e] - mu[i]) * rs[i];
+          o[e] = rs[i] * (dv[e] * gam[e] - m1 - xh * m2);
+        }
+        st_global_v4(dx + off, pack<T>(o));
+        if (kFused) {
+          uint32_t keep = 0xffu;
+          if (p > 0.f) keep = dropout_keep8(seed, offset, off / 8, thresh);
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) {
+            o[e] = ((keep >> e) & 1u) ? o[e] * keep_scale : 0.f;
+            dbi[e] += o[e];
+          }
+          if (dx_drop != dx) st_global_v4(dx_drop + off, pack<T>(o));
+        }
+      }
+    }
+  }
+
+  // Column sums across the row groups of this CTA, without shared-memory float atomics (those are
+  // CAS loops): groups that share a warp combine with shuffles, then one group (or warp) at a time
+  // adds its registers into the shared row.
+  const int narr = want_dbias ? 3 : (kRMS ? 1 : 2);
+  if (tpr < 32) {
+    for (int o = tpr; o < 32; o <<= 1) {
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) {
+        dg[e] += __shfl_xor_sync(0xffffffffu, dg[e], o);
+        db[e] += __shfl_xor_sync(0xffffffffu, db[e], o);
+        dbi[e] += __shfl_xor_sync(0xffffffffu, dbi[e], o);
+      }
+    }
+  }
+  const int n_owner = tpr < 32 ? (int)(blockDim.x >> 5) : g.groups;
+  const int my_owner = tpr < 32 ? (int)(threadIdx.x >> 5) : grp;
+  const bool writer = col_ok && (tpr >= 32 || (int)(threadIdx.x & 31) < tpr);
+  __syncthreads();
+  for (int w = 0; w < n_owner; ++w) {
+    if (writer && my_owner == w) {
+      float* a0 = sm_acc + j * EPV;
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) {
+        if (w == 0) {
+          a0[e] = dg[e];
+          a0[g.cols + e] = db[e];
+          if (want_dbias) a0[2 * g.cols + e] = dbi[e];
+        } else {
+          a0[e] += dg[e];
+          a0[g.cols + e] += db[e];
+          if (want_dbias) a0[2 * g.cols + e] += dbi[e];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int a = 0; a < 3; ++a) {
+    if (a == 1 && kRMS) continue;
+    if (a == 2 && !want_dbias) continue;
+    float* dst = part + ((size_t)a * gridDim.x + blockIdx.x) * g.cols;
+    for (int c = threadIdx.x; c < g.cols; c += blockDim.x) dst[c] = sm_acc[a * g.cols + c];
+  }
+  (void)narr;
+}
+
+// partial rows -> 16-bit column sums.  block = (32 columns) x (32 row slices); grid.y picks the array.
+template <typename T>
+__global__ void __launch_bounds__(1024) colsum_finalize_kernel(const float* __restrict__ part, int parts, int cols,
+                                                                 T* __restrict__ out0, T* __restrict__ out1,
+                                                                 T* __restrict__ out2) {
+  __shared__ float red[32][33];
+  T* out = blockIdx.y == 0 ? out0 : (blockIdx.y == 1 ? out1 : out2);
+  if (out == nullptr) return;
+  const float* src = part + (size_t)blockIdx.y * parts * cols;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  float a = 0.f;
+  if (col < cols) {
+#pragma unroll 4
+    for (int r = ry; r < parts; r += 32) a += src[(size_t)r * cols + col];
+  }
+  red[ry][cx] = a;
+  __syncthreads();
+  if (ry == 0 && col < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) s += red[r][cx];
+    out[col] = from_f32<T>(s);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -336,9 +653,36 @@ static int fwd_grid(const NormGeom& g) {
   return (int)(need < cap ? need : cap);
 }
 
-int norm_bwd_parts(int rows, int cols) {
-  // one partial row per CTA; 2 CTAs per SM keeps the finalize pass short
-  (void)cols;
+constexpr int kFwdR = 2, kBwdR = 2;
+
+static bool make_geom2(int rows, int cols, int epv, NormGeom2& g) {
+  g.rows = rows;
+  g.cols = cols;
+  g.nvec = cols / epv;
+  if (g.nvec < 1 || g.nvec > kNormV2Threads) return false;
+  g.tpr = g.nvec < 32 ? pow2ceil(g.nvec) : ((g.nvec + 31) / 32) * 32;
+  g.groups = kNormV2Threads / g.tpr;
+  return true;
+}
+
+static int v2_grid(const NormGeom2& g, int R) {
+  const long long need = ((long long)g.rows + (long long)g.groups * R - 1) / ((long long)g.groups * R);
+  const long long cap = (long long)sm_count() * 2;
+  const long long n = need < cap ? need : cap;
+  return (int)(n < 1 ? 1 : n);
+}
+
+static int dtype_epv(int dtype) { return dtype == kF32 ? 4 : 8; }
+
+bool norm_v2_supported(int cols, int dtype) {
+  NormGeom2 g;
+  return make_geom2(1, cols, dtype_epv(dtype), g);
+}
+
+int norm_bwd_parts(int rows, int cols, int dtype) {
+  // one fp32 partial row per CTA (x3 arrays); at most 2 CTAs per SM keeps the finalize pass short
+  NormGeom2 g;
+  if (make_geom2(rows, cols, dtype_epv(dtype), g)) return v2_grid(g, kBwdR);
   const long long cap = (long long)sm_count() * 2;
   const long long need = ((long long)rows + 7) / 8;
   long long n = need < cap ? need : cap;
@@ -366,10 +710,17 @@ template <typename T, bool kRMS, bool kFused>
 static void run_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows,
                     int cols, float eps, const void* bias, const void* residual, void* summed, float p,
                     unsigned long long seed, unsigned long long offset, cudaStream_t stream) {
+  const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  NormGeom2 g2;
+  if (make_geom2(rows, cols, VecTraits<T>::kElems, g2)) {
+    norm_fwd_v2_kernel<T, kFwdR, kRMS, kFused><<<v2_grid(g2, kFwdR), g2.tpr * g2.groups, 0, stream>>>(
+        (const T*)x, (const T*)gamma, (const T*)beta, (T*)y, mean, rstd, g2, eps, (const T*)bias, (const T*)residual,
+        (T*)summed, p, keep_scale, seed, offset);
+    return;
+  }
   int vpt;
   NormGeom g = make_geom(rows, cols, VecTraits<T>::kElems, vpt);
   const int grid = fwd_grid(g);
-  const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
   UB_DISPATCH_VPT(vpt, (norm_fwd_kernel<T, VPT, kRMS, kFused><<<grid, kNormThreads, 0, stream>>>(
                            (const T*)x, (const T*)gamma, (const T*)beta, (T*)y, mean, rstd, g, eps, (const T*)bias,
                            (const T*)residual, (T*)summed, p, keep_scale, seed, offset)));
@@ -377,13 +728,27 @@ static void run_fwd(const void* x, const void* gamma, const void* beta, void* y,
 
 template <typename T, bool kRMS, bool kFused>
 static void run_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma, void* dx,
-                    void* dgamma, void* dbeta, float* dg_part, float* db_part, int rows, int cols, void* dx_drop,
-                    float p, unsigned long long seed, unsigned long long offset, cudaStream_t stream) {
+                    void* dgamma, void* dbeta, void* dbias, float* part, int rows, int cols, void* dx_drop, float p,
+                    unsigned long long seed, unsigned long long offset, cudaStream_t stream) {
+  const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  NormGeom2 g2;
+  if (make_geom2(rows, cols, VecTraits<T>::kElems, g2)) {
+    const int grid = v2_grid(g2, kBwdR);
+    const size_t smem2 = (size_t)3 * cols * sizeof(float);
+    auto kern = norm_bwd_v2_kernel<T, kBwdR, kRMS, kFused>;
+    kern<<<grid, g2.tpr * g2.groups, smem2, stream>>>((const T*)dy, (const T*)x, mean, rstd, (const T*)gamma, (T*)dx,
+                                                       part, g2, (T*)dx_drop, dbias != nullptr ? 1 : 0, p, keep_scale,
+                                                       seed, offset);
+    colsum_finalize_kernel<T><<<dim3((cols + 31) / 32, 3), 1024, 0, stream>>>(part, grid, cols, (T*)dgamma, (T*)dbeta,
+                                                                              (T*)dbias);
+    return;
+  }
   int vpt;
   NormGeom g = make_geom(rows, cols, VecTraits<T>::kElems, vpt);
-  const int parts = norm_bwd_parts(rows, cols);
+  const int parts = norm_bwd_parts(rows, cols, std::is_same<T, float>::value ? kF32 : kF16);
+  float* dg_part = part;
+  float* db_part = part + (size_t)parts * cols;
   const size_t smem = (size_t)(kRMS ? 1 : 2) * cols * sizeof(float);
-  const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
   UB_DISPATCH_VPT(vpt, {
     auto kern = norm_bwd_kernel<T, VPT, kRMS, kFused>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -401,11 +766,10 @@ void launch_layernorm_fwd(const void* x, const void* gamma, const void* beta, vo
 }
 
 void launch_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
-                          void* dx, void* dgamma, void* dbeta, float* dgamma_part, float* dbeta_part,
-                          unsigned* counter, int rows, int cols, int dtype, cudaStream_t stream) {
-  (void)counter;
-  UB_DISPATCH_DTYPE(dtype, (run_bwd<T, false, false>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dgamma_part,
-                                                     dbeta_part, rows, cols, nullptr, 0.f, 0, 0, stream)));
+                          void* dx, void* dgamma, void* dbeta, float* part, int rows, int cols, int dtype,
+                          cudaStream_t stream) {
+  UB_DISPATCH_DTYPE(dtype, (run_bwd<T, false, false>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, nullptr, part, rows,
+                                                     cols, nullptr, 0.f, 0, 0, stream)));
 }
 
 void launch_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int rows, int cols, float eps,
@@ -415,10 +779,9 @@ void launch_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, 
 }
 
 void launch_rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* gamma, void* dx, void* dgamma,
-                        float* dgamma_part, unsigned* counter, int rows, int cols, int dtype, cudaStream_t stream) {
-  (void)counter;
-  UB_DISPATCH_DTYPE(dtype, (run_bwd<T, true, false>(dy, x, nullptr, rstd, gamma, dx, dgamma, nullptr, dgamma_part,
-                                                    nullptr, rows, cols, nullptr, 0.f, 0, 0, stream)));
+                        float* part, int rows, int cols, int dtype, cudaStream_t stream) {
+  UB_DISPATCH_DTYPE(dtype, (run_bwd<T, true, false>(dy, x, nullptr, rstd, gamma, dx, dgamma, nullptr, nullptr, part,
+                                                    rows, cols, nullptr, 0.f, 0, 0, stream)));
 }
 
 void launch_bias_dropout_add_ln_fwd(const void* x, const void* bias, const void* residual, const void* gamma,
@@ -436,16 +799,15 @@ void launch_bias_dropout_add_ln_fwd(const void* x, const void* bias, const void*
 
 void launch_bias_dropout_add_ln_bwd(const void* dy, const void* summed, const float* mean, const float* rstd,
                                     const void* gamma, void* dsum, void* dx, void* dgamma, void* dbeta,
-                                    float* dgamma_part, float* dbeta_part, unsigned* counter, int rows, int cols,
-                                    float p, unsigned long long seed, unsigned long long offset, int dtype,
-                                    cudaStream_t stream) {
-  (void)counter;
+                                    void* dbias, float* part, int rows, int cols, float p, unsigned long long seed,
+                                    unsigned long long offset, int dtype, cudaStream_t stream) {
+  // dbias (optional, v2 geometries only): column sums of dx, produced by the same pass
   if (dtype == kF16) {
-    run_bwd<__half, false, true>(dy, summed, mean, rstd, gamma, dsum, dgamma, dbeta, dgamma_part, dbeta_part, rows,
-                                 cols, dx, p, seed, offset, stream);
+    run_bwd<__half, false, true>(dy, summed, mean, rstd, gamma, dsum, dgamma, dbeta, dbias, part, rows, cols, dx, p,
+                                 seed, offset, stream);
   } else if (dtype == kBF16) {
-    run_bwd<__nv_bfloat16, false, true>(dy, summed, mean, rstd, gamma, dsum, dgamma, dbeta, dgamma_part, dbeta_part,
-                                        rows, cols, dx, p, seed, offset, stream);
+    run_bwd<__nv_bfloat16, false, true>(dy, summed, mean, rstd, gamma, dsum, dgamma, dbeta, dbias, part, rows, cols,
+                                        dx, p, seed, offset, stream);
   }
 }
 

@@ -334,3 +334,30 @@ def test_softmax_cross_entropy(dtype, vocab):
     (ref * 2.0).backward()
     assert abs(loss.item() - ref.item()) / abs(ref.item()) < 1e-4
     assert maxdiff(logits.grad, lr.grad) < (1e-5 if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_vocab_projection_padded_xent(dtype):
+    """LM head with a vocabulary that is not a multiple of 8: padded GEMMs + strided cross entropy."""
+    from unicore import ops
+
+    torch.manual_seed(0)
+    n, d, V = 333, 256, 30522
+    x = (torch.randn(n, d, device="cuda") * 0.5).to(dtype).requires_grad_(True)
+    w = (torch.randn(V, d, device="cuda") * 0.05).to(dtype).requires_grad_(True)
+    b = (torch.randn(V, device="cuda") * 0.1).to(dtype).requires_grad_(True)
+    tgt = torch.randint(0, V, (n,), device="cuda")
+    tgt[::7] = 1  # ignored
+    logits = ops.vocab_projection(x, w, b)
+    assert logits.shape == (n, V) and not logits.is_contiguous()
+    loss = ops.softmax_cross_entropy(logits, tgt, ignore_index=1)
+    loss.backward()
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    ref_logits = F.linear(xr, wr, br)
+    ref = F.nll_loss(F.log_softmax(ref_logits, dim=-1), tgt, ignore_index=1, reduction="sum")
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 2e-2 * abs(ref.item())
+    for g, gr in ((x.grad, xr.grad), (w.grad, wr.grad), (b.grad, br.grad)):
+        assert g.shape == gr.shape
+        tol = (3e-2 if dtype == torch.float16 else 8e-2) * max(1e-3, gr.abs().max().item())
+        assert (g.float() - gr).abs().max().item() < tol

@@ -155,7 +155,7 @@ class BertLMHead(nn.Module):
         else:
             x = self.activation_fn(self.dense(features))
         x = self.layer_norm(x)
-        return F.linear(x, self.weight, self.bias)
+        return ops.vocab_projection(x, self.weight, self.bias)
 
 
 class BertClassificationHead(nn.Module):

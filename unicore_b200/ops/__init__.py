@@ -6,7 +6,12 @@ from .attention_ops import (  # noqa: F401
     fused_attention_qkvpacked,
     fused_attention_supported,
 )
-from .fused_ops import bias_dropout_add_layer_norm, bias_gelu, softmax_cross_entropy  # noqa: F401
+from .fused_ops import (  # noqa: F401
+    bias_dropout_add_layer_norm,
+    bias_gelu,
+    softmax_cross_entropy,
+    vocab_projection,
+)
 from .norm_ops import layer_norm, rms_norm  # noqa: F401
 from .optim_ops import (  # noqa: F401
     ema_update_,

@@ -34,8 +34,7 @@ class _BiasGeluFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, bias = ctx.saved_tensors
-        dx = native().bias_gelu_bwd(dy.contiguous(), x, bias)
-        dbias = dx.view(-1, dx.shape[-1]).sum(dim=0) if bias is not None else None
+        dx, dbias = native().bias_gelu_bwd(dy.contiguous(), x, bias)
         return dx, dbias
 
 
@@ -67,10 +66,11 @@ class _BiasDropoutAddLNFn(torch.autograd.Function):
         summed, ln_weight, mean, rstd = ctx.saved_tensors
         dy2 = dy.contiguous().view(summed.shape)
         # dsum: gradient w.r.t. (residual + dropout(x+bias)); dx = dropout-masked dsum
-        dsum, dx, dgamma, dbeta = native().bias_dropout_add_ln_bwd(
-            dy2, summed, mean, rstd, ln_weight, ctx.p, ctx.rng[0], ctx.rng[1]
+        dsum, dx, dgamma, dbeta, dbias = native().bias_dropout_add_ln_bwd(
+            dy2, summed, mean, rstd, ln_weight, ctx.p, ctx.rng[0], ctx.rng[1], ctx.has_bias
         )
-        dbias = dx.sum(dim=0) if ctx.has_bias else None
+        if ctx.has_bias and dbias is None:
+            dbias = dx.sum(dim=0)
         return dx.view(dy.shape), dbias, dsum.view(dy.shape), dgamma, dbeta, None, None, None
 
 
@@ -100,17 +100,58 @@ def bias_dropout_add_layer_norm(x, bias, residual, ln_weight, ln_bias, p, eps, t
 # ------------------------------------------------------------------------------------------------
 class _SoftmaxXentFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, target, ignore_index):
-        loss_rows, lse = native().softmax_xent_fwd(logits, target, int(ignore_index))
+    def forward(ctx, logits, target, ignore_index, valid_cols):
+        loss_rows, lse = native().softmax_xent_fwd(logits, target, int(ignore_index), int(valid_cols))
         ctx.save_for_backward(logits, target, lse)
         ctx.ignore_index = int(ignore_index)
+        ctx.valid_cols = int(valid_cols)
         return loss_rows.sum()
 
     @staticmethod
     def backward(ctx, dloss):
         logits, target, lse = ctx.saved_tensors
-        dlogits = native().softmax_xent_bwd(logits, target, lse, dloss.float().reshape(1), ctx.ignore_index)
-        return dlogits, None, None
+        dlogits = native().softmax_xent_bwd(
+            logits, target, lse, dloss.float().reshape(1), ctx.ignore_index, ctx.valid_cols
+        )
+        return dlogits, None, None, None
+
+
+def _padded_base(logits):
+    """If ``logits`` is the ``[:, :V]`` slice of a wider contiguous 2-D tensor (a vocabulary padded for
+    GEMM alignment, see ``vocab_projection``) return that tensor, else None."""
+    base = logits._base
+    if (
+        base is not None
+        and base.dim() == 2
+        and base.is_contiguous()
+        and base.shape[0] == logits.shape[0]
+        and logits.storage_offset() == base.storage_offset()
+        and logits.stride() == (base.shape[1], 1)
+        and base.dtype == logits.dtype
+    ):
+        return base
+    return None
+
+
+def vocab_projection(x, weight, bias=None, multiple=64):
+    """``F.linear(x, weight, bias)`` for an output dimension (vocabulary) that is not a multiple of 8.
+
+    With V = 30522 the logits' rows are only 4-byte aligned, which sends all three GEMMs of the
+    projection (fwd, dgrad, wgrad) down cuBLAS' slow element-aligned path (measured 3x slower on
+    B200).  The weight/bias are zero-padded to a multiple of ``multiple`` rows on the fly (47 MB
+    copy for BERT-base, ~15 us) and the result is returned as the ``[:, :V]`` view of the padded
+    logits; ``softmax_cross_entropy`` recognises such views and reads/writes the padded buffer in
+    place, so no compaction copy is ever made.
+    """
+    V = weight.shape[0]
+    pad = (-V) % multiple
+    if pad == 0 or not x.is_cuda or x.dtype not in (torch.float16, torch.bfloat16):
+        return F.linear(x, weight, bias)
+    w = F.pad(weight, (0, 0, 0, pad))
+    b = F.pad(bias, (0, pad)) if bias is not None else None
+    lead = x.shape[:-1]
+    out = F.linear(x.reshape(-1, x.shape[-1]), w, b)
+    return out[:, :V] if len(lead) == 1 else out[:, :V].unflatten(0, lead)
 
 
 def softmax_cross_entropy(logits: torch.Tensor, target: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
@@ -119,11 +160,15 @@ def softmax_cross_entropy(logits: torch.Tensor, target: torch.Tensor, ignore_ind
         use_native(logits, target)
         and logits.dim() == 2
         and logits.dtype in (torch.float16, torch.bfloat16, torch.float32)
-        and logits.is_contiguous()
         and logits.numel() > 0
         and hasattr(native(), "softmax_xent_fwd")
     ):
-        return _SoftmaxXentFn.apply(logits, target.contiguous(), ignore_index)
+        if logits.is_contiguous():
+            return _SoftmaxXentFn.apply(logits, target.contiguous(), ignore_index, 0)
+        base = _padded_base(logits)
+        if base is not None:
+            return _SoftmaxXentFn.apply(base, target.contiguous(), ignore_index, logits.shape[1])
+        return _SoftmaxXentFn.apply(logits.contiguous(), target.contiguous(), ignore_index, 0)
     return F.nll_loss(
         F.log_softmax(logits, dim=-1, dtype=torch.float32), target, ignore_index=ignore_index, reduction="sum"
     )

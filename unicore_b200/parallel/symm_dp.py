@@ -48,7 +48,8 @@ def symm_available() -> bool:
             return False
         _symm_module()
         return True
-    except Exception:  # noqa: BLE001
+    except Exception as exc:  # noqa: BLE001
+        logger.warning("symmetric-memory data parallelism unavailable: %r", exc)
         return False
 
 
