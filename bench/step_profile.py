@@ -20,6 +20,7 @@ ap.add_argument("--prof-steps", type=int, default=3)
 ap.add_argument("--top", type=int, default=45)
 ap.add_argument("--gaps", type=int, default=12)
 ap.add_argument("--cprofile", type=int, default=0, help="also run this many steps under cProfile (host-side cost)")
+ap.add_argument("--trace", default="", help="write a chrome trace (CPU + CUDA activities) of the profiled steps here")
 a, rest = ap.parse_known_args()
 sys.argv = [sys.argv[0]] + rest
 args = B.parse()
@@ -61,10 +62,13 @@ if a.cprofile > 0:
         st.sort_stats("cumulative").print_stats(45)
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
-with profile(activities=[ProfilerActivity.CUDA]) as prof:
+acts = [ProfilerActivity.CUDA] + ([ProfilerActivity.CPU] if a.trace else [])
+with profile(activities=acts, with_stack=bool(a.trace)) as prof:
     for i in range(a.prof_steps):
         trainer.train_step([dev[i % 4]])
     torch.cuda.synchronize()
+if rank == 0 and a.trace:
+    prof.export_chrome_trace(a.trace)
 if rank == 0:
     rows = []
     for e in prof.key_averages():

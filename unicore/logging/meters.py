@@ -31,8 +31,8 @@ except ImportError:  # pragma: no cover
 
 def _scalar_type(value, n):
     """Cast ``n`` to something multiplicable with ``value`` without leaving its device."""
-    if _is_tensor(value) and not _is_tensor(n):
-        return value.new_tensor(n) if value.is_floating_point() else n
+    # a python number multiplies a tensor in place on its device; materialising it with
+    # ``new_tensor`` would be a blocking pageable host->device copy per logged scalar
     return n
 
 
@@ -79,7 +79,7 @@ class AverageMeter(Meter):
         if val is None:
             return
         self.val = val
-        if n > 0:
+        if _is_tensor(n) or n > 0:  # device-resident weights are not inspected (no host sync)
             self.sum = self.sum + val * _scalar_type(val, n)
             self.count = self.count + n
 
@@ -239,7 +239,41 @@ class MetersDict(OrderedDict):
             return meter.fn(self)
         return meter.smoothed_value
 
+    def localize(self) -> None:
+        """Bring device-resident meter state to the host with ONE transfer per dtype.
+
+        Every ``smoothed_value`` of a meter holding CUDA scalars ends in ``.item()``: a dozen
+        blocking device reads per ``get_smoothed_values`` call, i.e. per training step.  Here all
+        scalar CUDA tensors held by the meters (val / sum / count) are concatenated, read once and
+        written back as python numbers; accumulation simply continues from those.
+        """
+        if torch is None:
+            return
+        slots = []
+        for meter in self.values():
+            for attr in ("val", "sum", "count"):
+                v = getattr(meter, attr, None)
+                if _is_tensor(v) and v.is_cuda and v.numel() == 1:
+                    slots.append((meter, attr, v))
+        if not slots:
+            return
+        try:
+            from unicore.utils import tolist
+        except ImportError:  # pragma: no cover
+            def tolist(t):
+                return t.tolist()
+        for is_float in (True, False):
+            group = [sl for sl in slots if sl[2].is_floating_point() == is_float]
+            if not group:
+                continue
+            flat = torch.cat([v.detach().reshape(1) for _, _, v in group])
+            if is_float:
+                flat = flat.double()
+            for (meter, attr, _), x in zip(group, tolist(flat)):
+                setattr(meter, attr, x)
+
     def get_smoothed_values(self) -> Dict[str, float]:
+        self.localize()
         return OrderedDict(
             (key, self.get_smoothed_value(key)) for key in self.keys() if not key.startswith("_")
         )

@@ -278,7 +278,10 @@ class _FP16OptimizerMixin(object):
             grad_norm = aggregate_norm_fn(grad_norm)
         if self.scaler is not None:
             # ONE host read per step: needed for the overflow decision (skip / rescale)
-            norm_host = float(grad_norm)
+            norm_host = float(utils.item(grad_norm))
+            # downstream consumers (consistency check, gnorm/clip meters) get the host copy: no further
+            # device reads or tiny kernels between this point and the optimizer launch
+            grad_norm = torch.tensor(norm_host, dtype=torch.float32)
             if 0.0 < max_norm < norm_host:
                 self._multiply_factor = self._multiply_factor * (max_norm / norm_host)
             self.scaler.check_overflow(norm_host)

@@ -149,7 +149,8 @@ class UnicoreTask(object):
         exhausted shard) multiplies the loss by 0 so the collective schedule stays identical on
         all ranks.
         """
-        model.train()
+        if not model.training:  # Module.train() walks the whole tree; the trainer has usually done it
+            model.train()
         model.set_num_updates(update_num)
         with torch.autograd.profiler.record_function("forward"):
             loss_val, sample_size, logging_output = loss(model, sample)

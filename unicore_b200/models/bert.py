@@ -149,7 +149,8 @@ class BertLMHead(nn.Module):
 
     def forward(self, features, masked_tokens=None, **kwargs):
         if masked_tokens is not None:
-            features = features[masked_tokens, :]  # project only what the loss looks at
+            # project only what the loss looks at (indices shared with the loss: one host read per step)
+            features = features.reshape(-1, features.size(-1)).index_select(0, utils.mask_to_index(masked_tokens))
         if self._gelu and ops.use_native(features) and features.dtype in (torch.float16, torch.bfloat16):
             x = ops.bias_gelu(F.linear(features, self.dense.weight), self.dense.bias)
         else:
