@@ -228,7 +228,9 @@ def build_trainer(a, impl, world, rank, local_rank):
     register_bench_task(impl)
     parser = options.get_training_parser()
     flags = train_flags(a, world) + ["--bench-vocab", str(a.vocab)]
-    backend = a.ddp_backend or "c10d"
+    # ours: gradient all-reduce on the hand-written NVLink peer-memory kernels (falls back to c10d with a
+    # warning when symmetric memory is unavailable); reference: its own default (c10d DDP)
+    backend = a.ddp_backend or ("b200" if (impl != "reference" and world > 1) else "c10d")
     flags += ["--ddp-backend", backend, "--device-id", str(local_rank), "--distributed-rank", str(rank)]
     args = options.parse_args_and_arch(parser, input_args=flags)
     args.distributed_rank = rank
