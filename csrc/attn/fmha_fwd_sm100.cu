@@ -9,9 +9,10 @@
 //        previous tile's softmax ran
 //     2. S  = Q K_j^T          4 x tcgen05.mma (K=16 each), commit -> mbarrier
 //     3. softmax in ONE pass over registers: thread = (query row, 64-key half); TMEM lane = row.
-//        tcgen05.ld, fused scale/bias/key-mask FMA (log2 domain), row max exchanged between the two
-//        halves through shared memory, exp2, Philox dropout (keep bits are stored for backward),
-//        P -> shared memory, O rescaled in TMEM (32 columns per thread)
+//        tcgen05.ld, scale/bias FMA and exp2 argument on packed fp32x2 (FFMA2), row max exchanged
+//        between the two halves through shared memory, Philox dropout decided two keys per HSET2
+//        (the 0xffff/0 masks AND the packed P; keep bits are stored for backward), P -> shared
+//        memory, O rescaled in TMEM (32 columns per thread)
 //     4. O += P V_j            8 x tcgen05.mma (V presented MN-major from the same row-major bytes);
 //        V_j is only waited for here, so its latency hides behind the softmax
 //   q/k/v are read through strides straight out of the packed in_proj output; O is written as
@@ -108,15 +109,16 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
   const bool row_valid = row < p.Lq;
   const uint8_t* kpm_row = p.kpm != nullptr ? p.kpm + (long long)b * p.Lk : nullptr;
   const bool drop = p.p_drop > 0.f;
-  const uint32_t thresh = dropout_thresh16(p.p_drop);
-  const float keep_scale = drop ? 1.f / (1.f - p.p_drop) : 1.f;
+  const uint32_t t14 = dropout_thresh14(p.p_drop);
+  const uint32_t t14x2 = t14 | (t14 << 16);
+  // the 1/(1-p) of the kept probabilities is applied once, to the normalised output row
+  const float keep_scale = drop ? dropout_keep_scale14(t14) : 1.f;
   const unsigned long long row_lin = ((unsigned long long)b * p.H + h) * p.Lq + (row_valid ? row : 0);
   const unsigned long long drop_row_base = row_lin * p.Lk;
   uint32_t* bits_row = (drop && p.drop_bits != nullptr) ? p.drop_bits + row_lin * ((p.Lk + 31) / 32) : nullptr;
 
   constexpr float kLog2e = 1.4426950408889634f;
-  const float scale2 = p.scale * kLog2e;
-  float m_run = -CUDART_INF_F, l_run = 0.f;   // running max (log2 domain, common to both halves), partial sum
+  float m_run = -CUDART_INF_F, l_run = 0.f;   // running max of the logits (common to both halves), partial sum
   uint32_t phase_s = 0, phase_o = 0;
   const int n_tiles = (p.Lk + kBlockN - 1) / kBlockN;
 
@@ -134,14 +136,15 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
     cp_async_commit();
     cp_async_tile64<kFwdThreads, T>(smem_base + kSmemV, vg + (long long)key_tile0 * p.v_sl, p.v_sl, k_valid);
     cp_async_commit();
+    bool masked = false;
     if (tid < kBlockN) {  // additive key mask of this tile
       const int key = key_tile0 + tid;
-      const bool masked = key >= p.Lk || (kpm_row != nullptr && kpm_row[key] != 0);
+      masked = key >= p.Lk || (kpm_row != nullptr && kpm_row[key] != 0);
       kadd[tid] = masked ? -CUDART_INF_F : 0.f;
     }
     cp_async_wait<2>();            // all but {bias_j, V_j}: Q (first tile) and K_j have landed
     fence_proxy_async_smem();
-    __syncthreads();
+    const bool tile_masked = __syncthreads_or(masked) != 0;  // most tiles have no masked key: skip the adds
     if (tid == 0) {
       fence_after_thread_sync();
 #pragma unroll
@@ -162,9 +165,10 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
                                       min(kBlockN, p.Lk - key_tile0 - kBlockN));
     cp_async_commit();             // (possibly empty) group "K_{j+1}": keeps the group arithmetic uniform
 
-    // ---- logits of my 64 columns in registers (log2 domain): s2 = acc*scale*log2e + bias*log2e + kadd ----
-    float s2[64];
+    // ---- logits of my 64 columns in registers: x = acc*scale + bias (+ key mask), packed fp32x2 math ------
+    F2 x[32];
     float m_part = -CUDART_INF_F;
+    const F2 scale_2 = f2(p.scale);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int col0 = half * 64 + c * 32;
@@ -174,16 +178,21 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         float bf[8];
-        if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(smem + kSmemP + tile128_off(r, (col0 >> 3) + v)), bf);
-        const float4 ka = *reinterpret_cast<const float4*>(kadd + col0 + v * 8);
-        const float4 kb = *reinterpret_cast<const float4*>(kadd + col0 + v * 8 + 4);
-        const float kk8[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int i = c * 32 + v * 8 + e;
-          const float add = has_bias ? fmaf(bf[e], kLog2e, kk8[e]) : kk8[e];
-          s2[i] = fmaf(__uint_as_float(acc[v * 8 + e]), scale2, add);
-          m_part = fmaxf(m_part, s2[i]);
+        for (int e = 0; e < 8; ++e) bf[e] = 0.f;
+        if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(smem + kSmemP + tile128_off(r, (col0 >> 3) + v)), bf);
+        if (tile_masked) {
+          const float4 ka = *reinterpret_cast<const float4*>(kadd + col0 + v * 8);
+          const float4 kb = *reinterpret_cast<const float4*>(kadd + col0 + v * 8 + 4);
+          bf[0] += ka.x; bf[1] += ka.y; bf[2] += ka.z; bf[3] += ka.w;
+          bf[4] += kb.x; bf[5] += kb.y; bf[6] += kb.z; bf[7] += kb.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const F2 a2 = F2{__uint_as_float(acc[v * 8 + 2 * e]), __uint_as_float(acc[v * 8 + 2 * e + 1])};
+          const F2 xi = fma2(a2, scale_2, F2{bf[2 * e], bf[2 * e + 1]});
+          x[c * 16 + v * 4 + e] = xi;
+          m_part = fmaxf(m_part, fmaxf(xi.x, xi.y));
         }
       }
     }
@@ -192,41 +201,45 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
     const float m_tile = fmaxf(m_part, xchg[tid ^ 128]);
     const float m_new = fmaxf(m_run, m_tile);
     const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-    const float alpha = exp2f(m_run - m_use);  // m_run = -inf -> 0
+    const float alpha = exp2f((m_run - m_use) * kLog2e);  // m_run = -inf -> 0
     l_run *= alpha;
     m_run = m_new;
 
     // ---- probabilities, dropout, P -> shared memory (in place over the bias chunks) ---------------------
-    float psum = 0.f;
+    F2 psum2 = f2(0.f);
+    const F2 log2e_2 = f2(kLog2e), nm_2 = f2(-m_use * kLog2e);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int col0 = half * 64 + c * 32;
-      uint32_t keep_word = 0xffffffffu;
-      if (drop) {
-        keep_word = 0u;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const unsigned long long idx = drop_row_base + (unsigned long long)(key_tile0 + col0 + v * 8);
-          keep_word |= dropout_keep8(p.seed, p.offset, idx >> 3, thresh) << (8 * v);
-        }
-        if (bits_row != nullptr && row_valid && key_tile0 + col0 < p.Lk) bits_row[(key_tile0 + col0) >> 5] = keep_word;
-      }
+      uint32_t keep_word = 0u;   // bit (lane * 16 + i) = pair i (keys col0 + 2i, col0 + 2i + 1), lane = key parity
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        float pr[8];
+        uint32_t km[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (drop) {
+          const unsigned long long idx = drop_row_base + (unsigned long long)(key_tile0 + col0 + v * 8);
+          const Philox4 rnd = philox4x32<7>(p.seed, p.offset, idx >> 3);
+          km[0] = keep_mask2(rnd.x, t14x2);
+          km[1] = keep_mask2(rnd.y, t14x2);
+          km[2] = keep_mask2(rnd.z, t14x2);
+          km[3] = keep_mask2(rnd.w, t14x2);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          pr[e] = exp2f(s2[c * 32 + v * 8 + e] - m_use);
-          psum += pr[e];
-          if (drop) pr[e] = ((keep_word >> (v * 8 + e)) & 1u) ? pr[e] * keep_scale : 0.f;
+          for (int e = 0; e < 4; ++e) keep_word |= km[e] & (0x00010001u << (v * 4 + e));
         }
         Vec16 o;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o.w[e] = pack2<T>(pr[2 * e], pr[2 * e + 1]);
+        for (int e = 0; e < 4; ++e) {
+          const F2 arg = fma2(x[c * 16 + v * 4 + e], log2e_2, nm_2);
+          F2 pr;
+          pr.x = ex2_approx(arg.x);
+          pr.y = ex2_approx(arg.y);
+          psum2 = add2(psum2, pr);
+          o.w[e] = pack2<T>(pr.x, pr.y) & km[e];
+        }
         *reinterpret_cast<Vec16*>(smem + kSmemP + tile128_off(r, (col0 >> 3) + v)) = o;
       }
+      if (drop && bits_row != nullptr && row_valid && key_tile0 + col0 < p.Lk) bits_row[(key_tile0 + col0) >> 5] = keep_word;
     }
-    l_run += psum;
+    l_run += psum2.x + psum2.y;
 
     // ---- rescale the running output accumulator (32 of the 64 columns per thread) ------------------------
     if (j > 0) {
@@ -262,7 +275,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
   fence_after_thread_sync();
   __syncthreads();
   const float l_tot = l_run + xchg[tid ^ 128];
-  const float inv_l = l_tot > 0.f ? 1.f / l_tot : 0.f;
+  const float inv_l = l_tot > 0.f ? keep_scale / l_tot : 0.f;
   {
     uint32_t acc[32];
     tmem_ld32(lane_base + kTmemColO + half * 32, acc);
@@ -280,8 +293,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
     }
   }
   if (row_valid && half == 0) {
-    // natural-log LSE of the logits: (m2 + log2(l)) / log2(e)
-    p.lse[row_lin] = (l_tot > 0.f) ? (m_run + log2f(l_tot)) * 0.6931471805599453f : -CUDART_INF_F;
+    // natural-log LSE of the logits
+    p.lse[row_lin] = (l_tot > 0.f) ? m_run + log2f(l_tot) * 0.6931471805599453f : -CUDART_INF_F;
   }
   fence_before_thread_sync();
   __syncthreads();

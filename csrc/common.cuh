@@ -131,6 +131,21 @@ UB_DEVICE Vec16 pack<__nv_bfloat16>(const float* in) {
   return v;
 }
 
+// 14-bit dropout thresholds compared two at a time as fp16 bit patterns (HSET2): a random 16-bit
+// lane masked to 14 bits is a finite non-negative half whose float order equals its integer order,
+// so ONE instruction yields the 0xffff / 0x0000 select masks of a packed pair of probabilities.
+// drop <=> u14 < T14; the effective rate is T14 / 16384 (|p - p_eff| < 3.1e-5) and the keep scale
+// is computed from T14 so that forward and backward agree and the estimator stays unbiased.
+UB_DEVICE uint32_t dropout_thresh14(float p) {
+  const float t = p * 16384.f + 0.5f;
+  return t <= 0.f ? 0u : (t >= 16383.f ? 16383u : (uint32_t)t);
+}
+UB_DEVICE float dropout_keep_scale14(uint32_t t14) { return 16384.f / (16384.f - (float)t14); }
+UB_DEVICE uint32_t keep_mask2(uint32_t rnd, uint32_t t14x2) {
+  const uint32_t u = rnd & 0x3fff3fffu;
+  return __hge2_mask(*reinterpret_cast<const __half2*>(&u), *reinterpret_cast<const __half2*>(&t14x2));
+}
+
 // ------------------------------------------------------------------------------------------------
 // packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 - two fp32 lanes per issued instruction);
 // used where a kernel is issue-bound rather than bandwidth-bound (GELU, softmax statistics).
