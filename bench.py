@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--ema-decay", type=float, default=-1.0)
     ap.add_argument("--ddp-backend", default=None)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sync-overflow-check", action="store_true",
+                    help="ours: read the grad norm on the host every step (reference behaviour) instead of the "
+                         "deferred, device-side overflow skip")
     return ap.parse_args()
 
 
@@ -153,6 +156,8 @@ def train_flags(a, world):
     ]
     if a.precision == "fp16":
         flags += ["--fp16", "--fp16-init-scale", "4", "--fp16-scale-window", "256"]
+        if getattr(a, "impl", "ours") != "reference" and not getattr(a, "sync_overflow_check", False):
+            flags += ["--deferred-overflow-check"]  # ours only: see unicore/options.py
     else:
         flags += ["--bf16"]
     if a.ema_decay > 0:
@@ -402,7 +407,10 @@ def main():
                 "vocab": a.vocab,
                 "parallelism": "dp{}".format(world),
                 "ddp_backend": getattr(args, "ddp_backend", None),
-                "optimizer": "adam(0.9,0.98) clip 1.0 polynomial_decay, {} dynamic loss scale".format(a.precision),
+                "optimizer": "adam(0.9,0.98) clip 1.0 polynomial_decay, {} dynamic loss scale{}".format(
+                    a.precision,
+                    " (overflow skip decided on the device, scaler updated before the next backward)"
+                    if (a.impl != "reference" and a.precision == "fp16" and not a.sync_overflow_check) else ""),
                 "l2": "no explicit flush: each step streams >1.7 GB of weights/optimizer state/activations, "
                       "far above the 126 MB L2, and 8 distinct input batches rotate",
             },

@@ -4,6 +4,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <optional>
@@ -93,7 +94,24 @@ std::tuple<Tensor, Tensor, OptTensor> fmha_fwd(const Tensor& q, const Tensor& k,
     bits = torch::empty({p.B, p.H, p.Lq, (p.Lk + 31) / 32}, q.options().dtype(at::kInt));
     p.drop_bits = reinterpret_cast<uint32_t*>(bits->data_ptr());
   }
+  Tensor trace;
+  p.trace = nullptr;
+  if (std::getenv("UNICORE_FMHA_TRACE") != nullptr) {
+    trace = torch::zeros({64, 12}, q.options().dtype(at::kLong));
+    p.trace = reinterpret_cast<long long*>(trace.data_ptr<int64_t>());
+  }
   ub::launch_fmha_fwd(p, at::cuda::getCurrentCUDAStream().stream());
+  if (p.trace != nullptr) {
+    Tensor host = trace.cpu();
+    auto acc = host.accessor<int64_t, 2>();
+    const int tiles = (p.Lk + 127) / 128;
+    for (int j = 0; j < tiles && j < 64; ++j) {
+      printf("fmha_fwd trace tile %d:", j);
+      for (int sidx = 1; sidx < 12; ++sidx) printf(" %lld", (long long)(acc[j][sidx] - acc[j][sidx - 1]));
+      if (j > 0) printf("  | since prev tile start %lld", (long long)(acc[j][0] - acc[j - 1][0]));
+      printf("\n");
+    }
+  }
   cudaError_t err = cudaGetLastError();
   TORCH_CHECK(err == cudaSuccess, "fmha_fwd launch failed: ", cudaGetErrorString(err));
   return {out, lse, bits};

@@ -166,15 +166,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
   cp_async_tile64<kBwdThreads, T>(smem_base + kOffV, vg + (long long)key_tile0 * p.v_sl, p.v_sl, k_valid);
   issue_tile(0);
   cp_async_commit();
+  bool key_masked = false;
   if (tid < kBN) {
     const int key = key_tile0 + tid;
-    const bool masked = key >= p.Lk || (p.kpm != nullptr && p.kpm[(long long)b * p.Lk + key] != 0);
-    kadd[tid] = masked ? -CUDART_INF_F : 0.f;
+    key_masked = key >= p.Lk || (p.kpm != nullptr && p.kpm[(long long)b * p.Lk + key] != 0);
+    kadd[tid] = key_masked ? -CUDART_INF_F : 0.f;
   }
   cp_async_wait<0>();
   fence_proxy_async_smem();
   fence_before_thread_sync();
-  __syncthreads();
+  const bool tile_masked = __syncthreads_or(key_masked) != 0;  // usually no key of the tile is masked
   fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -200,9 +201,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
   if (tid == 0) issue_s_dp(0);
 
   const bool drop = p.p_drop > 0.f && p.drop_bits != nullptr;
-  const float keep_scale = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+  // same 14-bit threshold arithmetic as the forward kernel (common.cuh)
+  const float keep_scale = p.p_drop > 0.f ? dropout_keep_scale14(dropout_thresh14(p.p_drop)) : 1.f;
   constexpr float kLog2e = 1.4426950408889634f;
-  const float scale2 = p.scale * kLog2e;
+  const F2 scale_2 = f2(p.scale), log2e_2 = f2(kLog2e);
   const int words_per_row = (p.Lk + 31) / 32;
   uint32_t phase_a = 0, phase_b = 0;
 
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
     const float delta = row_valid ? bp.delta[stat_idx] : 0.f;
     // fully masked row (lse = -inf) or padding row -> p = 0
     const float lse2 = (lse == -CUDART_INF_F || !row_valid) ? CUDART_INF_F : lse * kLog2e;
+    const F2 nlse_2 = f2(-lse2), ndelta_2 = f2(-delta);
     uint32_t keep_word = 0xffffffffu;
     if (drop && row_valid && key_tile0 + col0 < p.Lk)
       keep_word = p.drop_bits[stat_idx * words_per_row + ((key_tile0 + col0) >> 5)];
@@ -240,19 +243,34 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
       for (int v = 0; v < 4; ++v) {
         const uint32_t off = tile128_off(r, (col0 >> 3) + v);
         float bf[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bf[e] = 0.f;
         if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(smem + offDS + off), bf);
-        const float4 ka = *reinterpret_cast<const float4*>(kadd + col0 + v * 8);
-        const float4 kb = *reinterpret_cast<const float4*>(kadd + col0 + v * 8 + 4);
-        const float kk8[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+        if (tile_masked) {
+          const float4 ka = *reinterpret_cast<const float4*>(kadd + col0 + v * 8);
+          const float4 kb = *reinterpret_cast<const float4*>(kadd + col0 + v * 8 + 4);
+          bf[0] += ka.x; bf[1] += ka.y; bf[2] += ka.z; bf[3] += ka.w;
+          bf[4] += kb.x; bf[5] += kb.y; bf[6] += kb.z; bf[7] += kb.w;
+        }
         float pd[8], ds[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float add = has_bias ? fmaf(bf[e], kLog2e, kk8[e]) : kk8[e];
-          const float s2 = fmaf(__uint_as_float(acc[v * 8 + e]), scale2, add);
-          const float pr = exp2f(s2 - lse2);
-          const float km = ((keep_word >> (v * 8 + e)) & 1u) ? keep_scale : 0.f;
-          pd[e] = pr * km;
-          ds[e] = pr * fmaf(__uint_as_float(dpr[v * 8 + e]), km, -delta);
+        for (int e = 0; e < 4; ++e) {
+          // keep bits of the pair (keys 2i, 2i+1 of my 32): bit i and bit 16 + i (see fmha_fwd)
+          const int pi = v * 4 + e;
+          const bool k0 = (keep_word >> pi) & 1u, k1 = (keep_word >> (16 + pi)) & 1u;
+          const F2 a2 = F2{__uint_as_float(acc[v * 8 + 2 * e]), __uint_as_float(acc[v * 8 + 2 * e + 1])};
+          const F2 x2 = fma2(a2, scale_2, F2{bf[2 * e], bf[2 * e + 1]});
+          const F2 arg = fma2(x2, log2e_2, nlse_2);
+          F2 pr;
+          pr.x = ex2_approx(arg.x);
+          pr.y = ex2_approx(arg.y);
+          const F2 km = F2{k0 ? keep_scale : 0.f, k1 ? keep_scale : 0.f};
+          const F2 dp2 = F2{__uint_as_float(dpr[v * 8 + 2 * e]), __uint_as_float(dpr[v * 8 + 2 * e + 1])};
+          const F2 d2 = mul2(pr, fma2(dp2, km, ndelta_2));
+          pd[2 * e] = k0 ? pr.x : 0.f;       // keep_scale is applied to dV in the epilogue
+          pd[2 * e + 1] = k1 ? pr.y : 0.f;
+          ds[2 * e] = d2.x;                   // the softmax scale is applied to dQ / dK at read-out
+          ds[2 * e + 1] = d2.y;
         }
         if (dbias_row != nullptr && key_tile0 + col0 + v * 8 < p.Lk && !(bp.debug_flags & 1)) {
           red_add_v4(dbias_row + col0 + v * 8, ds[0], ds[1], ds[2], ds[3]);
@@ -262,7 +280,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           op.w[e] = bwd_pack2<T>(pd[2 * e], pd[2 * e + 1]);
-          od.w[e] = bwd_pack2<T>(ds[2 * e] * p.scale, ds[2 * e + 1] * p.scale);
+          od.w[e] = bwd_pack2<T>(ds[2 * e], ds[2 * e + 1]);
         }
         *reinterpret_cast<Vec16*>(smem + kOffP + off) = op;
         *reinterpret_cast<Vec16*>(smem + offDS + off) = od;   // in place over the consumed bias chunk
@@ -308,8 +326,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
         float* dst = bp.dq_acc + (((long long)b * p.Lq + row) * p.H + h) * kD + quarter * 16;
 #pragma unroll
         for (int v = 0; v < 4; ++v)
-          red_add_v4(dst + v * 4, __uint_as_float(acc[v * 4]), __uint_as_float(acc[v * 4 + 1]),
-                     __uint_as_float(acc[v * 4 + 2]), __uint_as_float(acc[v * 4 + 3]));
+          red_add_v4(dst + v * 4, __uint_as_float(acc[v * 4]) * p.scale, __uint_as_float(acc[v * 4 + 1]) * p.scale,
+                     __uint_as_float(acc[v * 4 + 2]) * p.scale, __uint_as_float(acc[v * 4 + 3]) * p.scale);
       }
     }
   }
@@ -331,8 +349,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
         Vec16 ov, ok;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          ov.w[e] = bwd_pack2<T>(__uint_as_float(accv[v * 8 + 2 * e]), __uint_as_float(accv[v * 8 + 2 * e + 1]));
-          ok.w[e] = bwd_pack2<T>(__uint_as_float(acck[v * 8 + 2 * e]), __uint_as_float(acck[v * 8 + 2 * e + 1]));
+          ov.w[e] = bwd_pack2<T>(__uint_as_float(accv[v * 8 + 2 * e]) * keep_scale,
+                                 __uint_as_float(accv[v * 8 + 2 * e + 1]) * keep_scale);
+          ok.w[e] = bwd_pack2<T>(__uint_as_float(acck[v * 8 + 2 * e]) * p.scale,
+                                 __uint_as_float(acck[v * 8 + 2 * e + 1]) * p.scale);
         }
         st_global_v4(dvg + v * 8, ov);
         st_global_v4(dkg + v * 8, ok);

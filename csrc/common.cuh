@@ -183,6 +183,38 @@ UB_DEVICE float ex2_approx(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// 1-D bulk asynchronous copies (cp.async.bulk, the non-tensor form of TMA) + mbarrier completion:
+// ONE instruction by ONE thread moves a contiguous block of up to tens of KB from global to shared
+// memory with no register or LSU-issue cost; the bytes are counted on an mbarrier the consumers
+// wait on.  Addresses and sizes must be multiples of 16 bytes.
+// ------------------------------------------------------------------------------------------------
+UB_DEVICE uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+UB_DEVICE void bulk_bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+UB_DEVICE void bulk_bar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+UB_DEVICE void bulk_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+UB_DEVICE void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+UB_DEVICE void bulk_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && clock64() - t0 > 4000000000LL) __trap();  // ~2 s: never hang the GPU on a lost copy
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------------------------
 UB_DEVICE float warp_sum(float v) {

@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(256) norm_param_grad_kernel(const float* __res
 // parallelism comes from R consecutive rows kept in flight per thread instead.
 // ================================================================================================
 constexpr int kNormV2Threads = 384;
+constexpr int kNormStages = 4;  // bulk-copy input stages per CTA (<= ~25 KB each)
 constexpr int kNormV2Warps = kNormV2Threads / 32;
 
 struct NormGeom2 {
@@ -345,12 +346,37 @@ __global__ void __launch_bounds__(kNormV2Threads, 2) norm_fwd_v2_kernel(
     const T* __restrict__ bias, const T* __restrict__ residual, T* __restrict__ summed, float p, float keep_scale,
     unsigned long long seed, unsigned long long offset) {
   constexpr int EPV = VecTraits<T>::kElems;
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
   __shared__ float scratch[R * kNormV2Warps];
   const int tpr = g.tpr;
   const int grp = threadIdx.x / tpr, j = threadIdx.x - grp * tpr;
   const bool col_ok = j < g.nvec;
   const float inv_cols = 1.f / (float)g.cols;
   const uint32_t thresh = kFused ? dropout_thresh16(p) : 0u;
+
+  // ---- input pipeline: tiles of (groups * R) consecutive rows arrive by bulk copy, kNormStages deep ----
+  const int tile_rows = g.groups * R;
+  const uint32_t row_bytes = (uint32_t)g.cols * (uint32_t)sizeof(T);
+  const uint32_t tile_bytes = (uint32_t)tile_rows * row_bytes;
+  const uint32_t stage_bytes = tile_bytes * (kFused ? 2u : 1u);
+  const uint32_t stage_base = smem_addr_u32(dyn_smem);
+  const uint32_t bar_base = stage_base + kNormStages * stage_bytes;
+  const long long n_tiles = ((long long)g.rows + tile_rows - 1) / tile_rows;
+  const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);  // tiles blockIdx.x, +gridDim.x, ...
+  auto issue = [&](int it) {  // one thread
+    const uint32_t s = (uint32_t)(it % kNormStages);
+    const long long trow0 = ((long long)it * gridDim.x + blockIdx.x) * tile_rows;
+    const long long left = (long long)g.rows - trow0;
+    const uint32_t bytes = (uint32_t)(left < tile_rows ? left : tile_rows) * row_bytes;
+    bulk_expect_tx(bar_base + s * 8, bytes * (kFused ? 2u : 1u));
+    bulk_g2s(stage_base + s * stage_bytes, x + trow0 * g.cols, bytes, bar_base + s * 8);
+    if (kFused) bulk_g2s(stage_base + s * stage_bytes + tile_bytes, residual + trow0 * g.cols, bytes, bar_base + s * 8);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kNormStages; ++s) bulk_bar_init(bar_base + s * 8, 1);
+    bulk_bar_init_fence();
+    for (int it = 0; it < kNormStages && it < n_my; ++it) issue(it);
+  }
 
   float gam[EPV], bet[EPV], bia[EPV];
 #pragma unroll
@@ -360,20 +386,23 @@ __global__ void __launch_bounds__(kNormV2Threads, 2) norm_fwd_v2_kernel(
     if (!kRMS) unpack<T>(ldv(beta + j * EPV), bet);
     if (kFused && bias != nullptr) unpack<T>(ldv(bias + j * EPV), bia);
   }
+  __syncthreads();  // barrier objects are initialised before anyone waits on them
 
-  const int rows_per_iter = gridDim.x * g.groups * R;
-  const int n_iters = (g.rows + rows_per_iter - 1) / rows_per_iter;
-  for (int it = 0; it < n_iters; ++it) {
+  for (int it = 0; it < n_my; ++it) {
     const int row0 = ((it * gridDim.x + blockIdx.x) * g.groups + grp) * R;
+    const uint32_t s = (uint32_t)(it % kNormStages);
+    bulk_wait(bar_base + s * 8, (uint32_t)((it / kNormStages) & 1));
+    const uint8_t* st = dyn_smem + s * stage_bytes + (size_t)(grp * R) * row_bytes + (size_t)j * 16;
     Vec16 xv[R], rv[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       if (col_ok && row0 + i < g.rows) {
-        const size_t off = (size_t)(row0 + i) * g.cols + (size_t)j * EPV;
-        xv[i] = ld_global_nc_v4(x + off);
-        if (kFused) rv[i] = ld_global_nc_v4(residual + off);
+        xv[i] = *reinterpret_cast<const Vec16*>(st + (size_t)i * row_bytes);
+        if (kFused) rv[i] = *reinterpret_cast<const Vec16*>(st + tile_bytes + (size_t)i * row_bytes);
       }
     }
+    __syncthreads();  // the stage has been copied out by everybody: refill it
+    if (threadIdx.x == 0 && it + kNormStages < n_my) issue(it + kNormStages);
     float xs[R][EPV];
     float acc[R];
 #pragma unroll
@@ -459,7 +488,8 @@ __global__ void __launch_bounds__(kNormV2Threads, 2) norm_bwd_v2_kernel(
     NormGeom2 g, T* __restrict__ dx_drop, int want_dbias, float p, float keep_scale, unsigned long long seed,
     unsigned long long offset) {
   constexpr int EPV = VecTraits<T>::kElems;
-  extern __shared__ float sm_acc[];  // [3][cols]
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  float* sm_acc = reinterpret_cast<float*>(dyn_smem);  // [3][cols], then the input stages, then their barriers
   __shared__ float scratch[2 * R * kNormV2Warps];
   const int tpr = g.tpr;
   const int grp = threadIdx.x / tpr, j = threadIdx.x - grp * tpr;
@@ -467,15 +497,42 @@ __global__ void __launch_bounds__(kNormV2Threads, 2) norm_bwd_v2_kernel(
   const float inv_cols = 1.f / (float)g.cols;
   const uint32_t thresh = kFused ? dropout_thresh16(p) : 0u;
 
+  // ---- input pipeline (see norm_fwd_v2_kernel): every stage holds a dy tile and an x tile ----
+  const int tile_rows = g.groups * R;
+  const uint32_t row_bytes = (uint32_t)g.cols * (uint32_t)sizeof(T);
+  const uint32_t tile_bytes = (uint32_t)tile_rows * row_bytes;
+  const uint32_t stage_bytes = tile_bytes * 2u;
+  const uint32_t acc_bytes = (3u * (uint32_t)g.cols * 4u + 127u) & ~127u;
+  const uint32_t stage_base = smem_addr_u32(dyn_smem) + acc_bytes;
+  const uint32_t bar_base = stage_base + kNormStages * stage_bytes;
+  const long long n_tiles = ((long long)g.rows + tile_rows - 1) / tile_rows;
+  const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  auto issue = [&](int it) {  // one thread
+    const uint32_t s = (uint32_t)(it % kNormStages);
+    const long long trow0 = ((long long)it * gridDim.x + blockIdx.x) * tile_rows;
+    const long long left = (long long)g.rows - trow0;
+    const uint32_t bytes = (uint32_t)(left < tile_rows ? left : tile_rows) * row_bytes;
+    bulk_expect_tx(bar_base + s * 8, bytes * 2u);
+    bulk_g2s(stage_base + s * stage_bytes, dy + trow0 * g.cols, bytes, bar_base + s * 8);
+    bulk_g2s(stage_base + s * stage_bytes + tile_bytes, x + trow0 * g.cols, bytes, bar_base + s * 8);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kNormStages; ++s) bulk_bar_init(bar_base + s * 8, 1);
+    bulk_bar_init_fence();
+    for (int it = 0; it < kNormStages && it < n_my; ++it) issue(it);
+  }
+
   float gam[EPV], dg[EPV], db[EPV], dbi[EPV];
 #pragma unroll
   for (int e = 0; e < EPV; ++e) gam[e] = dg[e] = db[e] = dbi[e] = 0.f;
   if (col_ok) unpack<T>(ldv(gamma + j * EPV), gam);
+  __syncthreads();
 
-  const int rows_per_iter = gridDim.x * g.groups * R;
-  const int n_iters = (g.rows + rows_per_iter - 1) / rows_per_iter;
-  for (int it = 0; it < n_iters; ++it) {
+  for (int it = 0; it < n_my; ++it) {
     const int row0 = ((it * gridDim.x + blockIdx.x) * g.groups + grp) * R;
+    const uint32_t stg = (uint32_t)(it % kNormStages);
+    bulk_wait(bar_base + stg * 8, (uint32_t)((it / kNormStages) & 1));
+    const uint8_t* st = dyn_smem + acc_bytes + stg * stage_bytes + (size_t)(grp * R) * row_bytes + (size_t)j * 16;
     Vec16 xq[R], dq[R];
     float mu[R], rs[R];
 #pragma unroll
@@ -484,14 +541,15 @@ __global__ void __launch_bounds__(kNormV2Threads, 2) norm_bwd_v2_kernel(
       mu[i] = (ok && !kRMS) ? mean[row0 + i] : 0.f;
       rs[i] = ok ? rstd[row0 + i] : 0.f;
       if (ok && col_ok) {
-        const size_t off = (size_t)(row0 + i) * g.cols + (size_t)j * EPV;
-        xq[i] = ld_global_nc_v4(x + off);
-        dq[i] = ld_global_nc_v4(dy + off);
+        dq[i] = *reinterpret_cast<const Vec16*>(st + (size_t)i * row_bytes);
+        xq[i] = *reinterpret_cast<const Vec16*>(st + tile_bytes + (size_t)i * row_bytes);
       } else {
         xq[i].w[0] = xq[i].w[1] = xq[i].w[2] = xq[i].w[3] = 0u;
         dq[i] = xq[i];
       }
     }
+    __syncthreads();  // the stage has been copied out by everybody: refill it
+    if (threadIdx.x == 0 && it + kNormStages < n_my) issue(it + kNormStages);
     float s[2 * R];
 #pragma unroll
     for (int i = 0; i < R; ++i) {
@@ -713,7 +771,10 @@ static void run_fwd(const void* x, const void* gamma, const void* beta, void* y,
   const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
   NormGeom2 g2;
   if (make_geom2(rows, cols, VecTraits<T>::kElems, g2)) {
-    norm_fwd_v2_kernel<T, kFwdR, kRMS, kFused><<<v2_grid(g2, kFwdR), g2.tpr * g2.groups, 0, stream>>>(
+    auto fkern = norm_fwd_v2_kernel<T, kFwdR, kRMS, kFused>;
+    const size_t fsmem = (size_t)kNormStages * g2.groups * kFwdR * cols * sizeof(T) * (kFused ? 2 : 1) + 64;
+    cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    fkern<<<v2_grid(g2, kFwdR), g2.tpr * g2.groups, fsmem, stream>>>(
         (const T*)x, (const T*)gamma, (const T*)beta, (T*)y, mean, rstd, g2, eps, (const T*)bias, (const T*)residual,
         (T*)summed, p, keep_scale, seed, offset);
     return;
@@ -734,8 +795,10 @@ static void run_bwd(const void* dy, const void* x, const float* mean, const floa
   NormGeom2 g2;
   if (make_geom2(rows, cols, VecTraits<T>::kElems, g2)) {
     const int grid = v2_grid(g2, kBwdR);
-    const size_t smem2 = (size_t)3 * cols * sizeof(float);
+    const size_t smem2 = (((size_t)3 * cols * sizeof(float) + 127) & ~(size_t)127) +
+                         (size_t)kNormStages * g2.groups * kBwdR * cols * sizeof(T) * 2 + 64;
     auto kern = norm_bwd_v2_kernel<T, kBwdR, kRMS, kFused>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     kern<<<grid, g2.tpr * g2.groups, smem2, stream>>>((const T*)dy, (const T*)x, mean, rstd, (const T*)gamma, (T*)dx,
                                                        part, g2, (T*)dx_drop, dbias != nullptr ? 1 : 0, p, keep_scale,
                                                        seed, offset);

@@ -212,7 +212,13 @@ UB_DEVICE uint16_t bf16_sr_bits(float x, uint32_t rnd16) {
 }
 
 __global__ void __launch_bounds__(kThreads) adam_kernel(AdamTensors t, long long nchunks, AdamLaunch cfg) {
-  const float gmul = cfg.inv_scale / (cfg.scale_dev ? __ldg(cfg.scale_dev) : 1.f);
+  // A non-finite (or zero) device divisor means "the gradients overflowed": the update skips itself -
+  // parameters, moments and EMA stay untouched, only the gradient clearing happens - so the host does
+  // not have to read the gradient norm before it may launch this kernel (deferred overflow check).
+  const float sdev = cfg.scale_dev ? __ldg(cfg.scale_dev) : 1.f;
+  const bool skip = cfg.scale_dev != nullptr && !(isfinite(sdev) && sdev != 0.f);
+  if (skip && !cfg.zero_grad) return;
+  const float gmul = cfg.inv_scale / sdev;
   for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
     int ti;
     long long begin;
@@ -234,6 +240,11 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(AdamTensors t, long long
     if (vec_ok) {
       vend = begin + ((end - begin) & ~7LL);
       for (long long i = begin + (long long)threadIdx.x * 8; i < vend; i += kThreads * 8) {
+        if (skip) {
+          float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          store8(G, gdt, i, z);
+          continue;
+        }
         float g[8], p[8], m[8], v[8];
         load8(G, gdt, i, g);
         load8(P, pdt, i, p);
@@ -274,6 +285,10 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(AdamTensors t, long long
       }
     }
     for (long long i = vend + threadIdx.x; i < end; i += kThreads) {
+      if (skip) {
+        store1(G, gdt, i, 0.f);
+        continue;
+      }
       float p = load1(P, pdt, i), m = M[i], v = V[i];
       const float g = load1(G, gdt, i) * gmul;
       adam_math(p, m, v, g, b1, b2, eps, ss, dm);

@@ -1,0 +1,91 @@
+"""GPU trainer tests: fused optimizer tail, deferred (device-side) overflow handling, lazy logging output."""
+import importlib
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _trainer(extra):
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    importlib.import_module("bert")
+    from unicore import options, tasks
+    from unicore.trainer import Trainer
+
+    parser = options.get_training_parser()
+    args = options.parse_args_and_arch(parser, input_args=[
+        "--task", "synthetic_mlm", "--loss", "masked_lm", "--arch", "bert_base",
+        "--encoder-layers", "2", "--encoder-embed-dim", "128", "--encoder-ffn-embed-dim", "256",
+        "--encoder-attention-heads", "2", "--synthetic-vocab-size", "512", "--synthetic-seq-len", "64",
+        "--max-seq-len", "64", "--optimizer", "adam", "--lr", "1e-3", "--lr-scheduler", "fixed",
+        "--max-update", "100", "--batch-size", "8", "--fp16", "--clip-norm", "1.0", "--seed", "5",
+        "--distributed-world-size", "1", "--no-save", "--disable-validation", "--log-format", "none",
+    ] + extra)
+    task = tasks.setup_task(args)
+    model = task.build_model(args)
+    loss = task.build_loss(args)
+    trainer = Trainer(args, task, model, loss)
+    trainer._total_train_steps = args.max_update
+    task.load_dataset("train")
+    ds = task.dataset("train")
+    batches = [ds.collater([ds[k * 8 + i] for i in range(8)]) for k in range(4)]
+    return trainer, batches
+
+
+def _run(extra, steps):
+    torch.manual_seed(0)
+    trainer, batches = _trainer(extra)
+    outs = []
+    for i in range(steps):
+        outs.append(trainer.train_step([batches[i % 4]]))
+    trainer.optimizer.resolve_pending_overflow()
+    torch.cuda.synchronize()
+    return trainer, outs
+
+
+def test_deferred_overflow_matches_synchronous_path_without_overflow():
+    """No overflow: identical parameters and update counts; the logging output is lazy but complete."""
+    ta, outs_a = _run(["--fp16-init-scale", "4"], 6)
+    tb, outs_b = _run(["--fp16-init-scale", "4", "--deferred-overflow-check"], 6)
+    assert ta.get_num_updates() == tb.get_num_updates() == 6
+    pa = torch.cat([p.detach().float().reshape(-1) for p in ta.model.parameters()])
+    pb = torch.cat([p.detach().float().reshape(-1) for p in tb.model.parameters()])
+    assert torch.isfinite(pb).all()
+    assert (pa - pb).abs().max().item() < 2e-3
+    la, lb = float(outs_a[-1]["loss"]), float(outs_b[-1]["loss"])
+    assert math.isfinite(lb) and abs(la - lb) < 5e-2 * max(1.0, abs(la))
+    assert "loss" in outs_b[-1] and "sample_size" in outs_b[-1] and len(outs_b[-1]) >= 2
+
+
+def test_deferred_overflow_skips_on_device_and_rescales():
+    """A loss scale far too large overflows fp16 gradients: the fused Adam kernel must leave the weights
+    untouched, the scaler must come down, and skipped updates must not be counted."""
+    trainer, batches = _trainer(["--fp16-init-scale", str(2 ** 24), "--deferred-overflow-check",
+                                 "--fp16-scale-window", "1000"])
+    before = torch.cat([p.detach().float().reshape(-1).clone() for p in trainer.model.parameters()])
+    events = []
+    trainer.optimizer.add_late_overflow_handler(lambda msg: events.append(msg))
+    trainer.train_step([batches[0]])
+    torch.cuda.synchronize()
+    after = torch.cat([p.detach().float().reshape(-1) for p in trainer.model.parameters()])
+    assert torch.equal(before, after), "an overflowed update must be skipped on the device"
+    for i in range(1, 16):
+        trainer.train_step([batches[i % 4]])
+    trainer.optimizer.resolve_pending_overflow()
+    torch.cuda.synchronize()
+    assert len(events) >= 1
+    assert trainer.optimizer.scaler.loss_scale < 2 ** 24
+    assert trainer.get_num_updates() == 16 - len(events)
+    final = torch.cat([p.detach().float().reshape(-1) for p in trainer.model.parameters()])
+    assert torch.isfinite(final).all()
+    assert not torch.equal(before, final), "training must proceed once the scale has come down"
+    # Adam's bias-correction step count only advanced for the updates that really happened
+    inner = trainer.optimizer.fp32_optimizer.optimizer
+    steps = {int(st["step"]) for st in inner.state.values() if "step" in st}
+    assert steps == {trainer.get_num_updates()}

@@ -171,6 +171,7 @@ class _FP16OptimizerMixin(object):
 
     # -- state ----------------------------------------------------------------------------------
     def state_dict(self):
+        self.resolve_pending_overflow()
         state = self.fp32_optimizer.state_dict()
         if self.scaler is not None:
             state["loss_scale"] = self.scaler.loss_scale
@@ -184,6 +185,9 @@ class _FP16OptimizerMixin(object):
     # -- backward -------------------------------------------------------------------------------
     def backward(self, loss):
         """Scale the loss (fp16 only) and back-propagate; grads accumulate in the flat arena."""
+        # deferred overflow check: the previous update's gradient norm has long arrived on the host by now;
+        # the loss scale must be settled before this loss is scaled
+        self.resolve_pending_overflow()
         if self.scaler is not None:
             loss = self.scaler.scale(loss)
         loss.backward()
@@ -276,7 +280,20 @@ class _FP16OptimizerMixin(object):
         grad_norm = self._multiply_factor * raw
         if aggregate_norm_fn is not None:
             grad_norm = aggregate_norm_fn(grad_norm)
-        if self.scaler is not None:
+        if self.scaler is not None and self._deferred_overflow_active(grad_norm):
+            # no host read here: the clip coefficient stays on the device, the fused update skips itself if the
+            # norm is not finite, and the scaler is told before the next backward (resolve_pending_overflow)
+            self.resolve_pending_overflow()
+            factor = self._multiply_factor
+            if max_norm > 0.0:
+                factor = factor * (max_norm / (grad_norm + 1e-6)).clamp_(max=1.0)
+            factor = torch.as_tensor(factor, dtype=torch.float32, device=grad_norm.device)
+            self._multiply_factor = factor
+            self._device_grad_scale = torch.where(
+                torch.isfinite(grad_norm), factor.reciprocal(), torch.full_like(factor, float("inf"))
+            )
+            self._pending_norm = utils.AsyncHostRead(grad_norm)
+        elif self.scaler is not None:
             # ONE host read per step: needed for the overflow decision (skip / rescale)
             norm_host = float(utils.item(grad_norm))
             # downstream consumers (consistency check, gnorm/clip meters) get the host copy: no further
@@ -289,6 +306,42 @@ class _FP16OptimizerMixin(object):
             clip_coef = (max_norm / (grad_norm + 1e-6)).clamp_(max=1.0)
             self._multiply_factor = self._multiply_factor * clip_coef
         return grad_norm
+
+    # -- deferred overflow check ---------------------------------------------------------------------
+    def _deferred_overflow_active(self, grad_norm) -> bool:
+        return (
+            getattr(self, "_fused", False)
+            and getattr(self.args, "deferred_overflow_check", False)
+            and torch.is_tensor(grad_norm)
+            and grad_norm.is_cuda
+        )
+
+    def add_late_overflow_handler(self, fn) -> None:
+        """``fn(message)`` is called when an overflow is discovered after its update was already launched
+        (and skipped on the device); the trainer uses it to take back the update count."""
+        if not hasattr(self, "_late_overflow_handlers"):
+            self._late_overflow_handlers = []
+        self._late_overflow_handlers.append(fn)
+
+    def resolve_pending_overflow(self) -> None:
+        pending = getattr(self, "_pending_norm", None)
+        if pending is None:
+            return
+        self._pending_norm = None
+        norm_host = float(pending.get())
+        try:
+            self.scaler.check_overflow(norm_host)
+        except OverflowError as exc:
+            # the device skipped that update (non-finite divisor): undo the optimistic host bookkeeping
+            inner = self.fp32_optimizer.optimizer
+            for _, master in self._pairs():
+                state = inner.state.get(master, None)
+                if state is not None and state.get("step", 0) > 0:
+                    state["step"] -= 1
+            if getattr(self, "_grads_zeroed", False) and not self._has_accumulated:
+                self._multiply_factor = 1.0 / float(self.scaler.loss_scale)
+            for fn in getattr(self, "_late_overflow_handlers", []):
+                fn(str(exc))
 
     # -- update ---------------------------------------------------------------------------------
     def step(self, closure=None, groups=None):
@@ -330,9 +383,13 @@ class _FP16OptimizerMixin(object):
                 ))
                 offset += n
         factor = self._multiply_factor
+        grad_scale = getattr(self, "_device_grad_scale", None)
+        self._device_grad_scale = None
+        if grad_scale is None:
+            grad_scale = (1.0 / factor) if not torch.is_tensor(factor) else factor.reciprocal()
         ops.fused_adam(
             work,
-            grad_scale=(1.0 / factor) if not torch.is_tensor(factor) else factor.reciprocal(),
+            grad_scale=grad_scale,
             zero_grad=True,
             stochastic_rounding=self.bf16_sr,
         )
@@ -354,6 +411,7 @@ class _FP16OptimizerMixin(object):
         self._grads_zeroed = True
         self._needs_sync = False
         self._has_accumulated = False
+        self._device_grad_scale = None
         self._multiply_factor = 1.0 / float(self.scaler.loss_scale) if self.scaler is not None else 1.0
 
 

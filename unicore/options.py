@@ -52,6 +52,10 @@ def _global_rows():
         _flag("--fp16-no-flatten-grads", action="store_true", help="don't flatten FP16 grads tensor"),
         _flag("--fp16-init-scale", default=2 ** 7, type=int, help="default FP16 loss scale"),
         _flag("--fp16-scale-window", type=int, help="number of updates before increasing loss scale"),
+        _flag("--deferred-overflow-check", action="store_true",
+              help="fp16 + fused optimizer: do not read the gradient norm on the host before the update; the "
+                   "fused Adam kernel skips itself when the norm is non-finite and the loss scaler learns about "
+                   "the overflow before the next backward pass (removes the per-step pipeline drain)"),
         _flag("--fp16-scale-tolerance", default=0.0, type=float,
               help="pct of updates that can overflow before decreasing the loss scale"),
         _flag("--min-loss-scale", default=1e-4, type=float, metavar="D",

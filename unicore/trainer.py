@@ -201,6 +201,8 @@ class Trainer(object):
                 engine.attach_optimizer(self._optimizer)
         else:
             self._optimizer = optim.build_optimizer(self.args, named)
+        if hasattr(self._optimizer, "add_late_overflow_handler"):
+            self._optimizer.add_late_overflow_handler(self._on_late_overflow)
         self._lr_scheduler = lr_scheduler.build_lr_scheduler(self.args, self._optimizer, self._total_train_steps)
         self._lr_scheduler.step_update(0)
 
@@ -718,8 +720,15 @@ class Trainer(object):
         outputs = [{k: reduced["logging_outputs_" + k] for k in keys}] if keys is not None else []
         return outputs, extras
 
+    def _on_late_overflow(self, message):
+        """Deferred overflow check: the skipped update was counted optimistically; take it back."""
+        logger.info("NOTE: gradient overflow detected (update skipped on the device), ignoring gradient, " + message)
+        self.set_num_updates(max(0, self.get_num_updates() - 1))
+
     def _check_grad_norms(self, grad_norm):
         """Non-finite norm => FloatingPointError; all ranks must agree on the norm (replicas in sync)."""
+        if torch.is_tensor(grad_norm) and grad_norm.is_cuda and getattr(self.args, "deferred_overflow_check", False):
+            return  # nothing is read from the device on this path; the scaler sees the norm before the next backward
         if self.data_parallel_world_size > 1 and not getattr(self.args, "no_grad_norm_check", False):
             world = self.data_parallel_world_size
             mine = torch.as_tensor(grad_norm, dtype=torch.double).reshape(1)
@@ -759,11 +768,56 @@ class Trainer(object):
                     self._warn_once.add("loss")
                     logger.warning("Loss.reduce_metrics did not log a 'loss' value, which may break some functionality")
                 metrics.log_scalar("loss", -1)
-            out = agg.get_smoothed_values()
-            out["sample_size"] = sample_size
+            return _LazyStats(agg, sample_size)
+
+
+class _LazyStats(object):
+    """The logging output of one ``train_step``: a read-only mapping that is materialised on first access.
+
+    Producing the smoothed values means bringing device-resident meters to the host, i.e. waiting for the
+    step to finish on the GPU.  Callers that only test ``is not None`` (the CLI between log intervals,
+    the device-timed benchmark) never pay for that; callers that read a value get exactly what the eager
+    version returned.
+    """
+
+    def __init__(self, agg, sample_size):
+        self._agg, self._sample_size, self._values = agg, sample_size, None
+
+    def _get(self):
+        if self._values is None:
+            out = self._agg.get_smoothed_values()
+            out["sample_size"] = self._sample_size
             for key in ("ppl", "wps", "wpb", "bsz"):
                 out.pop(key, None)
-            return out
+            self._values, self._agg = out, None
+        return self._values
+
+    def __getitem__(self, key):
+        return self._get()[key]
+
+    def __contains__(self, key):
+        return key in self._get()
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __len__(self):
+        return len(self._get())
+
+    def get(self, key, default=None):
+        return self._get().get(key, default)
+
+    def keys(self):
+        return self._get().keys()
+
+    def values(self):
+        return self._get().values()
+
+    def items(self):
+        return self._get().items()
+
+    def __repr__(self):
+        return repr(self._get())
 
 
 def _is_nonzero_static(sample_size) -> bool:

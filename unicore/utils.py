@@ -113,6 +113,31 @@ class _HostReader:
 _host_reader = _HostReader()
 
 
+class AsyncHostRead:
+    """A device scalar on its way to the host: the copy is enqueued now, ``get()`` is called later
+    (normally long after the copy has completed, so it does not stall anything)."""
+
+    def __init__(self, t: torch.Tensor):
+        self._value = None
+        if not t.is_cuda:
+            self._value = t.detach().reshape(-1)[0].item()
+            return
+        self._buf = torch.empty(1, dtype=t.dtype, pin_memory=True)
+        self._buf.copy_(t.detach().reshape(-1)[:1], non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(t.device))
+
+    def ready(self) -> bool:
+        return self._value is not None or self._event.query()
+
+    def get(self):
+        if self._value is None:
+            while not self._event.query():
+                pass
+            self._value = self._buf[0].item()
+        return self._value
+
+
 def item(t):
     """``float(t)`` / ``t.item()`` for a device scalar via the polling reader; passes numbers through."""
     if not torch.is_tensor(t):

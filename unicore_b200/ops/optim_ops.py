@@ -91,7 +91,8 @@ def fused_adam(work: List[Dict], grad_scale: Scalar = 1.0, zero_grad: bool = Fal
     Each ``work`` item: ``p`` (fp32 master, or half/bf16 param), ``g`` (grad, any float dtype),
     ``m``/``v`` (fp32), optional ``p_half`` (16-bit copy to write), and scalars ``lr, beta1,
     beta2, eps, step, bias_correction, weight_decay``.  Gradients are divided by ``grad_scale``
-    (python float or device scalar) inside the kernel.  ``zero_grad`` clears ``g`` in the same
+    (python float or device scalar) inside the kernel; a device scalar that is non-finite or zero
+    makes the whole update skip itself (overflowed gradients, see ``--deferred-overflow-check``).  ``zero_grad`` clears ``g`` in the same
     pass; ``stochastic_rounding`` applies to bf16 ``p_half`` outputs (Philox keyed by the CUDA
     generator's seed/offset so all data-parallel ranks round identically).
     """
@@ -114,6 +115,13 @@ def fused_adam(work: List[Dict], grad_scale: Scalar = 1.0, zero_grad: bool = Fal
             scale_f, inv, bool(zero_grad), bool(stochastic_rounding),
         )
         return
+    if torch.is_tensor(grad_scale):
+        gs = float(grad_scale)
+        if not math.isfinite(gs) or gs == 0.0:  # same contract as the kernel: the update skips itself
+            if zero_grad:
+                for w in work:
+                    w["g"].zero_()
+            return
     inv_scale = (1.0 / grad_scale) if not torch.is_tensor(grad_scale) else grad_scale.reciprocal()
     for w in work:
         _adam_reference_math(w, inv_scale, zero_grad, stochastic_rounding)
