@@ -19,8 +19,16 @@ for name, kw in (("plain", {}), ("bias_mask_dropout", dict(bias=bias, key_paddin
         if it == 2:
             os.environ["UNICORE_FMHA_TRACE"] = "1"
             print("==", name, flush=True)
-        ops.fused_attention_qkvpacked(qkv, training=True, **kw)
+        q = qkv.detach().clone().requires_grad_(True)
+        b = kw.get("bias")
+        kw2 = dict(kw)
+        if b is not None:
+            kw2["bias"] = b.detach().clone().requires_grad_(True)
+        out = ops.fused_attention_qkvpacked(q, training=True, **kw2)
+        out.backward(torch.ones_like(out))
         torch.cuda.synchronize()
     os.environ.pop("UNICORE_FMHA_TRACE", None)
+print("bwd phases: 1 issue prefetch(i+1) | 2 lse/delta/bits loads | 3 wait S,dP | 4 softmax-grad math + dBias red + P/dS stores |"
+      " 5 wait prefetch | 6 fence+sync | 7 issue dV,dK,dQ MMAs (+S,dP of i+1) | 8 wait dQ | 9 dQ read-out + red")
 print("phases: 1 wait PV(j-1) | 2 issue copies+sync (K landed) | 3 QK issue | 4 wait bias | 5 wait S | 6 sync |"
       " 7 logits+max | 8 xchg sync | 9 exp/dropout/P store | 10 O rescale | 11 wait V + sync")

@@ -1,5 +1,6 @@
 // Host launchers of the tcgen05 fused attention kernels (csrc/attn/fmha_*_sm100.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -20,6 +21,8 @@ struct FmhaFwdParams {
   float scale, p_drop;
   unsigned long long seed, offset;
   long long* trace;        // profiling only: per-phase clock64() stamps of CTA (0,0,0), thread 0; usually null
+  // TMA descriptors (csrc/attn/tma_map.h): 128 x 64 tiles of q / k / v, 128 x 128 tiles of the bias
+  CUtensorMap tm_q, tm_k, tm_v, tm_bias;
 };
 void launch_fmha_fwd(const FmhaFwdParams& p, cudaStream_t stream);
 
@@ -32,8 +35,16 @@ struct FmhaBwdParams {
   void* dk;          // that they can be slices of one packed [B, L, 3, H, 64] gradient tensor
   void* dv;
   long long dq_sb, dq_sl, dq_sh, dk_sb, dk_sl, dk_sh, dv_sb, dv_sl, dv_sh;
-  float* dbias;      // [bias_batch, H, Lq, Lk] fp32, zero-initialised; null when not needed
+  // Bias gradient: every CTA stores its 16-bit dS tile (already in shared memory for the MMAs) with ONE TMA
+  // store into ds_buf [B, H, Lq, Lk]; a follow-up kernel sums it over the batch into dbias (fp32 accumulate)
+  // when the bias is shared by the batch.  (fp32 atomics on a shared dbias tensor were the bottleneck of the
+  // kernel: 4096 red.v4 per tile.)  Both null when the bias needs no gradient.
+  void* ds_buf;      // [B, H, Lq, Lk] 16-bit
+  void* dbias;       // [bias_batch, H, Lq, Lk] 16-bit; == ds_buf when bias_batch == B
+  CUtensorMap tm_ds;
   int debug_flags;   // profiling only: 1 = skip dBias reductions, 2 = skip dQ reductions, 4 = skip exp/dS math
+  long long* trace;  // profiling only: clock64() stamps of one CTA (see UB_BTRACE); usually null
+  CUtensorMap tm_do;  // 128 x 64 tiles of dO
 };
 void launch_fmha_bwd(const FmhaBwdParams& p, cudaStream_t stream);
 

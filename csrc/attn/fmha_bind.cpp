@@ -10,6 +10,7 @@
 #include <optional>
 
 #include "fmha_api.h"
+#include "tma_map.h"
 
 namespace {
 using torch::Tensor;
@@ -72,6 +73,17 @@ void fill_common(ub::FmhaFwdParams& p, const Tensor& q, const Tensor& k, const T
   }
   p.p_drop = (float)p_drop;
   p.scale = (float)scale;
+  // The driver API behind cuTensorMapEncodeTiled needs a current context in THIS thread; autograd worker
+  // threads only have the c10 device guard's notion of the device, so bind the primary context explicitly.
+  cudaSetDevice(q.get_device());
+  // TMA descriptors: heads must be contiguous (stride 64) so that (head, 16-byte chunk) is one dimension
+  TORCH_CHECK(q.stride(2) == 64 && k.stride(2) == 64 && v.stride(2) == 64, "q/k/v head stride must be 64");
+  const bool bf16 = p.is_bf16 != 0;
+  bool ok = ub::make_head_tile_map(&p.tm_q, p.q, bf16, p.B, p.Lq, p.H, p.q_sb, p.q_sl, 128);
+  ok = ok && ub::make_head_tile_map(&p.tm_k, p.k, bf16, p.B, p.Lk, p.H, p.k_sb, p.k_sl, 128);
+  ok = ok && ub::make_head_tile_map(&p.tm_v, p.v, bf16, p.B, p.Lk, p.H, p.v_sb, p.v_sl, 128);
+  if (p.bias != nullptr) ok = ok && ub::make_bias_tile_map(&p.tm_bias, p.bias, bf16, p.bias_batch * p.H, p.Lq, p.Lk);
+  TORCH_CHECK(ok, "cuTensorMapEncodeTiled failed for the attention operands");
 }
 
 std::tuple<Tensor, Tensor, OptTensor> fmha_fwd(const Tensor& q, const Tensor& k, const Tensor& v,
@@ -136,6 +148,9 @@ std::tuple<Tensor, Tensor, Tensor, OptTensor> fmha_bwd(const Tensor& dout, const
     p.f.drop_bits = reinterpret_cast<uint32_t*>(drop_bits->data_ptr());
   }
   p.dout = dout.data_ptr();
+  TORCH_CHECK(ub::make_head_tile_map(&p.tm_do, p.dout, p.f.is_bf16 != 0, p.f.B, p.f.Lq, p.f.H,
+                                     (long long)p.f.Lq * p.f.H * 64, (long long)p.f.H * 64, 128),
+              "cuTensorMapEncodeTiled failed for dO");
   {
     const char* dbg = std::getenv("UNICORE_FMHA_DEBUG");
     p.debug_flags = dbg ? std::atoi(dbg) : 0;
@@ -158,17 +173,40 @@ std::tuple<Tensor, Tensor, Tensor, OptTensor> fmha_bwd(const Tensor& dout, const
   p.dk_sb = dk.stride(0); p.dk_sl = dk.stride(1); p.dk_sh = dk.stride(2);
   p.dv_sb = dv.stride(0); p.dv_sl = dv.stride(1); p.dv_sh = dv.stride(2);
   OptTensor dbias;
+  Tensor ds_buf;
   p.dbias = nullptr;
+  p.ds_buf = nullptr;
   if (need_dbias && p.f.bias != nullptr) {
-    dbias = torch::zeros({p.f.bias_batch, p.f.H, p.f.Lq, p.f.Lk}, q.options().dtype(at::kFloat));
-    p.dbias = dbias->data_ptr<float>();
+    ds_buf = torch::empty({p.f.B, p.f.H, p.f.Lq, p.f.Lk}, q.options());
+    p.ds_buf = ds_buf.data_ptr();
+    dbias = (p.f.bias_batch == p.f.B) ? ds_buf : torch::empty({p.f.bias_batch, p.f.H, p.f.Lq, p.f.Lk}, q.options());
+    p.dbias = dbias->data_ptr();
+    TORCH_CHECK(ub::make_bias_tile_map(&p.tm_ds, p.ds_buf, p.f.is_bf16 != 0, p.f.B * p.f.H, p.f.Lq, p.f.Lk),
+                "cuTensorMapEncodeTiled failed for the dS scratch tensor");
   }
   p.delta = delta.data_ptr<float>();
   p.dq_acc = dq_acc.data_ptr<float>();
   p.dq = dq.data_ptr();
   p.dk = dk.data_ptr();
   p.dv = dv.data_ptr();
+  Tensor btrace;
+  p.trace = nullptr;
+  if (std::getenv("UNICORE_FMHA_TRACE") != nullptr) {
+    btrace = torch::zeros({64, 12}, q.options().dtype(at::kLong));
+    p.trace = reinterpret_cast<long long*>(btrace.data_ptr<int64_t>());
+  }
   ub::launch_fmha_bwd(p, at::cuda::getCurrentCUDAStream().stream());
+  if (p.trace != nullptr) {
+    Tensor host = btrace.cpu();
+    auto acc = host.accessor<int64_t, 2>();
+    const int tiles = (p.f.Lq + 127) / 128;
+    for (int j = 0; j < tiles && j < 64; ++j) {
+      printf("fmha_bwd trace tile %d:", j);
+      for (int sidx = 1; sidx < 10; ++sidx) printf(" %lld", (long long)(acc[j][sidx] - acc[j][sidx - 1]));
+      if (j > 0) printf("  | since prev tile start %lld", (long long)(acc[j][0] - acc[j - 1][0]));
+      printf("\n");
+    }
+  }
   cudaError_t err = cudaGetLastError();
   TORCH_CHECK(err == cudaSuccess, "fmha_bwd launch failed: ", cudaGetErrorString(err));
   return {dq, dk, dv, dbias};

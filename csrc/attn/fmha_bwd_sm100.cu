@@ -113,16 +113,24 @@ __global__ void __launch_bounds__(256) fmha_cast_kernel(const float* __restrict_
 }
 
 // ---- main kernel ----------------------------------------------------------------------------------------------
+#define UB_BTRACE(slot)                                                                     \
+  do {                                                                                      \
+    if (trace != nullptr) trace[i * 12 + (slot)] = clock64();                               \
+  } while (0)
+
 template <typename T>
-__global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams bp) {
+__global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_constant__ FmhaBwdParams bp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const FmhaFwdParams& p = bp.f;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & 127, quarter = tid >> 7;  // thread = (tile row, 32-column quarter)
   const int col0 = quarter * 32;                // my columns inside the key tile
   const int key_tile0 = blockIdx.x * kBN, h = blockIdx.y, b = blockIdx.z;
+  long long* trace = (bp.trace != nullptr && tid == 0 && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 1) ? bp.trace : nullptr;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_a = smem_base + kOffBar, bar_b = smem_base + kOffBar + 8;
+  // TMA completion barriers: the K/V tiles of this CTA, and the two (Q, dO, bias) input buffers
+  const uint32_t bar_kv = smem_base + kOffBar + 24, bar_in0 = smem_base + kOffBar + 32;  // bar_in1 = bar_in0 + 8
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 16);
   float* kadd = reinterpret_cast<float*>(smem + kOffKAdd);
 
@@ -133,6 +141,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
   if (tid == 0) {
     mbar_init(bar_a, 1);
     mbar_init(bar_b, 1);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_in0, 1);
+    mbar_init(bar_in0 + 8, 1);
     fence_mbarrier_init();
   }
   const T* qg = reinterpret_cast<const T*>(p.q) + (long long)b * p.q_sb + (long long)h * p.q_sh;
@@ -147,36 +158,37 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
                                 : nullptr;
   const int n_qtiles = (p.Lq + kBM - 1) / kBM;
 
-  auto issue_tile = [&](int i) {  // asynchronous copies of everything tile i needs
+  constexpr uint32_t kTileBytes = kBM * kD * 2, kBiasBytes = kBM * kBN * 2;
+  const int bias_nb = bb * p.H + h;
+  auto issue_tile = [&](int i) {  // ONE thread: three TMA boxes bring everything tile i needs
     const int q0 = i * kBM;
-    const int q_valid = min(kBM, p.Lq - q0);
     const uint32_t buf = (uint32_t)(i & 1);
-    cp_async_tile64<kBwdThreads, T>(smem_base + kOffQ + buf * 16384, qg + (long long)q0 * p.q_sl, p.q_sl, q_valid);
-    cp_async_tile64<kBwdThreads, T>(smem_base + kOffDO + buf * 16384, dog + (long long)q0 * o_sl, o_sl, q_valid);
-    if (has_bias)
-      cp_async_tile128<kBwdThreads, T>(smem_base + kOffDS + buf * 32768, bias_base + (long long)q0 * p.Lk, p.Lk,
-                                       q_valid, k_valid);
+    const uint32_t bar = bar_in0 + buf * 8;
+    mbar_expect_tx(bar, 2 * kTileBytes + (has_bias ? kBiasBytes : 0u));
+    tma_load_5d(smem_base + kOffQ + buf * 16384, &p.tm_q, 0, 0, h * 8, q0 / 8, b, bar);
+    tma_load_5d(smem_base + kOffDO + buf * 16384, &bp.tm_do, 0, 0, h * 8, q0 / 8, b, bar);
+    if (has_bias) tma_load_5d(smem_base + kOffDS + buf * 32768, &p.tm_bias, 0, 0, key_tile0 / 8, q0 / 8, bias_nb, bar);
   };
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t idesc_s = make_idesc_f16(kBM, kBN, kFmt, 0, 0);    // S, dP: both operands K-major
   constexpr uint32_t idesc_t = make_idesc_f16(kBN, kD, kFmt, 1, 1);     // dV, dK: both operands MN-major
   constexpr uint32_t idesc_q = make_idesc_f16(kBM, kD, kFmt, 0, 1);     // dQ: A K-major, B MN-major
 
-  cp_async_tile64<kBwdThreads, T>(smem_base + kOffK, kg + (long long)key_tile0 * p.k_sl, p.k_sl, k_valid);
-  cp_async_tile64<kBwdThreads, T>(smem_base + kOffV, vg + (long long)key_tile0 * p.v_sl, p.v_sl, k_valid);
-  issue_tile(0);
-  cp_async_commit();
   bool key_masked = false;
   if (tid < kBN) {
     const int key = key_tile0 + tid;
     key_masked = key >= p.Lk || (p.kpm != nullptr && p.kpm[(long long)b * p.Lk + key] != 0);
     kadd[tid] = key_masked ? -CUDART_INF_F : 0.f;
   }
-  cp_async_wait<0>();
-  fence_proxy_async_smem();
   fence_before_thread_sync();
   const bool tile_masked = __syncthreads_or(key_masked) != 0;  // usually no key of the tile is masked
   fence_after_thread_sync();
+  if (tid == 0) {  // barriers are initialised: K, V of this CTA and the first (Q, dO, bias) tile
+    mbar_expect_tx(bar_kv, 2 * kTileBytes);
+    tma_load_5d(smem_base + kOffK, &p.tm_k, 0, 0, h * 8, key_tile0 / 8, b, bar_kv);
+    tma_load_5d(smem_base + kOffV, &p.tm_v, 0, 0, h * 8, key_tile0 / 8, b, bar_kv);
+    issue_tile(0);
+  }
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 
@@ -198,7 +210,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
     }
     umma_commit(bar_a);
   };
-  if (tid == 0) issue_s_dp(0);
+  if (tid == 0) {
+    mbar_wait(bar_kv, 0);
+    mbar_wait(bar_in0, 0);
+    issue_s_dp(0);
+  }
 
   const bool drop = p.p_drop > 0.f && p.drop_bits != nullptr;
   // same 14-bit threshold arithmetic as the forward kernel (common.cuh)
@@ -213,8 +229,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
     const uint32_t buf = (uint32_t)(i & 1);
     const uint32_t sQ = smem_base + kOffQ + buf * 16384, sDO = smem_base + kOffDO + buf * 16384;
     const uint32_t offDS = kOffDS + buf * 32768;
-    if (i + 1 < n_qtiles) issue_tile(i + 1);  // prefetch under the softmax of tile i
-    cp_async_commit();
+    UB_BTRACE(0);
+    // prefetch tile i+1 under the softmax of tile i (its buffers were released by the MMAs of tile i-1,
+    // whose completion every thread observed on bar_b at the end of the previous iteration)
+    if (tid == 0 && i + 1 < n_qtiles) {
+      tma_store_wait_read();  // the dS store of tile i-1 has finished reading the buffer tile i+1 lands in
+      issue_tile(i + 1);
+    }
+    if (has_bias) mbar_wait(bar_in0 + buf * 8, (uint32_t)((i >> 1) & 1));  // bias tile i is visible to ordinary loads
+    UB_BTRACE(1);
 
     const int row = q0 + r;
     const bool row_valid = row < p.Lq;
@@ -227,13 +250,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
     uint32_t keep_word = 0xffffffffu;
     if (drop && row_valid && key_tile0 + col0 < p.Lk)
       keep_word = p.drop_bits[stat_idx * words_per_row + ((key_tile0 + col0) >> 5)];
-    float* dbias_row = (bp.dbias != nullptr && row_valid)
-                           ? bp.dbias + (((long long)bb * p.H + h) * p.Lq + row) * p.Lk + key_tile0
-                           : nullptr;
-
+    UB_BTRACE(2);
     mbar_wait(bar_a, phase_a);
     phase_a ^= 1;
     fence_after_thread_sync();
+    UB_BTRACE(3);
     {
       uint32_t acc[32], dpr[32];
       tmem_ld32(lane_base + kColS + col0, acc);
@@ -272,10 +293,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
           ds[2 * e] = d2.x;                   // the softmax scale is applied to dQ / dK at read-out
           ds[2 * e + 1] = d2.y;
         }
-        if (dbias_row != nullptr && key_tile0 + col0 + v * 8 < p.Lk && !(bp.debug_flags & 1)) {
-          red_add_v4(dbias_row + col0 + v * 8, ds[0], ds[1], ds[2], ds[3]);
-          red_add_v4(dbias_row + col0 + v * 8 + 4, ds[4], ds[5], ds[6], ds[7]);
-        }
         Vec16 op, od;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -286,13 +303,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
         *reinterpret_cast<Vec16*>(smem + offDS + off) = od;   // in place over the consumed bias chunk
       }
     }
-    cp_async_wait<0>();   // my share of tile i+1 has landed; the barrier below publishes it
-    fence_proxy_async_smem();
+    UB_BTRACE(4);
+    UB_BTRACE(5);
+    fence_proxy_async_smem();   // my P / dS stores (generic proxy) before the tensor core (async proxy) reads them
     fence_before_thread_sync();
     __syncthreads();
+    UB_BTRACE(6);
     if (tid == 0) {
       fence_after_thread_sync();
       const uint32_t sDS = smem_base + offDS;
+      if (bp.ds_buf != nullptr) {  // bias gradient: the dS tile leaves through one TMA store
+        tma_store_5d(&bp.tm_ds, 0, 0, key_tile0 / 8, q0 / 8, b * p.H + h, sDS);
+        tma_store_commit();
+      }
 #pragma unroll
       for (int kk = 0; kk < kBM / 16; ++kk) {  // reduction over the 128 query rows, 16 per step
         const uint64_t a_p = make_smem_desc(smem_base + kOffP + kk * 4096, 2048, 128);    // P^T  (MN-major)
@@ -313,11 +336,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
       }
       umma_commit(bar_b);
       // next tile's S / dP run on the tensor core while the dQ read-out and the atomics proceed
-      if (i + 1 < n_qtiles) issue_s_dp(i + 1);
+      if (i + 1 < n_qtiles) {
+        mbar_wait(bar_in0 + (uint32_t)((i + 1) & 1) * 8, (uint32_t)(((i + 1) >> 1) & 1));  // Q, dO of tile i+1 landed
+        issue_s_dp(i + 1);
+      }
     }
+    UB_BTRACE(7);
     mbar_wait(bar_b, phase_b);
     phase_b ^= 1;
     fence_after_thread_sync();
+    UB_BTRACE(8);
     {  // dQ_i partial -> global fp32 accumulator (16 of the 64 columns per thread)
       uint32_t acc[16];
       tmem_ld16(lane_base + kColDQ + quarter * 16, acc);
@@ -330,6 +358,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
                      __uint_as_float(acc[v * 4 + 2]) * p.scale, __uint_as_float(acc[v * 4 + 3]) * p.scale);
       }
     }
+    UB_BTRACE(9);
   }
 
   // ---- epilogue: dK_j, dV_j (16 of the 64 columns per thread) ---------------------------------------------------
@@ -359,9 +388,36 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(FmhaBwdParams 
       }
     }
   }
+  if (tid == 0) tma_store_wait_read();  // shared memory must outlive the last dS store's reads
   fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, kBwdTmemCols);
+}
+
+// dbias[n] = sum_b ds[b, n] (fp32 accumulate), n over H * Lq * Lk in 16-byte vectors
+template <typename T>
+__global__ void __launch_bounds__(256) fmha_dbias_reduce_kernel(const T* __restrict__ ds, T* __restrict__ dbias, int B,
+                                                                  long long nvec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b0 = 0; b0 < B; b0 += 4) {
+      Vec16 in[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (b0 + u < B) in[u] = ld_global_nc_v4(ds + ((long long)(b0 + u) * nvec + v) * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (b0 + u < B) {
+          float x[8];
+          unpack<T>(in[u], x);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += x[e];
+        }
+      }
+    }
+    st_global_v4(dbias + v * 8, pack<T>(acc));
+  }
 }
 
 template <typename T>
@@ -374,6 +430,13 @@ void run_bwd(const FmhaBwdParams& bp, cudaStream_t stream) {
   auto kern = fmha_bwd_kernel<T>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes);
   kern<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(bp);
+  if (bp.ds_buf != nullptr && bp.dbias != bp.ds_buf) {
+    const long long nv = (long long)p.H * p.Lq * p.Lk / 8;
+    long long rb = (nv + 255) / 256;
+    if (rb > 148 * 16) rb = 148 * 16;
+    fmha_dbias_reduce_kernel<T><<<(unsigned)rb, 256, 0, stream>>>(reinterpret_cast<const T*>(bp.ds_buf),
+                                                                 reinterpret_cast<T*>(bp.dbias), p.B, nv);
+  }
   const long long nvec = nrows * 64 / 8;
   long long blocks = (nvec + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;

@@ -69,7 +69,7 @@ UB_DEVICE uint32_t pack2<__nv_bfloat16>(float a, float b) {
   } while (0)
 
 template <typename T>
-__global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_constant__ FmhaFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & 127, half = tid >> 7;   // thread = (tile row, 64-key half)
@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
   long long* trace = (p.trace != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 1 && blockIdx.z == 1) ? p.trace : nullptr;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_s = smem_base + kSmemBar, bar_o = smem_base + kSmemBar + 8;
+  // TMA completion barriers: K tiles (the first phase also covers Q), V tiles, bias tiles
+  const uint32_t bar_k = smem_base + kSmemBar + 24, bar_v = smem_base + kSmemBar + 32, bar_b = smem_base + kSmemBar + 40;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemBar + 16);
   float* kadd = reinterpret_cast<float*>(smem + kSmemKAdd);
   float* xchg = reinterpret_cast<float*>(smem + kSmemXchg);
@@ -88,6 +90,9 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
   if (tid == 0) {
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_b, 1);
     fence_mbarrier_init();
   }
   const T* qg = reinterpret_cast<const T*>(p.q) + (long long)b * p.q_sb + (long long)h * p.q_sh + (long long)q0 * p.q_sl;
@@ -98,18 +103,20 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
   const T* bias_tile = has_bias ? reinterpret_cast<const T*>(p.bias) +
                                       (((long long)(p.bias_batch > 1 ? b : 0) * p.H + h) * p.Lq + q0) * p.Lk
                                 : nullptr;
-  // prologue copies: Q and K_0 (one group)
-  cp_async_tile64<kFwdThreads, T>(smem_base + kSmemQ, qg, p.q_sl, q_valid);
   // All CTAs walk the key tiles in the same order on purpose: CTAs of different batch entries then hit the
   // same bias lines in L2 at about the same time (a rotated order measured 4 % slower).
   const int n_tiles = (p.Lk + kBlockN - 1) / kBlockN;
   constexpr int rot = 0;
-  cp_async_tile64<kFwdThreads, T>(smem_base + kSmemK, kg + (long long)(rot * kBlockN) * p.k_sl, p.k_sl,
-                                  min(kBlockN, p.Lk - rot * kBlockN));
-  cp_async_commit();
+  constexpr uint32_t kTileBytes = kBlockM * kHeadDim * 2, kBiasBytes = kBlockM * kBlockN * 2;
+  const int bias_nb = (p.bias_batch > 1 ? b : 0) * p.H + h;
   fence_before_thread_sync();
   __syncthreads();
   fence_after_thread_sync();
+  if (tid == 0) {  // Q tile and K_0: two TMA boxes, one barrier phase
+    mbar_expect_tx(bar_k, 2 * kTileBytes);
+    tma_load_5d(smem_base + kSmemQ, &p.tm_q, 0, 0, h * 8, q0 / 8, b, bar_k);
+    tma_load_5d(smem_base + kSmemK, &p.tm_k, 0, 0, h * 8, (rot * kBlockN) / 8, b, bar_k);
+  }
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's TMEM lanes
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
@@ -143,20 +150,21 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
       fence_after_thread_sync();
     }
     UB_TRACE(1);
-    // group "bias_j" (into the P buffer), then group "V_j"; K_j is the older group already in flight
-    if (has_bias)
-      cp_async_tile128<kFwdThreads, T>(smem_base + kSmemP, bias_tile + key_tile0, p.Lk, q_valid, k_valid);
-    cp_async_commit();
-    cp_async_tile64<kFwdThreads, T>(smem_base + kSmemV, vg + (long long)key_tile0 * p.v_sl, p.v_sl, k_valid);
-    cp_async_commit();
+    if (tid == 0) {  // bias_j lands in the P buffer (PV_{j-1} has released it), V_j in the V buffer
+      if (has_bias) {
+        mbar_expect_tx(bar_b, kBiasBytes);
+        tma_load_5d(smem_base + kSmemP, &p.tm_bias, 0, 0, key_tile0 / 8, q0 / 8, bias_nb, bar_b);
+      }
+      mbar_expect_tx(bar_v, kTileBytes);
+      tma_load_5d(smem_base + kSmemV, &p.tm_v, 0, 0, h * 8, key_tile0 / 8, b, bar_v);
+    }
     bool masked = false;
     if (tid < kBlockN) {  // additive key mask of this tile
       const int key = key_tile0 + tid;
       masked = key >= p.Lk || (kpm_row != nullptr && kpm_row[key] != 0);
       kadd[tid] = masked ? -CUDART_INF_F : 0.f;
     }
-    cp_async_wait<2>();            // all but {bias_j, V_j}: Q (first tile) and K_j have landed
-    fence_proxy_async_smem();
+    mbar_wait(bar_k, (uint32_t)(j & 1));   // K_j (and Q on the first tile) have landed
     const bool tile_masked = __syncthreads_or(masked) != 0;  // most tiles have no masked key: skip the adds
     UB_TRACE(2);
     if (tid == 0) {
@@ -170,18 +178,17 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
       umma_commit(bar_s);
     }
     UB_TRACE(3);
-    cp_async_wait<1>();            // my share of the bias tile has landed (V_j may still be in flight)
+    if (has_bias) mbar_wait(bar_b, (uint32_t)(j & 1));   // the bias tile is visible to ordinary loads now
     UB_TRACE(4);
     mbar_wait(bar_s, phase_s);
     phase_s ^= 1;
     fence_after_thread_sync();
     UB_TRACE(5);
-    __syncthreads();               // everyone's bias chunks are visible; K buffer is free (S is complete)
+    if (tid == 0 && j + 1 < n_tiles) {  // S is complete, so the K buffer is free: prefetch K_{j+1} under the softmax
+      mbar_expect_tx(bar_k, kTileBytes);
+      tma_load_5d(smem_base + kSmemK, &p.tm_k, 0, 0, h * 8, (jt_next * kBlockN) / 8, b, bar_k);
+    }
     UB_TRACE(6);
-    if (j + 1 < n_tiles)           // prefetch K_{j+1} under the softmax
-      cp_async_tile64<kFwdThreads, T>(smem_base + kSmemK, kg + (long long)(jt_next * kBlockN) * p.k_sl, p.k_sl,
-                                      min(kBlockN, p.Lk - jt_next * kBlockN));
-    cp_async_commit();             // (possibly empty) group "K_{j+1}": keeps the group arithmetic uniform
 
     // ---- logits of my 64 columns in registers: x = acc*scale + bias (+ key mask), packed fp32x2 math ------
     F2 x[32];
@@ -273,8 +280,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(FmhaFwdParams 
       tmem_wait_st();
     }
     UB_TRACE(10);
-    cp_async_wait<1>();            // V_j has landed (K_{j+1} may still be in flight)
-    fence_proxy_async_smem();
+    mbar_wait(bar_v, (uint32_t)(j & 1));   // V_j has landed
+    fence_proxy_async_smem();      // my P stores (generic proxy) before the tensor core (async proxy) reads them
     fence_before_thread_sync();
     __syncthreads();
     UB_TRACE(11);

@@ -140,6 +140,28 @@ TC_DEVICE uint32_t tile64_off(int row, int chunk) { return (uint32_t)((row >> 3)
 // same for a [rows x 128 halfs] tile (16 chunks per row) => 2048 bytes per 8-row group.
 TC_DEVICE uint32_t tile128_off(int row, int chunk) { return (uint32_t)((row >> 3) * 2048 + chunk * 128 + (row & 7) * 16); }
 
+// ---- TMA: 5-D tiled tensor copy global -> shared, completion counted on an mbarrier ---------------------
+TC_DEVICE void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+TC_DEVICE void tma_load_5d(uint32_t dst_smem, const void* tensor_map, int c0, int c1, int c2, int c3, int c4,
+                           uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst_smem), "l"(tensor_map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
+}
+
+// shared -> global tile store through a tensor map (bulk async-group completion); out-of-bounds parts clipped
+TC_DEVICE void tma_store_5d(const void* tensor_map, int c0, int c1, int c2, int c3, int c4, uint32_t src_smem) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(tensor_map),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(src_smem)
+               : "memory");
+}
+TC_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed stores of this thread have finished READING shared memory (the source may be overwritten)
+TC_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---- asynchronous global -> shared copies (LDGSTS); src_bytes = 0 zero-fills the 16 destination bytes --------
 TC_DEVICE void cp_async16(uint32_t smem_addr, const void* gptr, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");

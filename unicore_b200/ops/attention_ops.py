@@ -93,7 +93,7 @@ def fused_attention_supported(q, k, v, bias=None, key_padding_mask=None) -> bool
     if key_padding_mask is not None and key_padding_mask.dtype != torch.bool:
         return False
     for t in (q, k, v):
-        if t.data_ptr() % 16 != 0 or any(s % 8 != 0 for s in t.stride()[:3]):
+        if t.data_ptr() % 16 != 0 or any(s % 8 != 0 for s in t.stride()[:3]) or t.stride(2) != 64:
             return False
     if q.dtype not in (torch.float16, torch.bfloat16) or k.dtype != q.dtype or v.dtype != q.dtype:
         return False
