@@ -44,11 +44,13 @@ constexpr uint32_t kTmemColS = 0, kTmemColO = 128;
 constexpr uint32_t kSmemQ = 0;
 constexpr uint32_t kSmemK = 16384;
 constexpr uint32_t kSmemV = 32768;
-constexpr uint32_t kSmemP = 49152;            // 128 x 128 x 2 = 32768 bytes: bias tile, then P
-constexpr uint32_t kSmemKAdd = 81920;         // float[128]: 0 or -inf per key of the tile
-constexpr uint32_t kSmemXchg = 81920 + 512;   // float[256]: row max / row sum exchange between halves
-constexpr uint32_t kSmemBar = 81920 + 512 + 1024;
-constexpr uint32_t kFwdSmemBytes = kSmemBar + 64;
+constexpr uint32_t kSmemP = 49152;            // 128 x 128 x 2 = 32768 bytes: P
+constexpr uint32_t kSmemBias = 81920;         // 32768 bytes: bias tile of the NEXT key tile (TMA, one tile ahead)
+constexpr uint32_t kSmemXchg = kSmemBias;     // float[256] row max / row sum exchange: aliases the bias tile, which
+                                              // is dead between "logits done" and the next bias copy
+constexpr uint32_t kSmemKAdd = 81920 + 32768; // float[128]: 0 or -inf per key of the tile
+constexpr uint32_t kSmemBar = kSmemKAdd + 512;
+constexpr uint32_t kFwdSmemBytes = kSmemBar + 64;   // 115,264 B: two CTAs (+1 KB reserve each) fit in 228 KB
 
 template <typename T>
 UB_DEVICE uint32_t pack2(float a, float b);
@@ -81,7 +83,10 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
   const uint32_t bar_k = smem_base + kSmemBar + 24, bar_v = smem_base + kSmemBar + 32, bar_b = smem_base + kSmemBar + 40;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemBar + 16);
   float* kadd = reinterpret_cast<float*>(smem + kSmemKAdd);
-  float* xchg = reinterpret_cast<float*>(smem + kSmemXchg);
+  // exchange slots of the two threads that share a query row: inside the bias tile, each in the first chunk
+  // that only its owner ever reads (so no other thread's bias loads can race with the write)
+  float* xchg_mine = reinterpret_cast<float*>(smem + kSmemXchg + tile128_off(r, half * 8));
+  float* xchg_peer = reinterpret_cast<float*>(smem + kSmemXchg + tile128_off(r, (half ^ 1) * 8));
 
   if (warp == 0) {
     tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -116,6 +121,10 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
     mbar_expect_tx(bar_k, 2 * kTileBytes);
     tma_load_5d(smem_base + kSmemQ, &p.tm_q, 0, 0, h * 8, q0 / 8, b, bar_k);
     tma_load_5d(smem_base + kSmemK, &p.tm_k, 0, 0, h * 8, (rot * kBlockN) / 8, b, bar_k);
+    if (p.bias != nullptr) {
+      mbar_expect_tx(bar_b, kBiasBytes);
+      tma_load_5d(smem_base + kSmemBias, &p.tm_bias, 0, 0, (rot * kBlockN) / 8, q0 / 8, bias_nb, bar_b);
+    }
   }
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's TMEM lanes
@@ -150,11 +159,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
       fence_after_thread_sync();
     }
     UB_TRACE(1);
-    if (tid == 0) {  // bias_j lands in the P buffer (PV_{j-1} has released it), V_j in the V buffer
-      if (has_bias) {
-        mbar_expect_tx(bar_b, kBiasBytes);
-        tma_load_5d(smem_base + kSmemP, &p.tm_bias, 0, 0, key_tile0 / 8, q0 / 8, bias_nb, bar_b);
-      }
+    if (tid == 0) {  // V_j into the V buffer (PV_{j-1} has released it); bias_j was requested one tile ago
       mbar_expect_tx(bar_v, kTileBytes);
       tma_load_5d(smem_base + kSmemV, &p.tm_v, 0, 0, h * 8, key_tile0 / 8, b, bar_v);
     }
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
         float bf[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) bf[e] = 0.f;
-        if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(smem + kSmemP + tile128_off(r, (col0 >> 3) + v)), bf);
+        if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(smem + kSmemBias + tile128_off(r, (col0 >> 3) + v)), bf);
         if (tile_masked) {
           const float4 ka = *reinterpret_cast<const float4*>(kadd + col0 + v * 8);
           const float4 kb = *reinterpret_cast<const float4*>(kadd + col0 + v * 8 + 4);
@@ -222,10 +227,15 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
       }
     }
     UB_TRACE(7);
-    xchg[tid] = m_part;
+    *xchg_mine = m_part;           // my own (already consumed) bias chunk doubles as exchange space
     __syncthreads();
     UB_TRACE(8);
-    const float m_tile = fmaxf(m_part, xchg[tid ^ 128]);
+    const float m_tile = fmaxf(m_part, *xchg_peer);
+    __syncthreads();               // exchange read by everybody: the bias tile of the next key tile may land now
+    if (tid == 0 && has_bias && j + 1 < n_tiles) {
+      mbar_expect_tx(bar_b, kBiasBytes);
+      tma_load_5d(smem_base + kSmemBias, &p.tm_bias, 0, 0, (jt_next * kBlockN) / 8, q0 / 8, bias_nb, bar_b);
+    }
     const float m_new = fmaxf(m_run, m_tile);
     const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
     const float alpha = exp2f((m_run - m_use) * kLog2e);  // m_run = -inf -> 0
@@ -300,11 +310,11 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
   }
 
   // ---- epilogue ---------------------------------------------------------------------------------------
-  xchg[tid] = l_run;
+  *xchg_mine = l_run;
   mbar_wait(bar_o, phase_o);
   fence_after_thread_sync();
   __syncthreads();
-  const float l_tot = l_run + xchg[tid ^ 128];
+  const float l_tot = l_run + *xchg_peer;
   const float inv_l = l_tot > 0.f ? keep_scale / l_tot : 0.f;
   {
     uint32_t acc[32];
