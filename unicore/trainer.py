@@ -497,7 +497,9 @@ class Trainer(object):
             logging_outputs, (sample_size, ooms, total_train_time) = self._aggregate_logging_outputs(
                 logging_outputs, sample_size, ooms, train_time, ignore=False, is_train=True
             )
-            self._cumulative_training_time = float(total_train_time) / self.data_parallel_world_size
+            # kept as the (device) tensor the all-reduce produced: converting it here would drain the launch
+            # queue right after backward on every multi-GPU step; cumulative_training_time() converts lazily
+            self._cumulative_training_time = total_train_time / self.data_parallel_world_size
 
         overflow = False
         grad_norm = None
@@ -645,6 +647,8 @@ class Trainer(object):
     def cumulative_training_time(self):
         if self._cumulative_training_time is None:
             return self._local_cumulative_training_time()
+        if torch.is_tensor(self._cumulative_training_time):
+            self._cumulative_training_time = float(utils.item(self._cumulative_training_time))
         return self._cumulative_training_time
 
     def _local_cumulative_training_time(self):
