@@ -384,7 +384,8 @@ def main():
         global_batch = world * a.batch_size * a.update_freq
         value = global_batch * a.steps / (elapsed_ms / 1e3)
         result = {
-            "metric": "BERT-base masked-LM training throughput (samples/s, whole job, device-timed, max over ranks)",
+            "metric": "{} masked-LM training throughput (samples/s, whole job, device-timed, max over ranks)".format(
+                {"bert_base": "BERT-base", "bert_large": "BERT-large"}.get(a.arch, a.arch)),
             "impl": a.impl,
             "value": value,
             "unit": "samples/s",
@@ -407,8 +408,8 @@ def main():
                 "vocab": a.vocab,
                 "parallelism": "dp{}".format(world),
                 "ddp_backend": getattr(args, "ddp_backend", None),
-                "optimizer": "adam(0.9,0.98) clip 1.0 polynomial_decay, {} dynamic loss scale{}".format(
-                    a.precision,
+                "optimizer": "adam(0.9,0.98) clip 1.0 polynomial_decay, {}{}".format(
+                    "fp16 dynamic loss scale" if a.precision == "fp16" else "bf16 (no loss scaling)",
                     " (overflow skip decided on the device, scaler updated before the next backward)"
                     if (a.impl != "reference" and a.precision == "fp16" and not a.sync_overflow_check) else ""),
                 "l2": "no explicit flush: each step streams >1.7 GB of weights/optimizer state/activations, "

@@ -30,7 +30,8 @@ struct FmhaBwdParams {
   FmhaFwdParams f;   // same inputs as forward (out/lse hold the forward results)
   const void* dout;  // [B, Lq, H, 64] contiguous
   float* delta;      // [B, H, Lq] scratch: rowsum(dO * O)
-  float* dq_acc;     // [B, Lq, H, 64] fp32, zero-initialised (atomically accumulated)
+  void* dq_part;     // [ceil(Lk / 128), B, Lq, H, 64] 16-bit: per-key-tile partial dQ (plain stores; fp32 atomics on one
+                     // accumulator cost ~4000 cycles per tile), summed by the finishing kernel
   void* dq;          // [B, Lq, H, 64] 16-bit results, addressed through (batch, seq, head) element strides so
   void* dk;          // that they can be slices of one packed [B, L, 3, H, 64] gradient tensor
   void* dv;

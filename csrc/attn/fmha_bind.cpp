@@ -156,7 +156,7 @@ std::tuple<Tensor, Tensor, Tensor, OptTensor> fmha_bwd(const Tensor& dout, const
     p.debug_flags = dbg ? std::atoi(dbg) : 0;
   }
   Tensor delta = torch::empty({p.f.B, p.f.H, p.f.Lq}, q.options().dtype(at::kFloat));
-  Tensor dq_acc = torch::zeros({p.f.B, p.f.Lq, p.f.H, 64}, q.options().dtype(at::kFloat));
+  Tensor dq_part = torch::empty({(p.f.Lk + 127) / 128, p.f.B, p.f.H, (p.f.Lq + 127) / 128 * 128, 64}, q.options());
   Tensor dq, dk, dv;
   if (packed_grad) {
     TORCH_CHECK(p.f.Lq == p.f.Lk, "packed gradients need self-attention shapes");
@@ -185,10 +185,13 @@ std::tuple<Tensor, Tensor, Tensor, OptTensor> fmha_bwd(const Tensor& dout, const
                 "cuTensorMapEncodeTiled failed for the dS scratch tensor");
   }
   p.delta = delta.data_ptr<float>();
-  p.dq_acc = dq_acc.data_ptr<float>();
+  p.dq_part = dq_part.data_ptr();
   p.dq = dq.data_ptr();
   p.dk = dk.data_ptr();
   p.dv = dv.data_ptr();
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(p.dk) & 31) == 0 && (reinterpret_cast<uintptr_t>(p.dv) & 31) == 0 &&
+                  (reinterpret_cast<uintptr_t>(p.dq_part) & 31) == 0,
+              "fmha_bwd outputs must be 32-byte aligned (256-bit stores)");
   Tensor btrace;
   p.trace = nullptr;
   if (std::getenv("UNICORE_FMHA_TRACE") != nullptr) {

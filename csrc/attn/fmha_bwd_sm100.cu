@@ -16,7 +16,7 @@
 //   buffer that later receives dS (same core-matrix layout => in-place overwrite, chunk by chunk).
 //   Every operand tile is written once and presented to the tensor core as K-major or MN-major by
 //   swapping descriptor strides (no transposes).
-// Pre-pass:  delta = rowsum(dO o O).   Post-pass: dq = cast(dq_acc).
+// Pre-pass:  delta = rowsum(dO o O).   Post-pass: dq = sum of the per-key-tile partials (and dbias = batch sum of dS).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
@@ -33,7 +33,9 @@ namespace {
 using namespace tc;
 
 constexpr int kBM = 128, kBN = 128, kD = 64;
-constexpr int kBwdThreads = 512;
+constexpr int kBwdMathThreads = 512;            // 16 warps: thread = (query row, 32-column quarter)
+constexpr int kBwdThreads = kBwdMathThreads + 32;  // + one warp that only issues TMA copies and tcgen05.mma
+constexpr int kIssuer = kBwdMathThreads;         // its elected thread
 constexpr uint32_t kBwdTmemCols = 512;
 constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
 
@@ -46,7 +48,7 @@ constexpr uint32_t kOffP = 98304;      // 32 KB
 constexpr uint32_t kOffDS = 131072;    // 2 x 32 KB: bias tile, then dS (in place)
 constexpr uint32_t kOffKAdd = 196608;  // float[128]
 constexpr uint32_t kOffBar = 196608 + 512;
-constexpr uint32_t kBwdSmemBytes = kOffBar + 64;
+constexpr uint32_t kBwdSmemBytes = kOffBar + 96;
 
 template <typename T>
 UB_DEVICE uint32_t bwd_pack2(float a, float b);
@@ -59,6 +61,13 @@ template <>
 UB_DEVICE uint32_t bwd_pack2<__nv_bfloat16>(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 256-bit store (sm_100: STG.E.256): one full 32-byte sector per thread and instruction
+UB_DEVICE void st_global_v8(void* addr, const Vec16& lo, const Vec16& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(addr), "r"(lo.w[0]), "r"(lo.w[1]), "r"(lo.w[2]),
+               "r"(lo.w[3]), "r"(hi.w[0]), "r"(hi.w[1]), "r"(hi.w[2]), "r"(hi.w[3])
+               : "memory");
 }
 
 UB_DEVICE void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -93,22 +102,43 @@ __global__ void __launch_bounds__(256) fmha_delta_kernel(const T* __restrict__ d
   }
 }
 
-// ---- post-pass: fp32 accumulator -> 16-bit ------------------------------------------------------------------
+// ---- post-pass: dq = sum over key tiles of the 16-bit partials (fp32 accumulate) ---------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) fmha_cast_kernel(const float* __restrict__ in, T* __restrict__ out, long long nvec,
-                                                          int H, int Lq, long long sb, long long sl, long long sh) {
-  // in: contiguous [B, Lq, H, 64] fp32; out: 16-bit with (batch, seq, head) element strides
+__global__ void __launch_bounds__(256) fmha_dq_sum_kernel(const T* __restrict__ part, T* __restrict__ out, long long nvec,
+                                                            int n_parts, int H, int Lq, int n_qt, long long sb,
+                                                            long long sl, long long sh) {
+  // part: [n_parts] x [B][H][n_qt][4][128][16] (see the main kernel); out: 16-bit with (batch, seq, head) strides
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    float x[8];
-    unpack<float>(ld_global_nc_v4(in + v * 8), x);
-    unpack<float>(ld_global_nc_v4(in + v * 8 + 4), x + 4);
-    const long long rowi = v >> 3;  // (b, q, h) row of 64 elements = 8 vectors
-    const int part = (int)(v & 7);
-    const int hh = (int)(rowi % H);
-    const long long bq = rowi / H;
-    const long long qq = bq % Lq, bb = bq / Lq;
-    st_global_v4(out + bb * sb + qq * sl + (long long)hh * sh + part * 8, pack<T>(x));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j0 = 0; j0 < n_parts; j0 += 4) {
+      Vec16 in[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < n_parts) in[u] = ld_global_nc_v4(part + ((long long)(j0 + u) * nvec + v) * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u < n_parts) {
+          float x[8];
+          unpack<T>(in[u], x);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += x[e];
+        }
+      }
+    }
+    // v enumerates the partial layout [b][h][q tile][quarter][row][2 x 8 columns]
+    const int c8 = (int)(v & 1);
+    const long long t1 = v >> 1;
+    const int rr = (int)(t1 % 128);
+    const long long t2 = t1 / 128;
+    const int qt = (int)(t2 & 3);
+    const long long t3 = t2 >> 2;
+    const int tile = (int)(t3 % n_qt);
+    const long long t4 = t3 / n_qt;
+    const int hh = (int)(t4 % H);
+    const long long bb = t4 / H;
+    const long long qq = (long long)tile * 128 + rr;
+    if (qq < Lq) st_global_v4(out + bb * sb + qq * sl + (long long)hh * sh + qt * 16 + c8 * 8, pack<T>(acc));
   }
 }
 
@@ -131,6 +161,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
   const uint32_t bar_a = smem_base + kOffBar, bar_b = smem_base + kOffBar + 8;
   // TMA completion barriers: the K/V tiles of this CTA, and the two (Q, dO, bias) input buffers
   const uint32_t bar_kv = smem_base + kOffBar + 24, bar_in0 = smem_base + kOffBar + 32;  // bar_in1 = bar_in0 + 8
+  // bar_q: dQ of the current tile is complete (read-out may start); bar_v: dV / dK of the current tile are
+  // complete (their operand buffers may be refilled).  bar_b is no longer used.
+  const uint32_t bar_q = smem_base + kOffBar + 48, bar_v = smem_base + kOffBar + 56;
+  // the bias tile has its own completion barrier (per buffer): the math warps need it first, Q / dO only matter
+  // to the issuing warp, much later
+  const uint32_t bar_bias0 = smem_base + kOffBar + 64;  // bar_bias1 = bar_bias0 + 8
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 16);
   float* kadd = reinterpret_cast<float*>(smem + kOffKAdd);
 
@@ -144,6 +180,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
     mbar_init(bar_kv, 1);
     mbar_init(bar_in0, 1);
     mbar_init(bar_in0 + 8, 1);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_bias0, 1);
+    mbar_init(bar_bias0 + 8, 1);
     fence_mbarrier_init();
   }
   const T* qg = reinterpret_cast<const T*>(p.q) + (long long)b * p.q_sb + (long long)h * p.q_sh;
@@ -164,10 +204,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
     const int q0 = i * kBM;
     const uint32_t buf = (uint32_t)(i & 1);
     const uint32_t bar = bar_in0 + buf * 8;
-    mbar_expect_tx(bar, 2 * kTileBytes + (has_bias ? kBiasBytes : 0u));
+    if (has_bias) {  // first: the math warps wait for it
+      mbar_expect_tx(bar_bias0 + buf * 8, kBiasBytes);
+      tma_load_5d(smem_base + kOffDS + buf * 32768, &p.tm_bias, 0, 0, key_tile0 / 8, q0 / 8, bias_nb, bar_bias0 + buf * 8);
+    }
+    mbar_expect_tx(bar, 2 * kTileBytes);
     tma_load_5d(smem_base + kOffQ + buf * 16384, &p.tm_q, 0, 0, h * 8, q0 / 8, b, bar);
     tma_load_5d(smem_base + kOffDO + buf * 16384, &bp.tm_do, 0, 0, h * 8, q0 / 8, b, bar);
-    if (has_bias) tma_load_5d(smem_base + kOffDS + buf * 32768, &p.tm_bias, 0, 0, key_tile0 / 8, q0 / 8, bias_nb, bar);
   };
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t idesc_s = make_idesc_f16(kBM, kBN, kFmt, 0, 0);    // S, dP: both operands K-major
@@ -183,7 +226,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
   fence_before_thread_sync();
   const bool tile_masked = __syncthreads_or(key_masked) != 0;  // usually no key of the tile is masked
   fence_after_thread_sync();
-  if (tid == 0) {  // barriers are initialised: K, V of this CTA and the first (Q, dO, bias) tile
+  if (tid == kIssuer) {  // barriers are initialised: K, V of this CTA and the first (Q, dO, bias) tile
     mbar_expect_tx(bar_kv, 2 * kTileBytes);
     tma_load_5d(smem_base + kOffK, &p.tm_k, 0, 0, h * 8, key_tile0 / 8, b, bar_kv);
     tma_load_5d(smem_base + kOffV, &p.tm_v, 0, 0, h * 8, key_tile0 / 8, b, bar_kv);
@@ -210,11 +253,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
     }
     umma_commit(bar_a);
   };
-  if (tid == 0) {
+  if (tid == kIssuer) {
     mbar_wait(bar_kv, 0);
     mbar_wait(bar_in0, 0);
     issue_s_dp(0);
   }
+  const bool math_thread = tid < kBwdMathThreads;
 
   const bool drop = p.p_drop > 0.f && p.drop_bits != nullptr;
   // same 14-bit threshold arithmetic as the forward kernel (common.cuh)
@@ -222,34 +266,39 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
   constexpr float kLog2e = 1.4426950408889634f;
   const F2 scale_2 = f2(p.scale), log2e_2 = f2(kLog2e);
   const int words_per_row = (p.Lk + 31) / 32;
-  uint32_t phase_a = 0, phase_b = 0;
+  uint32_t phase_a = 0;
+  auto load_row_stats = [&](int i, float& lse, float& delta, uint32_t& keep) {
+    const int row = i * kBM + r;
+    const bool ok = row < p.Lq && math_thread;
+    const long long stat_idx = ((long long)b * p.H + h) * p.Lq + (ok ? row : 0);
+    lse = ok ? p.lse[stat_idx] : CUDART_INF_F;
+    delta = ok ? bp.delta[stat_idx] : 0.f;
+    keep = 0xffffffffu;
+    if (drop && ok && key_tile0 + col0 < p.Lk) keep = p.drop_bits[stat_idx * words_per_row + ((key_tile0 + col0) >> 5)];
+  };
+  float nx_lse, nx_delta;
+  uint32_t nx_keep;
+  load_row_stats(0, nx_lse, nx_delta, nx_keep);
 
   for (int i = 0; i < n_qtiles; ++i) {
     const int q0 = i * kBM;
     const uint32_t buf = (uint32_t)(i & 1);
     const uint32_t sQ = smem_base + kOffQ + buf * 16384, sDO = smem_base + kOffDO + buf * 16384;
     const uint32_t offDS = kOffDS + buf * 32768;
-    UB_BTRACE(0);
-    // prefetch tile i+1 under the softmax of tile i (its buffers were released by the MMAs of tile i-1,
-    // whose completion every thread observed on bar_b at the end of the previous iteration)
-    if (tid == 0 && i + 1 < n_qtiles) {
-      tma_store_wait_read();  // the dS store of tile i-1 has finished reading the buffer tile i+1 lands in
-      issue_tile(i + 1);
-    }
-    if (has_bias) mbar_wait(bar_in0 + buf * 8, (uint32_t)((i >> 1) & 1));  // bias tile i is visible to ordinary loads
-    UB_BTRACE(1);
-
     const int row = q0 + r;
     const bool row_valid = row < p.Lq;
-    const long long stat_idx = ((long long)b * p.H + h) * p.Lq + (row_valid ? row : 0);
-    const float lse = row_valid ? p.lse[stat_idx] : CUDART_INF_F;
-    const float delta = row_valid ? bp.delta[stat_idx] : 0.f;
+    if (math_thread) {
+    UB_BTRACE(0);
+    if (has_bias) mbar_wait(bar_bias0 + buf * 8, (uint32_t)((i >> 1) & 1));  // bias tile i is visible to ordinary loads
+    UB_BTRACE(1);
+
+    // per-row statistics and keep bits of this tile were requested during the previous tile's math
+    const float lse = nx_lse, delta = nx_delta;
+    const uint32_t keep_word = nx_keep;
+    if (i + 1 < n_qtiles) load_row_stats(i + 1, nx_lse, nx_delta, nx_keep);
     // fully masked row (lse = -inf) or padding row -> p = 0
     const float lse2 = (lse == -CUDART_INF_F || !row_valid) ? CUDART_INF_F : lse * kLog2e;
     const F2 nlse_2 = f2(-lse2), ndelta_2 = f2(-delta);
-    uint32_t keep_word = 0xffffffffu;
-    if (drop && row_valid && key_tile0 + col0 < p.Lk)
-      keep_word = p.drop_bits[stat_idx * words_per_row + ((key_tile0 + col0) >> 5)];
     UB_BTRACE(2);
     mbar_wait(bar_a, phase_a);
     phase_a ^= 1;
@@ -307,62 +356,82 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
     UB_BTRACE(5);
     fence_proxy_async_smem();   // my P / dS stores (generic proxy) before the tensor core (async proxy) reads them
     fence_before_thread_sync();
-    __syncthreads();
+    } else if (tid == kIssuer && i + 1 < n_qtiles) {
+      // The issuing warp runs ahead of the math warps.  Tile i+1 lands in the buffers tile i-1 used: its dV / dK
+      // MMAs (bar_v) and its dS store must be done with them; the copy (64 KB in 16-byte rows, ~4000 cycles)
+      // then has the whole softmax-grad phase of tile i to land.
+      if (i >= 1) mbar_wait(bar_v, (uint32_t)((i - 1) & 1));
+      tma_store_wait_read();
+      issue_tile(i + 1);
+    }
+    __syncthreads();   // P and dS of tile i are in shared memory
     UB_BTRACE(6);
-    if (tid == 0) {
+    if (tid == kIssuer) {
       fence_after_thread_sync();
       const uint32_t sDS = smem_base + offDS;
       if (bp.ds_buf != nullptr) {  // bias gradient: the dS tile leaves through one TMA store
         tma_store_5d(&bp.tm_ds, 0, 0, key_tile0 / 8, q0 / 8, b * p.H + h, sDS);
         tma_store_commit();
       }
+      // Issue order = execution order on the tensor pipe: dQ first (the threads are waiting for it: its read-out and
+      // the next tile's statistics loads then run under dV / dK), then dV, dK, and S / dP of the next tile.
 #pragma unroll
-      for (int kk = 0; kk < kBM / 16; ++kk) {  // reduction over the 128 query rows, 16 per step
+      for (int kk = 0; kk < kBN / 16; ++kk) {  // dQ: reduction over the 128 keys
+        const uint64_t a_ds = make_smem_desc(sDS + kk * 256, 128, 2048);                  // dS   (K-major)
+        const uint64_t b_k = make_smem_desc(smem_base + kOffK + kk * 2048, 1024, 128);    // K    (MN-major)
+        umma_f16_ss(tmem_base + kColDQ, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_q);
+#pragma unroll
+      for (int kk = 0; kk < kBM / 16; ++kk) {  // dV: reduction over the 128 query rows, 16 per step
         const uint64_t a_p = make_smem_desc(smem_base + kOffP + kk * 4096, 2048, 128);    // P^T  (MN-major)
         const uint64_t b_do = make_smem_desc(sDO + kk * 2048, 1024, 128);                 // dO   (MN-major)
         umma_f16_ss(tmem_base + kColDV, a_p, b_do, idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
       }
 #pragma unroll
-      for (int kk = 0; kk < kBM / 16; ++kk) {
+      for (int kk = 0; kk < kBM / 16; ++kk) {  // dK
         const uint64_t a_ds = make_smem_desc(sDS + kk * 4096, 2048, 128);                 // dS^T (MN-major)
         const uint64_t b_q = make_smem_desc(sQ + kk * 2048, 1024, 128);                   // Q    (MN-major)
         umma_f16_ss(tmem_base + kColDK, a_ds, b_q, idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
       }
-#pragma unroll
-      for (int kk = 0; kk < kBN / 16; ++kk) {  // reduction over the 128 keys
-        const uint64_t a_ds = make_smem_desc(sDS + kk * 256, 128, 2048);                  // dS   (K-major)
-        const uint64_t b_k = make_smem_desc(smem_base + kOffK + kk * 2048, 1024, 128);    // K    (MN-major)
-        umma_f16_ss(tmem_base + kColDQ, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
-      }
-      umma_commit(bar_b);
-      // next tile's S / dP run on the tensor core while the dQ read-out and the atomics proceed
+      umma_commit(bar_v);
       if (i + 1 < n_qtiles) {
         mbar_wait(bar_in0 + (uint32_t)((i + 1) & 1) * 8, (uint32_t)(((i + 1) >> 1) & 1));  // Q, dO of tile i+1 landed
-        issue_s_dp(i + 1);
+        issue_s_dp(i + 1);   // commits bar_a: S / dP ready implies everything above is complete (P buffer is free)
       }
     }
     UB_BTRACE(7);
-    mbar_wait(bar_b, phase_b);
-    phase_b ^= 1;
+    if (math_thread) {
+    mbar_wait(bar_q, (uint32_t)(i & 1));
     fence_after_thread_sync();
     UB_BTRACE(8);
-    {  // dQ_i partial -> global fp32 accumulator (16 of the 64 columns per thread)
+    {  // dQ_i partial of this key tile -> 16-bit partial buffer (16 of the 64 columns per thread)
       uint32_t acc[16];
       tmem_ld16(lane_base + kColDQ + quarter * 16, acc);
       tmem_wait_ld();
       if (row_valid && !(bp.debug_flags & 2)) {
-        float* dst = bp.dq_acc + (((long long)b * p.Lq + row) * p.H + h) * kD + quarter * 16;
+        // partial layout [key tile][b][h][q tile][quarter][128 rows][16]: a warp (32 rows, one quarter) writes 1 KB
+        // of consecutive bytes
+        T* dst = reinterpret_cast<T*>(bp.dq_part) +
+                 ((((((long long)blockIdx.x * p.B + b) * p.H + h) * n_qtiles + i) * 4 + quarter) * kBM + r) * 16;
+        Vec16 o[2];
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
-          red_add_v4(dst + v * 4, __uint_as_float(acc[v * 4]) * p.scale, __uint_as_float(acc[v * 4 + 1]) * p.scale,
-                     __uint_as_float(acc[v * 4 + 2]) * p.scale, __uint_as_float(acc[v * 4 + 3]) * p.scale);
+        for (int v = 0; v < 2; ++v) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[v].w[e] = bwd_pack2<T>(__uint_as_float(acc[v * 8 + 2 * e]) * p.scale, __uint_as_float(acc[v * 8 + 2 * e + 1]) * p.scale);
+        }
+        st_global_v8(dst, o[0], o[1]);
       }
     }
     UB_BTRACE(9);
+    }
   }
 
   // ---- epilogue: dK_j, dV_j (16 of the 64 columns per thread) ---------------------------------------------------
-  {
+  mbar_wait(bar_v, (uint32_t)((n_qtiles - 1) & 1));   // the last dV / dK accumulation has completed
+  fence_after_thread_sync();
+  if (math_thread) {
     const int key = key_tile0 + r;
     uint32_t accv[16], acck[16];
     tmem_ld16(lane_base + kColDV + quarter * 16, accv);
@@ -373,22 +442,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
                quarter * 16;
       T* dkg = reinterpret_cast<T*>(bp.dk) + (long long)b * bp.dk_sb + (long long)key * bp.dk_sl + (long long)h * bp.dk_sh +
                quarter * 16;
+      Vec16 ov[2], ok[2];
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        Vec16 ov, ok;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          ov.w[e] = bwd_pack2<T>(__uint_as_float(accv[v * 8 + 2 * e]) * keep_scale,
-                                 __uint_as_float(accv[v * 8 + 2 * e + 1]) * keep_scale);
-          ok.w[e] = bwd_pack2<T>(__uint_as_float(acck[v * 8 + 2 * e]) * p.scale,
-                                 __uint_as_float(acck[v * 8 + 2 * e + 1]) * p.scale);
+          ov[v].w[e] = bwd_pack2<T>(__uint_as_float(accv[v * 8 + 2 * e]) * keep_scale,
+                                    __uint_as_float(accv[v * 8 + 2 * e + 1]) * keep_scale);
+          ok[v].w[e] = bwd_pack2<T>(__uint_as_float(acck[v * 8 + 2 * e]) * p.scale,
+                                    __uint_as_float(acck[v * 8 + 2 * e + 1]) * p.scale);
         }
-        st_global_v4(dvg + v * 8, ov);
-        st_global_v4(dkg + v * 8, ok);
       }
+      st_global_v8(dvg, ov[0], ov[1]);   // 32-byte aligned: tensor bases are, and head / quarter offsets are multiples of 32 B
+      st_global_v8(dkg, ok[0], ok[1]);
     }
   }
-  if (tid == 0) tma_store_wait_read();  // shared memory must outlive the last dS store's reads
+  if (tid == kIssuer) tma_store_wait_read();  // shared memory must outlive the last dS store's reads
   fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, kBwdTmemCols);
@@ -437,11 +506,13 @@ void run_bwd(const FmhaBwdParams& bp, cudaStream_t stream) {
     fmha_dbias_reduce_kernel<T><<<(unsigned)rb, 256, 0, stream>>>(reinterpret_cast<const T*>(bp.ds_buf),
                                                                  reinterpret_cast<T*>(bp.dbias), p.B, nv);
   }
-  const long long nvec = nrows * 64 / 8;
+  const int n_qt = (p.Lq + kBM - 1) / kBM;
+  const long long nvec = (long long)p.B * p.H * n_qt * kBM * 64 / 8;   // partial layout is padded to whole q tiles
   long long blocks = (nvec + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  fmha_cast_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(bp.dq_acc, reinterpret_cast<T*>(bp.dq), nvec, p.H, p.Lq,
-                                                            bp.dq_sb, bp.dq_sl, bp.dq_sh);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fmha_dq_sum_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const T*>(bp.dq_part),
+                                                              reinterpret_cast<T*>(bp.dq), nvec, (p.Lk + kBN - 1) / kBN, p.H,
+                                                              p.Lq, n_qt, bp.dq_sb, bp.dq_sl, bp.dq_sh);
 }
 
 }  // namespace
