@@ -2,17 +2,21 @@
 // probabilities are recomputed from the saved log-sum-exp; the dropout keep bits come from the
 // forward pass (1 bit / element).
 //
-//   grid = (key tiles, H, B); one CTA (512 threads) owns K_j, V_j (128 keys) and walks the query tiles i:
+//   grid = (key tiles, H, B); one CTA owns K_j, V_j (128 keys) and walks the query tiles i.  16 math warps
+//   (thread = (query row, 32-column quarter): no cross-thread reductions) + 1 warp that only issues TMA copies
+//   and tcgen05.mma, so the copy / MMA queues never sit behind softmax-grad arithmetic:
 //     S   = Q_i K_j^T                      tcgen05.mma  -> TMEM [  0,128)
 //     dP  = dO_i V_j^T                     tcgen05.mma  -> TMEM [128,256)
-//     P   = exp2(S*scale*log2e + bias*log2e + kmask - LSE_i*log2e) ;  dS = P o (drop(dP) - delta_i)
-//           thread = (query row, 32-column quarter): no cross-thread reductions; 16 warps hide latency
+//     P   = exp2((S*scale + bias + kmask - LSE_i) * log2e) ;  dS = P o (drop(dP) - delta_i)   (packed fp32x2)
+//     dQ_i  = dS K_j                       tcgen05.mma  -> TMEM [384,448) -> 16-bit partial of this key tile
 //     dV_j += drop(P)^T dO_i               tcgen05.mma  -> TMEM [256,320)   (A and B MN-major views)
-//     dK_j += scale * dS^T Q_i             tcgen05.mma  -> TMEM [320,384)
-//     dQ_i  = scale * dS K_j               tcgen05.mma  -> TMEM [384,448) -> red.global.add.v4.f32
-//     dBias += dS                          red.global.add.v4.f32 (bias broadcast over the batch)
-//   Software pipeline: Q_{i+1}, dO_{i+1} and the bias tile of (i+1, j) are fetched with cp.async
-//   into the alternate buffers while tile i is being processed; the bias tile is staged in the
+//     dK_j += dS^T Q_i                     tcgen05.mma  -> TMEM [320,384)
+//     dS tile (16-bit, already in shared memory for the MMAs) -> ONE TMA store; a follow-up kernel sums it over
+//     the batch into dBias.  (The first versions used red.global.add.v4.f32 for dQ and dBias: 6144 per tile,
+//     which made the kernel atomics-bound.)
+//   Tensor-pipe order per tile: dQ_i (the math warps wait for it; its read-out and the next tile's loads then
+//   run under the rest), dV, dK, S / dP of tile i+1.  Q_{i+1}, dO_{i+1} and the bias tile of (i+1, j) arrive by
+//   TMA (5-D tensor maps, csrc/attn/tma_map.h) in the alternate buffers one tile ahead; the bias tile lands in the
 //   buffer that later receives dS (same core-matrix layout => in-place overwrite, chunk by chunk).
 //   Every operand tile is written once and presented to the tensor core as K-major or MN-major by
 //   swapping descriptor strides (no transposes).
@@ -70,9 +74,6 @@ UB_DEVICE void st_global_v8(void* addr, const Vec16& lo, const Vec16& hi) {
                : "memory");
 }
 
-UB_DEVICE void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 // ---- pre-pass: delta[b,h,q] = sum_d dO * O -----------------------------------------------------------------
 template <typename T>
@@ -186,16 +187,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
     mbar_init(bar_bias0 + 8, 1);
     fence_mbarrier_init();
   }
-  const T* qg = reinterpret_cast<const T*>(p.q) + (long long)b * p.q_sb + (long long)h * p.q_sh;
-  const T* kg = reinterpret_cast<const T*>(p.k) + (long long)b * p.k_sb + (long long)h * p.k_sh;
-  const T* vg = reinterpret_cast<const T*>(p.v) + (long long)b * p.v_sb + (long long)h * p.v_sh;
-  const long long o_sl = (long long)p.H * kD;  // contiguous [B, L, H, 64] tensors
-  const T* dog = reinterpret_cast<const T*>(bp.dout) + ((long long)b * p.Lq * p.H + h) * kD;
-  const int k_valid = min(kBN, p.Lk - key_tile0);
   const int bb = p.bias_batch > 1 ? b : 0;
   const bool has_bias = p.bias != nullptr;
-  const T* bias_base = has_bias ? reinterpret_cast<const T*>(p.bias) + (((long long)bb * p.H + h) * p.Lq) * p.Lk + key_tile0
-                                : nullptr;
   const int n_qtiles = (p.Lq + kBM - 1) / kBM;
 
   constexpr uint32_t kTileBytes = kBM * kD * 2, kBiasBytes = kBM * kBN * 2;

@@ -4,9 +4,9 @@
 // Tensor-core path: tcgen05.mma (cta_group::1, M=128) with fp32 accumulators in tensor memory.
 //   S (128 x 128 fp32) lives in TMEM columns [0,128), O (128 x 64 fp32) in columns [128,192).
 //   One CTA (256 threads) = one 128-row query tile of one (batch, head); it walks the key tiles:
-//     1. cp.async: bias tile (staged *into the P buffer*, same core-matrix layout, so each thread
-//        later overwrites exactly the bias chunks it consumed) and V_j; K_j was prefetched while the
-//        previous tile's softmax ran
+//     1. TMA (5-D tensor maps that write the UMMA core-matrix layout, csrc/attn/tma_map.h): V_j at the top of the
+//        tile; K_{j+1} as soon as S_j is complete; the bias tile of tile j+1 as soon as tile j's has been consumed
+//        (own 32 KB buffer) - every copy is one instruction from one thread, completion on an mbarrier
 //     2. S  = Q K_j^T          4 x tcgen05.mma (K=16 each), commit -> mbarrier
 //     3. softmax in ONE pass over registers: thread = (query row, 64-key half); TMEM lane = row.
 //        tcgen05.ld, scale/bias FMA and exp2 argument on packed fp32x2 (FFMA2), row max exchanged
@@ -17,7 +17,7 @@
 //        V_j is only waited for here, so its latency hides behind the softmax
 //   q/k/v are read through strides straight out of the packed in_proj output; O is written as
 //   [B, Lq, H, 64] so that out_proj consumes it without a transpose.
-// Two CTAs are resident per SM (82 KB smem, 256 TMEM columns, <= 128 registers/thread) so one CTA's
+// Two CTAs are resident per SM (113 KB smem, 256 TMEM columns, <= 128 registers/thread) so one CTA's
 // softmax overlaps the other's copies and MMAs; 16 warps per SM hide the ALU/MUFU latencies.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -100,14 +100,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
     mbar_init(bar_b, 1);
     fence_mbarrier_init();
   }
-  const T* qg = reinterpret_cast<const T*>(p.q) + (long long)b * p.q_sb + (long long)h * p.q_sh + (long long)q0 * p.q_sl;
-  const T* kg = reinterpret_cast<const T*>(p.k) + (long long)b * p.k_sb + (long long)h * p.k_sh;
-  const T* vg = reinterpret_cast<const T*>(p.v) + (long long)b * p.v_sb + (long long)h * p.v_sh;
-  const int q_valid = min(kBlockM, p.Lq - q0);
   const bool has_bias = p.bias != nullptr;
-  const T* bias_tile = has_bias ? reinterpret_cast<const T*>(p.bias) +
-                                      (((long long)(p.bias_batch > 1 ? b : 0) * p.H + h) * p.Lq + q0) * p.Lk
-                                : nullptr;
   // All CTAs walk the key tiles in the same order on purpose: CTAs of different batch entries then hit the
   // same bias lines in L2 at about the same time (a rotated order measured 4 % slower).
   const int n_tiles = (p.Lk + kBlockN - 1) / kBlockN;
@@ -151,7 +144,6 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
   for (int j = 0; j < n_tiles; ++j) {
     const int jt = (j + rot) % n_tiles, jt_next = (j + 1 + rot) % n_tiles;
     const int key_tile0 = jt * kBlockN;
-    const int k_valid = min(kBlockN, p.Lk - key_tile0);
     UB_TRACE(0);
     if (j > 0) {  // previous P V must be done before V / P shared memory is overwritten
       mbar_wait(bar_o, phase_o);

@@ -1,0 +1,56 @@
+"""Multi-GPU tests (skipped on single-GPU boxes): NVLink peer-memory all-reduce kernels and the
+``--ddp-backend b200`` data-parallel engine, each launched under ``torch.distributed.run``."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _torchrun(nproc, script_args, timeout=600):
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port())] + script_args
+    out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    assert out.returncode == 0, out.stdout[-4000:]
+    return out.stdout
+
+
+needs_two = pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+
+
+@needs_two
+def test_symmetric_allreduce_kernels_match_reference():
+    """one-shot / two-shot / NVLS kernels: bit-exact against a rank-ordered fp32 reference, all sizes."""
+    n = min(torch.cuda.device_count(), 8)
+    log = _torchrun(n, [os.path.join(ROOT, "bench", "allreduce_sweep.py"), "--check", "--max-mb", "16"])
+    summary = [json.loads(line) for line in log.splitlines() if line.startswith('{"summary"')]
+    assert summary and summary[-1]["failures"] == 0, log[-2000:]
+
+
+@needs_two
+def test_b200_backend_trains_like_c10d():
+    """Three updates of BERT-base under both engines on 2 GPUs: same loss trajectory."""
+    losses = {}
+    for backend in ("c10d", "b200"):
+        log = _torchrun(2, [os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "3", "--warmup", "3",
+                            "--batch-size", "4", "--seq-len", "128", "--ddp-backend", backend])
+        line = [l for l in log.splitlines() if l.startswith('{"metric"')][-1]
+        res = json.loads(line)
+        assert res["n_gpus"] == 2 and res["config"]["ddp_backend"] == backend
+        assert res["value"] > 0 and res["e2e"]["value"] > 0
+        losses[backend] = res
+    assert losses["b200"]["gpu_launches"] > 0
