@@ -40,6 +40,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-mb", type=int, default=256)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--stress", action="store_true", help="random per-rank delays before every collective")
     ap.add_argument("--dtypes", default="float16")
     args = ap.parse_args()
     rank = int(os.environ["RANK"])
@@ -75,12 +76,19 @@ def main():
                 view.copy_(src)
                 torch.cuda.synchronize()
                 dist.barrier()
-                red(buf, 0, n, scale=1.0, algo=algo)
+                sq = torch.zeros(1, device="cuda")
+                if args.stress:  # skew the ranks: the flag protocol must tolerate any arrival order
+                    torch.cuda._sleep(int(torch.randint(0, 2_000_000, (1,)).item()))
+                red(buf, 0, n, scale=1.0, algo=algo, sq_acc=sq)
                 torch.cuda.synchronize()
                 if args.check:
                     err = (view.float() - ref.float()).abs().max().item()
                     denom = max(1.0, ref.float().abs().max().item())
                     ok = err / denom < (1e-6 if dtype == torch.float32 else 4e-3)
+                    # the kernels also accumulate |result|^2 over each rank's slice: the ranks' partials add up to it
+                    dist.all_reduce(sq)
+                    want = ref.float().pow(2).sum().item()
+                    ok = ok and abs(sq.item() - want) <= 2e-3 * max(want, 1e-6)
                     allsame = view.clone()
                     dist.broadcast(allsame, src=0)
                     identical = bool(torch.equal(allsame, view))

@@ -70,6 +70,22 @@ UB_DEVICE void acc_add(float (&acc)[16 / sizeof(T)], const Vec16& v) {
   for (int e = 0; e < (int)(16 / sizeof(T)); ++e) acc[e] += t[e];
 }
 
+// sum of squares over the CTA -> one atomicAdd into the local accumulator
+UB_DEVICE void publish_sq(float sq, float* sq_acc) {
+  if (sq_acc == nullptr) return;
+  __shared__ float red[kCommThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kCommThreads / 32 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0 && v != 0.f) atomicAdd(sq_acc, v);
+  }
+}
+
 // ---- one-shot / two-shot ------------------------------------------------------------------------------------------
 // Range = [begin_vec, end_vec) in 16-byte vectors relative to each buffer base.
 constexpr int kCommUnroll = 4;  // vectors per thread in flight per peer (NVLink latency ~2-3 us)
@@ -79,7 +95,7 @@ constexpr int kCommUnroll = 4;  // vectors per thread in flight per peer (NVLink
 // reduced value waits in registers across a second barrier.  (Host guarantees grid * 512 >= vectors.)
 template <typename T>
 __global__ void __launch_bounds__(kCommThreads) allreduce_oneshot_kernel(CommPeers peers, long long begin_vec,
-                                                                          long long end_vec, float scale) {
+                                                                          long long end_vec, float scale, float* sq_acc) {
   constexpr int EPV = 16 / sizeof(T);
   // (the handshake kernel ahead of us in the stream established that every rank's producers finished)
   const long long v = begin_vec + (long long)blockIdx.x * kCommThreads + threadIdx.x;
@@ -99,18 +115,27 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_oneshot_kernel(CommPee
     }
   }
   block_barrier(peers, /*release_first=*/false);  // all peers hold their sums in registers
+  float sq = 0.f;
   if (active) {
 #pragma unroll
     for (int e = 0; e < EPV; ++e) acc[e] *= scale;
     st_global_v4(reinterpret_cast<uint8_t*>(peers.buf[peers.rank]) + v * 16, pack<T>(acc));
+    // every rank holds the whole result here; each counts only "its" 1/world slice so that the ranks' sums add up
+    const long long n = end_vec - begin_vec, per = (n + peers.world - 1) / peers.world;
+    const long long lo = begin_vec + per * peers.rank;
+    if (v >= lo && v < lo + per) {
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) sq += acc[e] * acc[e];
+    }
   }
+  publish_sq(sq, sq_acc);
 }
 
 // Two-shot: rank r owns slice r: reduce-scatter by peer loads, all-gather by peer stores.
 // W = compile-time bound on the world size (2 / 4 / 8); W * kU = 16 peer vectors in flight per thread.
 template <typename T, int W>
 __global__ void __launch_bounds__(kCommThreads) allreduce_twoshot_kernel(CommPeers peers, long long begin_vec,
-                                                                          long long end_vec, float scale) {
+                                                                          long long end_vec, float scale, float* sq_acc) {
   constexpr int EPV = 16 / sizeof(T);
   constexpr int kU = 16 / W;
   const long long n = end_vec - begin_vec;
@@ -119,6 +144,7 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_twoshot_kernel(CommPee
   const long long hi = lo + per < end_vec ? lo + per : end_vec;
   if (lo > end_vec) lo = end_vec;
   const long long stride = (long long)gridDim.x * kCommThreads;
+  float sq = 0.f;
   for (long long v0 = lo + (long long)blockIdx.x * kCommThreads + threadIdx.x; v0 < hi; v0 += stride * kU) {
     Vec16 in[kU][W];
 #pragma unroll
@@ -141,7 +167,10 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_twoshot_kernel(CommPee
           if (p < peers.world) acc_add<T>(acc, in[u][p]);
         }
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) acc[e] *= scale;
+        for (int e = 0; e < EPV; ++e) {
+          acc[e] *= scale;
+          sq += acc[e] * acc[e];
+        }
         const Vec16 out = pack<T>(acc);
 #pragma unroll
         for (int p = 0; p < W; ++p) {
@@ -150,6 +179,7 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_twoshot_kernel(CommPee
       }
     }
   }
+  publish_sq(sq, sq_acc);
   block_barrier(peers, /*release_first=*/true);  // my stores are visible at the peers before anyone proceeds
 }
 
@@ -191,7 +221,7 @@ UB_DEVICE void multimem_st(void* mc_addr, const Vec16& v) {
 
 template <typename T>
 __global__ void __launch_bounds__(kCommThreads) allreduce_nvls_kernel(CommPeers peers, long long begin_vec,
-                                                                        long long end_vec, float scale) {
+                                                                        long long end_vec, float scale, float* sq_acc) {
   constexpr int EPV = 16 / sizeof(T);
   const long long n = end_vec - begin_vec;
   const long long per = (n + peers.world - 1) / peers.world;
@@ -200,6 +230,7 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_nvls_kernel(CommPeers 
   if (lo > end_vec) lo = end_vec;
   uint8_t* mc = reinterpret_cast<uint8_t*>(peers.multicast);
   const long long stride = (long long)gridDim.x * kCommThreads;
+  float sq = 0.f;
   for (long long v0 = lo + (long long)blockIdx.x * kCommThreads + threadIdx.x; v0 < hi; v0 += stride * kCommUnroll) {
     Vec16 r[kCommUnroll];
 #pragma unroll
@@ -211,36 +242,40 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_nvls_kernel(CommPeers 
     for (int u = 0; u < kCommUnroll; ++u) {
       const long long v = v0 + u * stride;
       if (v < hi) {
-        if (scale != 1.f) {
+        if (scale != 1.f || sq_acc != nullptr) {
           float acc[EPV];
           unpack<T>(r[u], acc);
 #pragma unroll
-          for (int e = 0; e < EPV; ++e) acc[e] *= scale;
+          for (int e = 0; e < EPV; ++e) {
+            acc[e] *= scale;
+            sq += acc[e] * acc[e];
+          }
           r[u] = pack<T>(acc);
         }
         multimem_st(mc + v * 16, r[u]);
       }
     }
   }
+  publish_sq(sq, sq_acc);
   block_barrier(peers, true);
 }
 
 // ---- host --------------------------------------------------------------------------------------------------------------
 template <typename T>
 static void run_allreduce(const CommPeers& peers, long long begin_vec, long long end_vec, float scale, int algo,
-                          int blocks, cudaStream_t stream) {
+                          int blocks, float* sq_acc, cudaStream_t stream) {
   symm_handshake_kernel<<<1, 32, 0, stream>>>(peers);
   if (algo == kAlgoNvls) {
-    allreduce_nvls_kernel<T><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
+    allreduce_nvls_kernel<T><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale, sq_acc);
   } else if (algo == kAlgoTwoShot) {
     if (peers.world <= 2)
-      allreduce_twoshot_kernel<T, 2><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
+      allreduce_twoshot_kernel<T, 2><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale, sq_acc);
     else if (peers.world <= 4)
-      allreduce_twoshot_kernel<T, 4><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
+      allreduce_twoshot_kernel<T, 4><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale, sq_acc);
     else
-      allreduce_twoshot_kernel<T, 8><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
+      allreduce_twoshot_kernel<T, 8><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale, sq_acc);
   } else {
-    allreduce_oneshot_kernel<T><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale);
+    allreduce_oneshot_kernel<T><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale, sq_acc);
   }
 }
 
@@ -251,7 +286,7 @@ int pick_allreduce_algo(long long bytes, int world, bool has_multicast) {
 }
 
 void launch_allreduce(const CommPeers& peers, long long byte_offset, long long bytes, int dtype, float scale, int algo,
-                      int blocks, cudaStream_t stream) {
+                      int blocks, float* sq_acc, cudaStream_t stream) {
   const long long begin_vec = byte_offset / 16, end_vec = (byte_offset + bytes) / 16;
   if (end_vec <= begin_vec) return;
   if (algo == kAlgoAuto) algo = pick_allreduce_algo(bytes, peers.world, peers.multicast != nullptr);
@@ -264,9 +299,9 @@ void launch_allreduce(const CommPeers& peers, long long byte_offset, long long b
     if (blocks <= 0) blocks = 24;
     if (blocks > kMaxCommBlocks - 1) blocks = kMaxCommBlocks - 1;  // the last slot belongs to the handshake
   }
-  if (dtype == kF32) run_allreduce<float>(peers, begin_vec, end_vec, scale, algo, blocks, stream);
-  else if (dtype == kF16) run_allreduce<__half>(peers, begin_vec, end_vec, scale, algo, blocks, stream);
-  else run_allreduce<__nv_bfloat16>(peers, begin_vec, end_vec, scale, algo, blocks, stream);
+  if (dtype == kF32) run_allreduce<float>(peers, begin_vec, end_vec, scale, algo, blocks, sq_acc, stream);
+  else if (dtype == kF16) run_allreduce<__half>(peers, begin_vec, end_vec, scale, algo, blocks, sq_acc, stream);
+  else run_allreduce<__nv_bfloat16>(peers, begin_vec, end_vec, scale, algo, blocks, sq_acc, stream);
 }
 
 }  // namespace ub

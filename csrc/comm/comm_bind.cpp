@@ -14,7 +14,7 @@ namespace {
 // by the symmetric-memory rendezvous; multicast_ptr: NVLS alias or 0.
 void symm_allreduce(const std::vector<int64_t>& buffer_ptrs, const std::vector<int64_t>& flag_ptrs,
                     int64_t multicast_ptr, int64_t rank, int64_t byte_offset, int64_t bytes, int64_t dtype,
-                    double scale, int64_t algo, int64_t blocks) {
+                    double scale, int64_t algo, int64_t blocks, int64_t sq_acc_ptr) {
   const int world = (int)buffer_ptrs.size();
   TORCH_CHECK(world >= 1 && world <= ub::kMaxPeers, "world size must be in [1, ", ub::kMaxPeers, "]");
   TORCH_CHECK((int)flag_ptrs.size() == world && rank >= 0 && rank < world);
@@ -28,7 +28,7 @@ void symm_allreduce(const std::vector<int64_t>& buffer_ptrs, const std::vector<i
   peers.rank = (int)rank;
   peers.world = world;
   ub::launch_allreduce(peers, byte_offset, bytes, (int)dtype, (float)scale, (int)algo, (int)blocks,
-                       at::cuda::getCurrentCUDAStream().stream());
+                       reinterpret_cast<float*>(sq_acc_ptr), at::cuda::getCurrentCUDAStream().stream());
   cudaError_t err = cudaGetLastError();
   TORCH_CHECK(err == cudaSuccess, "symm_allreduce launch failed: ", cudaGetErrorString(err));
 }

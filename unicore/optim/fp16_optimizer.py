@@ -265,8 +265,18 @@ class _FP16OptimizerMixin(object):
         return grad_norm
 
     # -- norm / clip ----------------------------------------------------------------------------
+    def set_external_grad_sq_norm(self, fn) -> None:
+        """``fn() -> squared L2 norm of the flat gradients (device scalar) or None``: the NVLink all-reduce kernels
+        accumulate it while they reduce, which saves the separate norm pass over the arena."""
+        self._external_sq_norm = fn
+
     def _raw_grad_norm(self) -> torch.Tensor:
         """L2 norm of the (still scaled) gradients as an fp32 device scalar."""
+        fn = getattr(self, "_external_sq_norm", None)
+        if fn is not None and self._fused:
+            sq = fn()
+            if sq is not None:
+                return sq.float().sqrt()
         if self._fused:
             grads = [f.grad for g in self.fp16_params for f in g["params"]]
         else:

@@ -93,8 +93,11 @@ class SymmAllReduce:
         return SymmBuffer(numel, dtype, self.device, self.group)
 
     def __call__(self, buf: SymmBuffer, elem_offset: int = 0, numel: Optional[int] = None, scale: float = 1.0,
-                 algo: int = 0, blocks: int = 0):
-        """In-place sum over ranks of ``buf.tensor[elem_offset : elem_offset + numel]`` (x ``scale``)."""
+                 algo: int = 0, blocks: int = 0, sq_acc: Optional[torch.Tensor] = None):
+        """In-place sum over ranks of ``buf.tensor[elem_offset : elem_offset + numel]`` (x ``scale``).
+
+        ``sq_acc`` (fp32 device scalar): this rank adds the sum of squares of the reduced values of its
+        1/world slice; summed over ranks that is the squared L2 norm of the result."""
         t = buf.tensor
         numel = t.numel() - elem_offset if numel is None else numel
         esz = t.element_size()
@@ -104,7 +107,7 @@ class SymmAllReduce:
         tag = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[t.dtype]
         self.native.symm_allreduce(
             buf.ptrs, self.flags.ptrs, buf.multicast_ptr, self.rank, byte_off, nbytes, tag, float(scale), int(algo),
-            int(blocks),
+            int(blocks), 0 if sq_acc is None else sq_acc.data_ptr(),
         )
 
 
@@ -134,6 +137,11 @@ class SymmDataParallel(nn.Module):
         self._hooks = []
         self._comm_stream = torch.cuda.Stream(priority=-1)
         self._started = False
+        # squared gradient norm, accumulated by the reduction kernels themselves (4 floats = one 16-byte vector)
+        self._sq = self.reducer.allocate(4, torch.float32)
+        self._sq.tensor.zero_()
+        self._sq_valid = False
+        self._covers_all_params = False
         # replicas must start identical (reference: DDP broadcasts from rank 0 at construction)
         with torch.no_grad():
             for t in list(module.parameters()) + list(module.buffers()):
@@ -193,6 +201,14 @@ class SymmDataParallel(nn.Module):
                     self._param_bucket[p] = touched
                     self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
         self._reset_counters()
+        trainable = [p for p in self.module.parameters() if p.requires_grad]
+        self._covers_all_params = len(self._buckets) > 0 and all(p in self._param_bucket for p in trainable)
+        if self._covers_all_params and hasattr(optimizer, "set_external_grad_sq_norm"):
+            optimizer.set_external_grad_sq_norm(self.grad_sq_norm)
+
+    def grad_sq_norm(self):
+        """Squared L2 norm of the (averaged) gradients of the step just reduced, or None if unavailable."""
+        return self._sq.tensor[0] if self._sq_valid else None
 
     def _reset_counters(self):
         for b in self._buckets:
@@ -209,12 +225,14 @@ class SymmDataParallel(nn.Module):
                 self._launch(b)
 
     def _launch(self, b: _Bucket):
-        if not self._started:
-            self._started = True
         # the bucket's gradients were produced on the current (compute) stream
         self._comm_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._comm_stream):
-            self.reducer(b.buffer, b.lo, b.hi - b.lo, scale=1.0 / self.world_size)
+            if not self._started:  # first bucket of this update: restart the norm accumulator
+                self._started = True
+                self._sq_valid = False
+                self._sq.tensor.zero_()
+            self.reducer(b.buffer, b.lo, b.hi - b.lo, scale=1.0 / self.world_size, sq_acc=self._sq.tensor)
         b.launched = True
 
     def all_reduce_grads(self):
@@ -230,5 +248,9 @@ class SymmDataParallel(nn.Module):
         for b in self._buckets:
             if not b.launched:
                 self._launch(b)
+        with torch.cuda.stream(self._comm_stream):
+            # every rank holds the squares of its slices: one 16-byte one-shot reduction gives all of them the total
+            self.reducer(self._sq, 0, 4, scale=1.0, algo=1)
+        self._sq_valid = self._covers_all_params
         torch.cuda.current_stream().wait_stream(self._comm_stream)
         self._reset_counters()
