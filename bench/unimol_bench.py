@@ -53,7 +53,7 @@ def main():
         "--total-num-update", "100000", "--max-update", "100000", "--batch-size", str(a.batch_size),
         "--update-freq", "1", "--seed", "1", "--no-save", "--disable-validation", "--log-format", "none",
         "--distributed-world-size", str(world), "--ddp-backend", backend, "--device-id", str(local_rank),
-        "--distributed-rank", str(rank), "--" + a.precision,
+        "--distributed-rank", str(rank), "--" + a.precision, "--deferred-overflow-check",
     ]
     parser = options.get_training_parser()
     args = options.parse_args_and_arch(parser, input_args=flags)

@@ -3,7 +3,7 @@ smooth-L1 + representation norm regularisers (weights from the model flags)."""
 import torch
 import torch.nn.functional as F
 
-from unicore import metrics
+from unicore import metrics, utils
 from unicore.losses import UnicoreLoss, register_loss
 
 
@@ -20,10 +20,13 @@ class UniMolLoss(UnicoreLoss):
         tgt_tokens = sample["target"]["tokens_target"]
         masked_tokens = tgt_tokens.ne(self.padding_idx)
         sample_size = masked_tokens.long().sum()
+        utils.mask_to_index(masked_tokens)  # resolved before the encoder is launched (cached for the head below)
         logits, pred_dist, pred_coord, x_norm, delta_norm = model(
             **sample["net_input"], encoder_masked_tokens=masked_tokens
         )
-        target = tgt_tokens[masked_tokens]
+        # one host read for the number of masked atoms, shared by the model head and every gather below
+        midx = utils.mask_to_index(masked_tokens)
+        target = tgt_tokens.reshape(-1).index_select(0, midx)
         token_loss = F.nll_loss(F.log_softmax(logits, dim=-1, dtype=torch.float32), target,
                                 ignore_index=self.padding_idx, reduction="mean")
         loss = token_loss * self.args.masked_token_loss
@@ -31,17 +34,21 @@ class UniMolLoss(UnicoreLoss):
                "seq_len": tgt_tokens.size(1) * tgt_tokens.size(0)}
         if pred_coord is not None:
             coord_target = sample["target"]["coord_target"]
-            coord_loss = F.smooth_l1_loss(pred_coord[masked_tokens].view(-1, 3).float(),
-                                          coord_target[masked_tokens].view(-1, 3), reduction="mean", beta=1.0)
+            coord_loss = F.smooth_l1_loss(pred_coord.reshape(-1, 3).index_select(0, midx).float(),
+                                          coord_target.reshape(-1, 3).index_select(0, midx), reduction="mean", beta=1.0)
             loss = loss + coord_loss * self.args.masked_coord_loss
             log["masked_coord_loss"] = coord_loss.data
         if pred_dist is not None:
-            dist_target = sample["target"]["distance_target"][masked_tokens]
-            non_pad = tgt_tokens.ne(self.padding_idx).new_ones(tgt_tokens.shape) & sample["net_input"]["src_tokens"].ne(self.padding_idx)
-            non_pad_rows = non_pad.unsqueeze(1).expand(-1, tgt_tokens.size(1), -1)[masked_tokens]
-            pd = pred_dist[masked_tokens][non_pad_rows].float()
-            td = (dist_target[non_pad_rows].float() - self.dist_mean) / self.dist_std
-            dist_loss = F.smooth_l1_loss(pd, td, reduction="mean", beta=1.0)
+            L = tgt_tokens.size(1)
+            dist_target = sample["target"]["distance_target"].reshape(-1, L).index_select(0, midx)
+            non_pad = sample["net_input"]["src_tokens"].ne(self.padding_idx)
+            # rows of masked atoms x non-padding columns, as a weight instead of a second boolean gather (which would
+            # cost another host synchronisation for its element count)
+            w = non_pad.unsqueeze(1).expand(-1, L, -1).reshape(-1, L).index_select(0, midx)
+            pd = pred_dist.reshape(-1, L).index_select(0, midx).float()
+            td = (dist_target.float() - self.dist_mean) / self.dist_std
+            per_elem = F.smooth_l1_loss(pd, td, reduction="none", beta=1.0)
+            dist_loss = (per_elem * w).sum() / w.sum().clamp(min=1)
             loss = loss + dist_loss * self.args.masked_dist_loss
             log["masked_dist_loss"] = dist_loss.data
         if self.args.x_norm_loss > 0 and x_norm is not None:

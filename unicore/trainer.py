@@ -731,7 +731,8 @@ class Trainer(object):
 
     def _check_grad_norms(self, grad_norm):
         """Non-finite norm => FloatingPointError; all ranks must agree on the norm (replicas in sync)."""
-        if torch.is_tensor(grad_norm) and grad_norm.is_cuda and getattr(self.args, "deferred_overflow_check", False):
+        if (torch.is_tensor(grad_norm) and grad_norm.is_cuda and getattr(self.args, "deferred_overflow_check", False)
+                and getattr(self.optimizer, "scaler", None) is not None):
             return  # nothing is read from the device on this path; the scaler sees the norm before the next backward
         if self.data_parallel_world_size > 1 and not getattr(self.args, "no_grad_norm_check", False):
             world = self.data_parallel_world_size
@@ -752,7 +753,15 @@ class Trainer(object):
                     + "-" * 80 + "\ngrad_norm across the workers:\n{}\n".format(detail) + "-" * 80
                 )
             return
-        value = float(grad_norm)
+        if torch.is_tensor(grad_norm) and grad_norm.is_cuda and getattr(self.args, "deferred_overflow_check", False):
+            # bf16 / fp32 runs have no loss scaler, the norm is only inspected for NaN/Inf: look at the PREVIOUS
+            # step's value (long since copied to the host) instead of waiting for this one
+            pending, self._pending_norm_check = getattr(self, "_pending_norm_check", None), utils.AsyncHostRead(grad_norm)
+            if pending is None:
+                return
+            value = float(pending.get())
+        else:
+            value = float(grad_norm)
         if value != value or abs(value) == float("inf"):
             raise FloatingPointError("gradients are Nan/Inf")
 

@@ -95,7 +95,7 @@ class MaskLMHead(nn.Module):
 
     def forward(self, features, masked_tokens=None, **kwargs):
         if masked_tokens is not None:
-            features = features[masked_tokens, :]
+            features = features.reshape(-1, features.size(-1)).index_select(0, utils.mask_to_index(masked_tokens))
         x = self.layer_norm(self.activation_fn(self.dense(features)))
         return F.linear(x, self.weight) + self.bias
 
