@@ -354,3 +354,55 @@ def test_ema_and_utils():
     assert abs(out.float().mean().item() - (1 + 2 ** -10)) < 1e-3
     y = utils.checkpoint_sequential([torch.nn.Linear(4, 4), torch.tanh], torch.randn(2, 4, requires_grad=True))
     y.sum().backward()
+
+
+def test_host_read_helpers_and_lazy_stats_cpu():
+    """utils.item / tolist / AsyncHostRead / mask_to_index degrade gracefully on CPU tensors."""
+    import torch
+
+    from unicore import utils
+
+    t = torch.tensor([3.5])
+    assert utils.item(t) == 3.5 and utils.item(2) == 2
+    assert utils.tolist(torch.tensor([1.0, 2.0])) == [1.0, 2.0]
+    pending = utils.AsyncHostRead(torch.tensor(7.0))
+    assert pending.ready() and pending.get() == 7.0
+    mask = torch.tensor([[True, False, True], [False, False, True]])
+    idx = utils.mask_to_index(mask)
+    assert idx.tolist() == [0, 2, 5] and utils.mask_to_index(mask) is idx  # cached per mask object
+    x = torch.arange(12.0).view(2, 3, 2)
+    assert torch.equal(x[mask], x.reshape(-1, 2).index_select(0, idx))
+
+
+def test_meters_localize_and_scheduler_module_aliases():
+    import torch
+
+    from unicore.logging import meters
+    from unicore.optim.lr_scheduler.polynomial_decay_schedule import PolynomialDecayLRSchedule
+    from unicore.optim.lr_scheduler import LR_SCHEDULER_REGISTRY
+
+    assert LR_SCHEDULER_REGISTRY["polynomial_decay"] is PolynomialDecayLRSchedule
+    md = meters.MetersDict()
+    md.add_meter("loss", meters.AverageMeter(round=3), 10)
+    md["loss"].update(torch.tensor(2.0), 4)
+    md["loss"].update(torch.tensor(4.0), 4)
+    md.localize()  # no CUDA tensors: a no-op that must not disturb the values
+    assert abs(float(md.get_smoothed_values()["loss"]) - 3.0) < 1e-6
+
+
+def test_torch_seed_is_scoped_and_reproducible():
+    import torch
+
+    from unicore import utils
+
+    torch.manual_seed(11)
+    outside_a = torch.rand(3)
+    torch.manual_seed(11)
+    with utils.torch_seed(5, 1, 2):
+        inside_a = torch.rand(3)
+    outside_b = torch.rand(3)
+    with utils.torch_seed(5, 1, 2):
+        inside_b = torch.rand(3)
+    with utils.torch_seed(5, 1, 3):
+        inside_c = torch.rand(3)
+    assert torch.equal(outside_a, outside_b) and torch.equal(inside_a, inside_b) and not torch.equal(inside_a, inside_c)
