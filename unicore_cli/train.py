@@ -22,6 +22,9 @@ from typing import Callable, Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
+if __package__ in (None, ""):  # started as a script from a source checkout: make the checkout importable
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 from unicore import checkpoint_utils, options, tasks, utils
 from unicore.data import iterators
 from unicore.distributed import utils as distributed_utils
