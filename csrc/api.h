@@ -105,6 +105,15 @@ void launch_bias_dropout_add_ln_bwd(const void* dy, const void* summed, const fl
                                     const void* gamma, void* dsum, void* dx, void* dgamma, void* dbeta,
                                     void* dbias, float* part, int rows, int cols, float p, unsigned long long seed,
                                     unsigned long long offset, int dtype, cudaStream_t stream);
+// ---- Gaussian radial basis of (mul[edge] * d + bias[edge]) (Uni-Mol pair features), csrc/fused/gaussian.cu ----------
+// y: [n, K] in `dtype` (fp16 / bf16), K a multiple of 8 with K / 8 a power of two <= 32
+void launch_gbf_fwd(const void* d, const long long* edge, const void* mul_w, const void* bias_w, const void* means,
+                    const void* stds, void* y, long long n, int K, int dtype, cudaStream_t stream);
+// part: float[gbf_parts(n, K)][2 * K] per-CTA partial (d mean, d std); hist: float[2 * E] zero-initialised (d mul, d bias)
+int gbf_parts(long long n, int K);
+void launch_gbf_bwd(const void* dy, const void* d, const long long* edge, const void* mul_w, const void* bias_w,
+                    const void* means, const void* stds, float* part, float* hist, long long n, int K, int E, int dtype,
+                    cudaStream_t stream);
 // loss_rows[i] = lse_i - logit_i[target_i] (0 when target == ignore_index); lse saved for backward
 void launch_softmax_xent_fwd(const void* logits, const long long* target, float* loss_rows, float* lse, int rows,
                              int cols, int stride, long long ignore_index, int dtype, cudaStream_t stream);

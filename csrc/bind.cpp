@@ -443,6 +443,49 @@ Tensor softmax_xent_bwd(const Tensor& logits, const Tensor& target, const Tensor
   return dlogits;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Gaussian basis (Uni-Mol)
+// ---------------------------------------------------------------------------------------------------
+Tensor gbf_fwd(const Tensor& d, const Tensor& edge, const Tensor& mul_w, const Tensor& bias_w, const Tensor& means,
+               const Tensor& stds) {
+  check_cuda_contig(d, "d");
+  check_cuda_contig(edge, "edge");
+  TORCH_CHECK(edge.scalar_type() == at::kLong && edge.numel() == d.numel());
+  TORCH_CHECK(d.scalar_type() == at::kHalf || d.scalar_type() == at::kBFloat16);
+  for (const Tensor* t : {&mul_w, &bias_w, &means, &stds})
+    TORCH_CHECK(t->is_cuda() && t->is_contiguous() && t->scalar_type() == d.scalar_type());
+  const int K = (int)means.numel();
+  TORCH_CHECK(K % 8 == 0 && K / 8 <= 32 && ((K / 8) & (K / 8 - 1)) == 0 && stds.numel() == K, "K must be 8 * 2^i <= 256");
+  const c10::cuda::CUDAGuard guard(d.device());
+  auto sizes = d.sizes().vec();
+  sizes.push_back(K);
+  Tensor y = torch::empty(sizes, d.options());
+  ub::launch_gbf_fwd(d.data_ptr(), (const long long*)edge.data_ptr<int64_t>(), mul_w.data_ptr(), bias_w.data_ptr(),
+                     means.data_ptr(), stds.data_ptr(), y.data_ptr(), d.numel(), K, dtype_tag(d), cur_stream());
+  check_launch("gbf_fwd");
+  return y;
+}
+
+// returns (d mul [E], d bias [E], d means [K], d stds_abs [K]) in fp32
+std::tuple<Tensor, Tensor, Tensor, Tensor> gbf_bwd(const Tensor& dy, const Tensor& d, const Tensor& edge,
+                                                   const Tensor& mul_w, const Tensor& bias_w, const Tensor& means,
+                                                   const Tensor& stds) {
+  check_cuda_contig(dy, "dy");
+  const int K = (int)means.numel(), E = (int)mul_w.numel();
+  TORCH_CHECK(dy.scalar_type() == d.scalar_type() && dy.numel() == d.numel() * K && bias_w.numel() == E);
+  TORCH_CHECK(E <= 8192, "edge-type table too large for the shared-memory histogram");
+  const c10::cuda::CUDAGuard guard(d.device());
+  const int parts = ub::gbf_parts(d.numel(), K);
+  Tensor part = torch::empty({parts, 2 * K}, d.options().dtype(at::kFloat));
+  Tensor hist = torch::zeros({2, E}, d.options().dtype(at::kFloat));
+  ub::launch_gbf_bwd(dy.data_ptr(), d.data_ptr(), (const long long*)edge.data_ptr<int64_t>(), mul_w.data_ptr(),
+                     bias_w.data_ptr(), means.data_ptr(), stds.data_ptr(), part.data_ptr<float>(), hist.data_ptr<float>(),
+                     d.numel(), K, E, dtype_tag(d), cur_stream());
+  check_launch("gbf_bwd");
+  Tensor cols = part.sum(0);
+  return {hist[0], hist[1], cols.slice(0, 0, K), cols.slice(0, K, 2 * K)};
+}
+
 }  // namespace
 
 // defined in attn/fmha_bind.cpp and comm/comm_bind.cpp
@@ -468,6 +511,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bias_dropout_add_ln_bwd", &bias_dropout_add_ln_bwd);
   m.def("softmax_xent_fwd", &softmax_xent_fwd);
   m.def("softmax_xent_bwd", &softmax_xent_bwd);
+  m.def("gbf_fwd", &gbf_fwd);
+  m.def("gbf_bwd", &gbf_bwd);
   register_fmha(m);
   register_comm(m);
 }

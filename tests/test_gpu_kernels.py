@@ -361,3 +361,32 @@ def test_vocab_projection_padded_xent(dtype):
         assert g.shape == gr.shape
         tol = (3e-2 if dtype == torch.float16 else 8e-2) * max(1e-3, gr.abs().max().item())
         assert (g.float() - gr).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_gaussian_basis(dtype):
+    """Uni-Mol pair features: fused kernels vs the embedding + broadcast formulation in fp32."""
+    from unicore import ops
+
+    torch.manual_seed(0)
+    B, L, K, E = 3, 40, 128, 961
+    dist = (torch.rand(B, L, L, device="cuda") * 6).to(dtype)
+    edge = torch.randint(0, E, (B, L, L), device="cuda")
+    mul_w = (1 + 0.2 * torch.randn(E, 1, device="cuda")).to(dtype).requires_grad_(True)
+    bias_w = (0.2 * torch.randn(E, 1, device="cuda")).to(dtype).requires_grad_(True)
+    means = (torch.rand(1, K, device="cuda") * 3).to(dtype).requires_grad_(True)
+    stds = (torch.rand(1, K, device="cuda") * 3 - 0.5).to(dtype).requires_grad_(True)  # some negative: |.| path
+    y = ops.gaussian_basis(dist, edge, mul_w, bias_w, means, stds)
+    assert y.shape == (B, L, L, K) and y.dtype == dtype
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    ref_in = [t.detach().float().requires_grad_(True) for t in (mul_w, bias_w, means, stds)]
+    t = (ref_in[0].view(-1)[edge] * dist.float() + ref_in[1].view(-1)[edge]).unsqueeze(-1)
+    std = ref_in[3].view(-1).abs() + 1e-5
+    yr = torch.exp(-0.5 * ((t - ref_in[2].view(-1)) / std) ** 2) / ((2 * 3.14159) ** 0.5 * std)
+    yr.backward(dy.float())
+    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3
+    assert (y.float() - yr).abs().max().item() < tol * max(1.0, yr.abs().max().item())
+    for got, ref in zip((mul_w, bias_w, means, stds), ref_in):
+        scale = max(1.0, ref.grad.abs().max().item())
+        assert (got.grad.float() - ref.grad.view_as(got.grad)).abs().max().item() < 3e-2 * scale

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from unicore import utils
+from unicore import ops, utils
 from unicore.models import BaseUnicoreModel
 from unicore.modules import LayerNorm, TransformerEncoderLayer, init_bert_params
 
@@ -62,6 +62,11 @@ class GaussianLayer(nn.Module):
         nn.init.constant_(self.mul.weight, 1)
 
     def forward(self, x, edge_type):
+        if ops.use_native(x, edge_type) and self.means.weight.dtype in (torch.float16, torch.bfloat16):
+            # one fused kernel per direction instead of two embedding look-ups (whose backward sorts B*L*L indices)
+            # and a TorchScript expression over [B, L, L, K] fp32 temporaries
+            return ops.gaussian_basis(x, edge_type, self.mul.weight, self.bias.weight, self.means.weight,
+                                      self.stds.weight)
         mul = self.mul(edge_type).type_as(x)
         bias = self.bias(edge_type).type_as(x)
         x = (mul * x.unsqueeze(-1) + bias).expand(-1, -1, -1, self.K)

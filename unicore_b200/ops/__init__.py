@@ -9,6 +9,8 @@ from .attention_ops import (  # noqa: F401
 from .fused_ops import (  # noqa: F401
     bias_dropout_add_layer_norm,
     bias_gelu,
+    gaussian_basis,
+    gaussian_basis_reference,
     softmax_cross_entropy,
     vocab_projection,
 )
