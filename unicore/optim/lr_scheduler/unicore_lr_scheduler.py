@@ -1,38 +1,53 @@
-"""LR scheduler base (reference ``unicore/optim/lr_scheduler/unicore_lr_scheduler.py:12-50``).
+"""Base class of the learning-rate schedules (interface of reference
+``unicore/optim/lr_scheduler/unicore_lr_scheduler.py:12-50``).
 
-Call protocol: ``step_update(num_updates)`` at build time with 0 and after
-every successful update; ``step_begin_epoch(epoch)`` at each epoch start; ``step(epoch, val_loss)``
-at each epoch end.
+The trainer drives a schedule through three entry points:
+
+========================  ==========================================================================
+``step_update(n)``        once with ``n = 0`` when the schedule is built, then after every successful
+                          parameter update; returns the learning rate now in force
+``step_begin_epoch(e)``   at the start of epoch ``e``
+``step(e, val_loss)``     at the end of epoch ``e``; the base class only tracks the best validation loss
+========================  ==========================================================================
+
+``state_dict`` / ``load_state_dict`` carry that best loss through checkpoints.
 """
 from unicore.optim import UnicoreOptimizer
 
 
+def _better(current, candidate):
+    """Smaller validation loss wins; ``None`` means "nothing seen yet"."""
+    if candidate is None:
+        return current
+    return candidate if current is None else min(current, candidate)
+
+
 class UnicoreLRScheduler(object):
     def __init__(self, args, optimizer, total_train_steps):
-        super().__init__()
-        if optimizer is not None and not isinstance(optimizer, UnicoreOptimizer):
+        if not (optimizer is None or isinstance(optimizer, UnicoreOptimizer)):
             raise ValueError("optimizer must be an instance of UnicoreOptimizer")
-        self.args = args
-        self.optimizer = optimizer
+        self.args, self.optimizer = args, optimizer
         self.total_train_steps = total_train_steps
         self.best = None
 
+    # -- flags contributed by the concrete schedule ----------------------------------------------------
     @classmethod
     def add_args(cls, parser):
-        pass
+        """Schedules override this to register their own flags."""
 
-    def state_dict(self):
-        return {"best": self.best}
+    # -- driven by the trainer ---------------------------------------------------------------------------
+    def step_update(self, num_updates):
+        return self.optimizer.get_lr()
 
+    def step_begin_epoch(self, epoch):
+        """Hook for schedules that change per epoch."""
+
+    def step(self, epoch, val_loss=None):
+        self.best = _better(self.best, val_loss)
+
+    # -- checkpointing -----------------------------------------------------------------------------------
     def load_state_dict(self, state_dict):
         self.best = state_dict["best"]
 
-    def step_begin_epoch(self, epoch):
-        pass
-
-    def step(self, epoch, val_loss=None):
-        if val_loss is not None:
-            self.best = val_loss if self.best is None else min(self.best, val_loss)
-
-    def step_update(self, num_updates):
-        return self.optimizer.get_lr()
+    def state_dict(self):
+        return dict(best=self.best)

@@ -117,19 +117,17 @@ class UnicoreOptimizer(object):
         return utils.clip_grad_norm_(list(self.params), max_norm, aggregate_norm_fn)
 
     def step(self, closure=None, scale=1.0, groups=None):
-        """One update; ``scale`` divides the grads (fused into the kernel when supported)."""
+        """One update.  ``scale`` divides the gradients: inside the kernel when the wrapped optimizer can do that
+        (``supports_step_with_scale``), by a multi-tensor pre-pass otherwise; ``groups`` is forwarded to optimizers
+        that update a subset of their parameter groups (``supports_groups``)."""
+        extra = {}
         if self.supports_step_with_scale:
-            if self.supports_groups:
-                self.optimizer.step(closure, scale=scale, groups=groups)
-            else:
-                self.optimizer.step(closure, scale=scale)
-        else:
-            if scale != 1.0:
-                self.multiply_grads(1.0 / scale)
-            if self.supports_groups:
-                self.optimizer.step(closure, groups=groups)
-            else:
-                self.optimizer.step(closure)
+            extra["scale"] = scale
+        elif scale != 1.0:
+            self.multiply_grads(1.0 / scale)
+        if self.supports_groups:
+            extra["groups"] = groups
+        self.optimizer.step(closure, **extra)
 
     def zero_grad(self):
         for p in self.params:
@@ -139,20 +137,18 @@ class UnicoreOptimizer(object):
             for buf in self._grad_buffer:
                 buf.zero_()
 
-    # -- capabilities -----------------------------------------------------------------------------
-    @property
-    def supports_memory_efficient_fp16(self):
-        return getattr(self.optimizer, "supports_memory_efficient_fp16", False)
 
-    @property
-    def supports_step_with_scale(self):
-        return getattr(self.optimizer, "supports_step_with_scale", False)
 
-    @property
-    def supports_groups(self):
-        return getattr(self.optimizer, "supports_groups", False)
+def _capability(name, doc):
+    """Capability flags are read off the wrapped ``torch.optim.Optimizer`` (absent means False)."""
+    return property(lambda self: getattr(self.optimizer, name, False), doc=doc)
 
-    @property
-    def supports_flat_params(self):
-        """Whether the optimizer is correct when all parameters are views of one flat tensor."""
-        return getattr(self.optimizer, "supports_flat_params", False)
+
+for _name, _doc in (
+    ("supports_memory_efficient_fp16", "the update can run on half-precision parameters directly"),
+    ("supports_step_with_scale", "``step(scale=...)`` divides the gradients inside the update kernel"),
+    ("supports_groups", "``step(groups=...)`` restricts the update to some parameter groups"),
+    ("supports_flat_params", "the update is correct when all parameters are views of one flat tensor"),
+):
+    setattr(UnicoreOptimizer, _name, _capability(_name, _doc))
+del _name, _doc
