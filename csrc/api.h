@@ -83,10 +83,13 @@ void launch_rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const 
 // mask row = row / mask_div (mask_rows = rows / mask_div), bias row = row % bias_rows
 void launch_softmax_dropout_fwd(void* x, void* out, const void* mask, const void* bias, long long rows, int K,
                                 long long mask_div, long long bias_rows, float p, unsigned long long seed,
-                                unsigned long long offset, int dtype, cudaStream_t stream);
-// dx may alias dy
-void launch_softmax_dropout_bwd(const void* dy, void* dx, const void* probs, long long rows, int K, float p, unsigned long long seed,
-                                unsigned long long offset, int dtype, cudaStream_t stream);
+                                unsigned long long offset, int dtype, cudaStream_t stream, void* logits = nullptr,
+                                float* lse = nullptr);
+// dx may alias dy.  Logits mode (lse != nullptr): `probs` holds the logits forward wrote; `addend` (nullable) is
+// added to dx before the store.
+void launch_softmax_dropout_bwd(const void* dy, void* dx, const void* probs, long long rows, int K, float p,
+                                unsigned long long seed, unsigned long long offset, int dtype, cudaStream_t stream,
+                                const float* lse = nullptr, const void* addend = nullptr);
 
 // ---- fused element-wise ---------------------------------------------------------------------------------------
 void launch_bias_gelu_fwd(const void* x, const void* bias, void* y, long long rows, int cols, int dtype,

@@ -12,6 +12,14 @@
 //   * fully masked rows produce zeros instead of NaN.
 // Contract kept: x is overwritten with the probabilities; mask row = row / mask_div; bias row =
 // row % bias_rows; backward overwrites dy with dx = (d - sum(d*y)) * y, d = keep ? dy/(1-p) : 0.
+//
+// "Logits mode" (lse != nullptr) serves pair-representation models (Uni-Mol: the biased logits of one
+// layer are the bias of the next, reference unicore/modules/multihead_attention.py:98-103 adds the bias
+// in its own pass and clones before the softmax): the kernel writes z = x + mask + bias (rounded to the
+// storage type, exactly what the unfused formulation feeds the softmax) to `logits`, the row
+// log-sum-exp to `lse`, and the dropped-out probabilities to `out`; x is left untouched and no
+// probability tensor is stored.  Backward rebuilds y = exp(z - lse) from the logits and adds the
+// gradient that arrived for the logits output (`addend`) before its single store.
 #include <math_constants.h>
 
 #include "../api.h"
@@ -50,13 +58,15 @@ struct SmGeom {
 template <typename T, int VPT>
 __global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
     T* __restrict__ x, T* __restrict__ out, const T* __restrict__ mask, const T* __restrict__ bias, SmGeom g, float p,
-    float keep_scale, unsigned long long seed, unsigned long long offset) {
+    float keep_scale, unsigned long long seed, unsigned long long offset, T* __restrict__ logits,
+    float* __restrict__ lse) {
   constexpr int EPV = VecTraits<T>::kElems;
   __shared__ float scratch[8];
   const int tpr = g.tpr, rows_per_cta = kSmThreads / tpr;
   const int grp = threadIdx.x / tpr, j = threadIdx.x % tpr;
   const uint32_t thresh = dropout_thresh16(p);
   const bool drop = p > 0.f;
+  const bool logits_mode = lse != nullptr;
   const long long stride_rows = (long long)gridDim.x * rows_per_cta;
   const long long iters = (g.rows + stride_rows - 1) / stride_rows;
   for (long long it = 0; it < iters; ++it) {
@@ -81,6 +91,11 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
 #pragma unroll
           for (int e = 0; e < EPV; ++e) v[k][e] += t[e];
         }
+        if (logits_mode) {
+          const Vec16 z = pack<T>(v[k]);
+          st_global_v4(logits + row * g.K + (long long)vi * EPV, z);
+          unpack<T>(z, v[k]);  // the softmax sees the stored (rounded) logits
+        }
 #pragma unroll
         for (int e = 0; e < EPV; ++e) mx = fmaxf(mx, v[k][e]);
       } else {
@@ -102,6 +117,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
     sum = group_reduce<false>(sum, tpr, scratch);
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
     if (active) {
+      if (logits_mode && j == 0) lse[row] = sum > 0.f ? mx + logf(sum) : CUDART_INF_F;
 #pragma unroll
       for (int k = 0; k < VPT; ++k) {
         const int vi = j + k * tpr;
@@ -111,7 +127,8 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
 #pragma unroll
           for (int e = 0; e < EPV; ++e) pr[e] = v[k][e] * inv;
           const Vec16 packed = pack<T>(pr);
-          st_global_v4(x + off, packed);
+          if (!logits_mode) st_global_v4(x + off, packed);
+          else if (!drop) st_global_v4(out + off, packed);
           if (drop) {
             const uint32_t keep = dropout_keep8(seed, offset, (unsigned long long)off >> 3, thresh) >> (off & 7);
             float rounded[EPV], o[EPV];
@@ -129,7 +146,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
 template <typename T, int VPT>
 __global__ void __launch_bounds__(kSmThreads) softmax_dropout_bwd_kernel(
     const T* dy, T* dx, const T* __restrict__ probs, SmGeom g, float p, float keep_scale, unsigned long long seed,
-    unsigned long long offset) {
+    unsigned long long offset, const float* __restrict__ lse, const T* __restrict__ addend) {
   constexpr int EPV = VecTraits<T>::kElems;
   __shared__ float scratch[8];
   const int tpr = g.tpr, rows_per_cta = kSmThreads / tpr;
@@ -143,6 +160,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_bwd_kernel(
     const bool active = row < g.rows;
     float d[VPT][EPV], y[VPT][EPV];
     float dot = 0.f;
+    const float row_lse = (lse != nullptr && active) ? lse[row] : 0.f;
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       const int vi = j + k * tpr;
@@ -150,6 +168,11 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_bwd_kernel(
         const long long off = row * g.K + (long long)vi * EPV;
         unpack<T>(ld_global_nc_v4(dy + off), d[k]);
         unpack<T>(ld_global_nc_v4(probs + off), y[k]);
+        if (lse != nullptr) {  // `probs` holds logits: rebuild the (rounded) probabilities forward used
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) y[k][e] = exp2f((y[k][e] - row_lse) * 1.4426950408889634f);
+          unpack<T>(pack<T>(y[k]), y[k]);
+        }
         if (drop) {
           const uint32_t keep = dropout_keep8(seed, offset, (unsigned long long)off >> 3, thresh) >> (off & 7);
 #pragma unroll
@@ -171,10 +194,17 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_bwd_kernel(
       for (int k = 0; k < VPT; ++k) {
         const int vi = j + k * tpr;
         if (vi < g.nvec) {
+          const long long off = row * g.K + (long long)vi * EPV;
           float o[EPV];
 #pragma unroll
           for (int e = 0; e < EPV; ++e) o[e] = d[k][e] - y[k][e] * dot;
-          st_global_v4(dx + row * g.K + (long long)vi * EPV, pack<T>(o));
+          if (addend != nullptr) {
+            float a[EPV];
+            unpack<T>(ld_global_nc_v4(addend + off), a);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) o[e] += a[e];
+          }
+          st_global_v4(dx + off, pack<T>(o));
         }
       }
     }
@@ -184,33 +214,40 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_bwd_kernel(
 // ---- scalar fallback (row length not a multiple of the vector width): one warp per row ----------------
 template <typename T>
 __global__ void softmax_dropout_fwd_scalar(T* x, T* out, const T* mask, const T* bias, SmGeom g, float p,
-                                           float keep_scale, unsigned long long seed, unsigned long long offset) {
+                                           float keep_scale, unsigned long long seed, unsigned long long offset,
+                                           T* logits, float* lse) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const uint32_t thresh = dropout_thresh16(p);
+  const bool logits_mode = lse != nullptr;
   for (long long row = warp; row < g.rows; row += nwarps) {
     T* xr = x + row * g.K;
+    T* zr = logits_mode ? logits + row * g.K : nullptr;
     const T* mr = mask ? mask + (row / g.mask_div) * g.K : nullptr;
     const T* br = bias ? bias + (row % g.bias_rows) * g.K : nullptr;
+    auto biased = [&](int c) { return to_f32<T>(xr[c]) + (mr ? to_f32<T>(mr[c]) : 0.f) + (br ? to_f32<T>(br[c]) : 0.f); };
     float mx = -CUDART_INF_F;
     for (int c = lane; c < g.K; c += 32) {
-      float v = to_f32<T>(xr[c]) + (mr ? to_f32<T>(mr[c]) : 0.f) + (br ? to_f32<T>(br[c]) : 0.f);
+      float v = biased(c);
+      if (logits_mode) {
+        zr[c] = from_f32<T>(v);  // later passes re-read this thread's own stores
+        v = to_f32<T>(zr[c]);
+      }
       mx = fmaxf(mx, v);
     }
     mx = warp_max(mx);
     if (mx == -CUDART_INF_F) mx = 0.f;
     float sum = 0.f;
-    for (int c = lane; c < g.K; c += 32) {
-      float v = to_f32<T>(xr[c]) + (mr ? to_f32<T>(mr[c]) : 0.f) + (br ? to_f32<T>(br[c]) : 0.f);
-      sum += expf(v - mx);
-    }
+    for (int c = lane; c < g.K; c += 32) sum += expf((logits_mode ? to_f32<T>(zr[c]) : biased(c)) - mx);
     sum = warp_sum(sum);
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    if (logits_mode && lane == 0) lse[row] = sum > 0.f ? mx + logf(sum) : CUDART_INF_F;
     for (int c = lane; c < g.K; c += 32) {
-      float v = to_f32<T>(xr[c]) + (mr ? to_f32<T>(mr[c]) : 0.f) + (br ? to_f32<T>(br[c]) : 0.f);
+      const float v = logits_mode ? to_f32<T>(zr[c]) : biased(c);
       const T pr = from_f32<T>(expf(v - mx) * inv);
-      xr[c] = pr;
+      if (!logits_mode) xr[c] = pr;
+      else if (p <= 0.f) out[row * g.K + c] = pr;
       if (p > 0.f) {
         const unsigned long long idx = (unsigned long long)(row * g.K + c);
         const uint32_t keep = dropout_keep8(seed, offset, idx >> 3, thresh);
@@ -222,32 +259,37 @@ __global__ void softmax_dropout_fwd_scalar(T* x, T* out, const T* mask, const T*
 
 template <typename T>
 __global__ void softmax_dropout_bwd_scalar(const T* dy, T* dx, const T* probs, SmGeom g, float p, float keep_scale,
-                                           unsigned long long seed, unsigned long long offset) {
+                                           unsigned long long seed, unsigned long long offset, const float* lse,
+                                           const T* addend) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const uint32_t thresh = dropout_thresh16(p);
   for (long long row = warp; row < g.rows; row += nwarps) {
-    float dot = 0.f;
-    for (int c = lane; c < g.K; c += 32) {
-      const unsigned long long idx = (unsigned long long)(row * g.K + c);
+    const float row_lse = lse != nullptr ? lse[row] : 0.f;
+    auto prob = [&](unsigned long long idx) {
+      const float t = to_f32<T>(probs[idx]);
+      return lse != nullptr ? to_f32<T>(from_f32<T>(expf(t - row_lse))) : t;
+    };
+    auto grad = [&](unsigned long long idx) {
       float d = to_f32<T>(dy[idx]);
       if (p > 0.f) {
         const uint32_t keep = dropout_keep8(seed, offset, idx >> 3, thresh);
         d = ((keep >> (idx & 7)) & 1u) ? d * keep_scale : 0.f;
       }
-      dot += d * to_f32<T>(probs[idx]);
+      return d;
+    };
+    float dot = 0.f;
+    for (int c = lane; c < g.K; c += 32) {
+      const unsigned long long idx = (unsigned long long)(row * g.K + c);
+      dot += grad(idx) * prob(idx);
     }
     dot = warp_sum(dot);
     for (int c = lane; c < g.K; c += 32) {
       const unsigned long long idx = (unsigned long long)(row * g.K + c);
-      float d = to_f32<T>(dy[idx]);
-      if (p > 0.f) {
-        const uint32_t keep = dropout_keep8(seed, offset, idx >> 3, thresh);
-        d = ((keep >> (idx & 7)) & 1u) ? d * keep_scale : 0.f;
-      }
-      const float y = to_f32<T>(probs[idx]);
-      dx[idx] = from_f32<T>((d - dot) * y);
+      float o = (grad(idx) - dot) * prob(idx);
+      if (addend != nullptr) o += to_f32<T>(addend[idx]);
+      dx[idx] = from_f32<T>(o);
     }
   }
 }
@@ -296,12 +338,13 @@ static bool make_sm_geom(SmGeom& g, long long rows, int K, int epv, int& vpt) {
 template <typename T>
 static void run_sm_fwd(void* x, void* out, const void* mask, const void* bias, long long rows, int K,
                        long long mask_div, long long bias_rows, float p, unsigned long long seed,
-                       unsigned long long offset, cudaStream_t stream) {
+                       unsigned long long offset, void* logits, float* lse, cudaStream_t stream) {
   SmGeom g;
   int vpt = 0;
   const bool vec = make_sm_geom(g, rows, K, VecTraits<T>::kElems, vpt) &&
                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
-                     reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+                     reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(bias) |
+                     reinterpret_cast<uintptr_t>(logits)) & 15) == 0;
   g.mask_div = mask_div > 0 ? mask_div : 1;
   g.bias_rows = bias_rows > 0 ? bias_rows : 1;
   const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
@@ -311,23 +354,24 @@ static void run_sm_fwd(void* x, void* out, const void* mask, const void* bias, l
     const long long cap = (long long)sm_count2() * 8;
     const int grid = (int)(need < cap ? need : cap);
     UB_SM_VPT(vpt, (softmax_dropout_fwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>(
-                       (T*)x, (T*)out, (const T*)mask, (const T*)bias, g, p, keep_scale, seed, offset)));
+                       (T*)x, (T*)out, (const T*)mask, (const T*)bias, g, p, keep_scale, seed, offset, (T*)logits, lse)));
   } else {
     long long need = (rows + 7) / 8;
     const long long cap = (long long)sm_count2() * 8;
     const int grid = (int)(need < cap ? need : cap);
     softmax_dropout_fwd_scalar<T><<<grid, 256, 0, stream>>>((T*)x, (T*)out, (const T*)mask, (const T*)bias, g, p,
-                                                            keep_scale, seed, offset);
+                                                            keep_scale, seed, offset, (T*)logits, lse);
   }
 }
 
 template <typename T>
 static void run_sm_bwd(const void* dy, void* dx, const void* probs, long long rows, int K, float p, unsigned long long seed,
-                       unsigned long long offset, cudaStream_t stream) {
+                       unsigned long long offset, const float* lse, const void* addend, cudaStream_t stream) {
   SmGeom g;
   int vpt = 0;
   const bool vec = make_sm_geom(g, rows, K, VecTraits<T>::kElems, vpt) &&
-                   ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(probs)) & 15) == 0;
+                   ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(probs) |
+                     reinterpret_cast<uintptr_t>(addend)) & 15) == 0;
   g.mask_div = 1;
   g.bias_rows = 1;
   const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
@@ -336,31 +380,36 @@ static void run_sm_bwd(const void* dy, void* dx, const void* probs, long long ro
     long long need = (rows + rows_per_cta - 1) / rows_per_cta;
     const long long cap = (long long)sm_count2() * 8;
     const int grid = (int)(need < cap ? need : cap);
-    UB_SM_VPT(vpt, (softmax_dropout_bwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>((const T*)dy, (T*)dx, (const T*)probs, g, p,
-                                                                                         keep_scale, seed, offset)));
+    UB_SM_VPT(vpt, (softmax_dropout_bwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>(
+                       (const T*)dy, (T*)dx, (const T*)probs, g, p, keep_scale, seed, offset, lse, (const T*)addend)));
   } else {
     long long need = (rows + 7) / 8;
     const long long cap = (long long)sm_count2() * 8;
     const int grid = (int)(need < cap ? need : cap);
-    softmax_dropout_bwd_scalar<T><<<grid, 256, 0, stream>>>((const T*)dy, (T*)dx, (const T*)probs, g, p, keep_scale, seed, offset);
+    softmax_dropout_bwd_scalar<T><<<grid, 256, 0, stream>>>((const T*)dy, (T*)dx, (const T*)probs, g, p, keep_scale, seed,
+                                                            offset, lse, (const T*)addend);
   }
 }
 
 void launch_softmax_dropout_fwd(void* x, void* out, const void* mask, const void* bias, long long rows, int K,
                                 long long mask_div, long long bias_rows, float p, unsigned long long seed,
-                                unsigned long long offset, int dtype, cudaStream_t stream) {
+                                unsigned long long offset, int dtype, cudaStream_t stream, void* logits, float* lse) {
   if (rows <= 0 || K <= 0) return;
-  if (dtype == kF32) run_sm_fwd<float>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, stream);
-  else if (dtype == kF16) run_sm_fwd<__half>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, stream);
-  else run_sm_fwd<__nv_bfloat16>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, stream);
+  if (dtype == kF32)
+    run_sm_fwd<float>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, logits, lse, stream);
+  else if (dtype == kF16)
+    run_sm_fwd<__half>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, logits, lse, stream);
+  else
+    run_sm_fwd<__nv_bfloat16>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, logits, lse, stream);
 }
 
-void launch_softmax_dropout_bwd(const void* dy, void* dx, const void* probs, long long rows, int K, float p, unsigned long long seed,
-                                unsigned long long offset, int dtype, cudaStream_t stream) {
+void launch_softmax_dropout_bwd(const void* dy, void* dx, const void* probs, long long rows, int K, float p,
+                                unsigned long long seed, unsigned long long offset, int dtype, cudaStream_t stream,
+                                const float* lse, const void* addend) {
   if (rows <= 0 || K <= 0) return;
-  if (dtype == kF32) run_sm_bwd<float>(dy, dx, probs, rows, K, p, seed, offset, stream);
-  else if (dtype == kF16) run_sm_bwd<__half>(dy, dx, probs, rows, K, p, seed, offset, stream);
-  else run_sm_bwd<__nv_bfloat16>(dy, dx, probs, rows, K, p, seed, offset, stream);
+  if (dtype == kF32) run_sm_bwd<float>(dy, dx, probs, rows, K, p, seed, offset, lse, addend, stream);
+  else if (dtype == kF16) run_sm_bwd<__half>(dy, dx, probs, rows, K, p, seed, offset, lse, addend, stream);
+  else run_sm_bwd<__nv_bfloat16>(dy, dx, probs, rows, K, p, seed, offset, lse, addend, stream);
 }
 
 }  // namespace ub

@@ -268,27 +268,37 @@ std::tuple<Tensor, Tensor> rmsnorm_bwd(const Tensor& dy, const Tensor& x, const 
 // ---------------------------------------------------------------------------------------------------
 // softmax + dropout
 // ---------------------------------------------------------------------------------------------------
-std::tuple<Tensor, int64_t, int64_t> softmax_dropout_fwd(Tensor x, const OptTensor& mask, const OptTensor& bias, double p,
-                                                         bool training) {
+struct SmBroadcast {
+  long long rows, mask_div = 1, bias_rows = 1;
+  int K;
+};
+
+static SmBroadcast softmax_broadcast_plan(const Tensor& x, const OptTensor& mask, const OptTensor& bias) {
   check_cuda_contig(x, "input");
   TORCH_CHECK(x.dim() == 3, "input must be 3-D [batch, q, k]");
-  const c10::cuda::CUDAGuard guard(x.device());
-  const long long rows = x.size(0) * x.size(1);
-  const int K = (int)x.size(2);
-  long long mask_div = 1, bias_rows = 1;
+  SmBroadcast b;
+  b.rows = x.size(0) * x.size(1);
+  b.K = (int)x.size(2);
   if (mask.has_value() && mask->defined()) {
     check_cuda_contig(*mask, "mask");
-    TORCH_CHECK(mask->scalar_type() == x.scalar_type() && mask->dim() == 3 && mask->size(2) == K);
+    TORCH_CHECK(mask->scalar_type() == x.scalar_type() && mask->dim() == 3 && mask->size(2) == b.K);
     const long long mask_rows = mask->size(0) * mask->size(1);
-    TORCH_CHECK(mask_rows > 0 && rows % mask_rows == 0, "mask rows must divide input rows");
-    mask_div = rows / mask_rows;
+    TORCH_CHECK(mask_rows > 0 && b.rows % mask_rows == 0, "mask rows must divide input rows");
+    b.mask_div = b.rows / mask_rows;
   }
   if (bias.has_value() && bias->defined()) {
     check_cuda_contig(*bias, "bias");
-    TORCH_CHECK(bias->scalar_type() == x.scalar_type() && bias->dim() == 3 && bias->size(2) == K);
-    bias_rows = bias->size(0) * bias->size(1);
-    TORCH_CHECK(bias_rows > 0 && rows % bias_rows == 0, "bias rows must divide input rows");
+    TORCH_CHECK(bias->scalar_type() == x.scalar_type() && bias->dim() == 3 && bias->size(2) == b.K);
+    b.bias_rows = bias->size(0) * bias->size(1);
+    TORCH_CHECK(b.bias_rows > 0 && b.rows % b.bias_rows == 0, "bias rows must divide input rows");
   }
+  return b;
+}
+
+std::tuple<Tensor, int64_t, int64_t> softmax_dropout_fwd(Tensor x, const OptTensor& mask, const OptTensor& bias, double p,
+                                                         bool training) {
+  const SmBroadcast b = softmax_broadcast_plan(x, mask, bias);
+  const c10::cuda::CUDAGuard guard(x.device());
   const float pf = training ? (float)p : 0.f;
   uint64_t seed = 0, offset = 0;
   Tensor out = x;
@@ -298,10 +308,52 @@ std::tuple<Tensor, int64_t, int64_t> softmax_dropout_fwd(Tensor x, const OptTens
     offset = so.second;
     out = torch::empty_like(x);
   }
-  ub::launch_softmax_dropout_fwd(x.data_ptr(), out.data_ptr(), opt_ptr(mask), opt_ptr(bias), rows, K, mask_div,
-                                 bias_rows, pf, seed, offset, dtype_tag(x), cur_stream());
+  ub::launch_softmax_dropout_fwd(x.data_ptr(), out.data_ptr(), opt_ptr(mask), opt_ptr(bias), b.rows, b.K, b.mask_div,
+                                 b.bias_rows, pf, seed, offset, dtype_tag(x), cur_stream());
   check_launch("softmax_dropout_fwd");
   return {out, (int64_t)seed, (int64_t)offset};
+}
+
+// Logits mode: x is read-only; returns (dropout(softmax(z)), z = x + mask + bias, row log-sum-exp, seed, offset).
+std::tuple<Tensor, Tensor, Tensor, int64_t, int64_t> softmax_dropout_logits_fwd(const Tensor& x, const OptTensor& mask,
+                                                                                 const OptTensor& bias, double p,
+                                                                                 bool training) {
+  const SmBroadcast b = softmax_broadcast_plan(x, mask, bias);
+  const c10::cuda::CUDAGuard guard(x.device());
+  const float pf = training ? (float)p : 0.f;
+  uint64_t seed = 0, offset = 0;
+  if (pf > 0.f) {
+    auto so = philox_reserve(4);
+    seed = so.first;
+    offset = so.second;
+  }
+  Tensor out = torch::empty_like(x), logits = torch::empty_like(x);
+  Tensor lse = torch::empty({x.size(0), x.size(1)}, x.options().dtype(torch::kFloat32));
+  ub::launch_softmax_dropout_fwd(x.data_ptr(), out.data_ptr(), opt_ptr(mask), opt_ptr(bias), b.rows, b.K, b.mask_div,
+                                 b.bias_rows, pf, seed, offset, dtype_tag(x), cur_stream(), logits.data_ptr(),
+                                 lse.data_ptr<float>());
+  check_launch("softmax_dropout_logits_fwd");
+  return {out, logits, lse, (int64_t)seed, (int64_t)offset};
+}
+
+Tensor softmax_dropout_logits_bwd(const Tensor& dy, const Tensor& logits, const Tensor& lse, const OptTensor& addend,
+                                  double p, int64_t seed, int64_t offset) {
+  check_cuda_contig(dy, "grad_output");
+  check_cuda_contig(logits, "logits");
+  check_cuda_contig(lse, "lse");
+  TORCH_CHECK(dy.dim() == 3 && dy.sizes() == logits.sizes() && dy.scalar_type() == logits.scalar_type());
+  TORCH_CHECK(lse.scalar_type() == torch::kFloat32 && lse.numel() == dy.size(0) * dy.size(1));
+  if (addend.has_value() && addend->defined()) {
+    check_cuda_contig(*addend, "grad_logits");
+    TORCH_CHECK(addend->sizes() == dy.sizes() && addend->scalar_type() == dy.scalar_type());
+  }
+  const c10::cuda::CUDAGuard guard(dy.device());
+  Tensor dx = torch::empty_like(dy);
+  ub::launch_softmax_dropout_bwd(dy.data_ptr(), dx.data_ptr(), logits.data_ptr(), dy.size(0) * dy.size(1),
+                                 (int)dy.size(2), (float)p, (uint64_t)seed, (uint64_t)offset, dtype_tag(dy),
+                                 cur_stream(), lse.data_ptr<float>(), opt_ptr(addend));
+  check_launch("softmax_dropout_logits_bwd");
+  return dx;
 }
 
 Tensor softmax_dropout_bwd(Tensor dy, const Tensor& probs, double p, int64_t seed, int64_t offset) {
@@ -505,6 +557,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
   m.def("softmax_dropout_fwd", &softmax_dropout_fwd);
   m.def("softmax_dropout_bwd", &softmax_dropout_bwd);
+  m.def("softmax_dropout_logits_fwd", &softmax_dropout_logits_fwd);
+  m.def("softmax_dropout_logits_bwd", &softmax_dropout_logits_bwd);
   m.def("bias_gelu_fwd", &bias_gelu_fwd);
   m.def("bias_gelu_bwd", &bias_gelu_bwd);
   m.def("bias_dropout_add_ln_fwd", &bias_dropout_add_ln_fwd);

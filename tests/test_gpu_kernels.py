@@ -265,6 +265,55 @@ def test_softmax_inplace_contract():
     assert out2.data_ptr() != x2.data_ptr()
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("k,p", [(128, 0.0), (248, 0.2), (100, 0.2), (2048, 0.0)])
+def test_softmax_dropout_with_logits(dtype, k, p):
+    """Logits mode: z = x + mask + bias is an output with its own gradient; -inf bias entries (padding) included."""
+    ops = _ops()
+    torch.manual_seed(11)
+    B, H, Q = 3, 4, 24
+    x = torch.randn(B, H, Q, k, device="cuda").to(dtype)
+    bias = torch.randn(B, H, Q, k, device="cuda").to(dtype)
+    bias[1, :, :, k - 5:] = float("-inf")
+    bias[2, 1, 3, :] = float("-inf")  # a fully masked row must give zeros, not NaN
+    pad = torch.zeros(B, 1, 1, k, device="cuda", dtype=dtype)
+    pad[0, :, :, :3] = float("-inf")
+    xin, bin_ = x.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    x_before = xin.detach().clone()
+    out, z = ops.softmax_dropout_with_logits(xin, p, True, mask=pad, bias=bin_)
+    assert torch.equal(xin.detach(), x_before), "input must not be overwritten"
+    z_ref = (x + pad) + bias if dtype != torch.float32 else x + pad + bias
+    finite = torch.isfinite(z_ref)
+    assert torch.equal(torch.isfinite(z), finite)
+    assert maxdiff(torch.where(finite, z, torch.zeros_like(z)), torch.where(finite, z_ref, torch.zeros_like(z))) <= TOL[dtype] * 4
+    kept = (out != 0) if p > 0 else torch.ones_like(out, dtype=torch.bool)
+    zr = z.detach().float().masked_fill(~finite, float("-inf"))
+    probs_ref = torch.nan_to_num(F.softmax(zr, dim=-1), nan=0.0)
+    assert not torch.isnan(out).any()
+    assert ((out.float() - probs_ref / (1 - p)).abs() * kept).max().item() < (2e-3 if dtype != torch.bfloat16 else 1.6e-2)
+    if p > 0:
+        live = probs_ref > 1e-4
+        assert abs((kept & live).float().sum().item() / live.float().sum().item() - (1 - p)) < 0.02
+    # gradients: through the probabilities AND directly into the logits output
+    dy, dz = torch.randn_like(out), torch.randn_like(z)
+    torch.autograd.backward([out, z], [dy, dz])
+    safe = z.detach().float().masked_fill(~finite, -1e4).requires_grad_(True)
+    alive = finite.any(dim=-1, keepdim=True).float()  # fully masked rows: zero probabilities, gradient = dz only
+    ref = F.softmax(safe, dim=-1) * kept.float() * alive / (1 - p)
+    torch.autograd.backward([ref, safe * 1.0], [dy.float(), dz.float()])
+    tol = 2e-3 if dtype == torch.float16 else (2e-2 if dtype == torch.bfloat16 else 1e-5)
+    scale = max(1.0, dz.abs().max().item())
+    assert maxdiff(xin.grad, safe.grad) < tol * scale
+    assert maxdiff(bin_.grad, safe.grad) < tol * scale
+    # only the probability path: no gradient arrives for the logits
+    xin2 = x.clone().requires_grad_(True)
+    out2, _ = ops.softmax_dropout_with_logits(xin2, 0.0, True, mask=pad, bias=bias)
+    out2.backward(dy)
+    safe2 = safe.detach().requires_grad_(True)
+    (F.softmax(safe2, dim=-1) * alive).backward(dy.float())
+    assert maxdiff(xin2.grad, safe2.grad) < tol
+
+
 # ---------------------------------------------------------------------------------------------------
 # fused element-wise
 # ---------------------------------------------------------------------------------------------------

@@ -42,21 +42,20 @@ def _materialised_attention(q, k, v, scaling, key_padding_mask, attn_bias4, drop
     qh = (q * scaling).permute(0, 2, 1, 3).reshape(bsz * heads, tgt_len, dim)
     kh = k.permute(0, 2, 1, 3).reshape(bsz * heads, src_len, dim)
     vh = v.permute(0, 2, 1, 3).reshape(bsz * heads, src_len, dim)
-    attn_weights = torch.bmm(qh, kh.transpose(1, 2))
+    w4 = torch.bmm(qh, kh.transpose(1, 2)).view(bsz, heads, tgt_len, src_len)
+    pad = None
     if key_padding_mask is not None:
-        attn_weights = attn_weights.view(bsz, heads, tgt_len, src_len)
-        attn_weights.masked_fill_(key_padding_mask[:, None, None, :].to(torch.bool), float("-inf"))
-        attn_weights = attn_weights.view(bsz * heads, tgt_len, src_len)
-    w4 = attn_weights.view(bsz, heads, tgt_len, src_len)
-    bias = attn_bias4.to(attn_weights.dtype) if attn_bias4 is not None else None
+        # additive [B, 1, 1, K] mask: consumed by the softmax kernel's broadcast instead of a masked_fill_ pass
+        pad = torch.zeros(bsz, 1, 1, src_len, dtype=w4.dtype, device=w4.device)
+        pad.masked_fill_(key_padding_mask[:, None, None, :].to(torch.bool), float("-inf"))
+    bias = attn_bias4.to(w4.dtype) if attn_bias4 is not None else None
     if not return_attn:
-        attn = ops.softmax_dropout(w4, dropout, training, bias=bias)
+        attn = ops.softmax_dropout(w4, dropout, training, mask=pad, bias=bias)
         logits = probs = None
     else:
-        if bias is not None:
-            w4 = w4 + bias
-        logits = w4.view(bsz * heads, tgt_len, src_len)
-        attn = ops.softmax_dropout(w4, dropout, training, inplace=False)
+        # logits (scores + mask + bias) are an output: the pair representation of the next layer
+        attn, logits = ops.softmax_dropout_with_logits(w4, dropout, training, mask=pad, bias=bias)
+        logits = logits.view(bsz * heads, tgt_len, src_len)
         probs = attn.view(bsz * heads, tgt_len, src_len)
     attn = attn.view(bsz * heads, tgt_len, src_len)
     out = torch.bmm(attn, vh)

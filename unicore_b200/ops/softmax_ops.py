@@ -78,10 +78,67 @@ class _SoftmaxDropoutFn(torch.autograd.Function):
         if dy.data_ptr() == probs.data_ptr():
             dy = dy.clone()
         dx = native().softmax_dropout_bwd(dy, probs, ctx.p, ctx.rng[0], ctx.rng[1])
-        dbias = None
-        if ctx.bias_rows > 0:
-            dbias = dx.view(-1, ctx.bias_rows, dx.shape[-2], dx.shape[-1]).sum(dim=0)
-        return dx, None, dbias, None, None
+        return dx, None, _bias_grad(dx, ctx.bias_rows), None, None
+
+
+def _bias_grad(dx3, bias_rows):
+    """Gradient of a ``[bias_rows, Q, K]`` bias that was broadcast (modulo) over the rows of ``dx3``."""
+    if bias_rows <= 0:
+        return None
+    if bias_rows == dx3.shape[0]:
+        return dx3  # nothing was broadcast: the two gradients are the same tensor, no pass over it
+    return dx3.view(-1, bias_rows, dx3.shape[-2], dx3.shape[-1]).sum(dim=0)
+
+
+class _SoftmaxDropoutLogitsFn(torch.autograd.Function):
+    """``z = x + mask + bias`` and ``dropout(softmax(z))`` from one kernel; ``z`` is an output (the pair
+    representation handed to the next layer), its incoming gradient is folded into the backward kernel's store."""
+
+    @staticmethod
+    def forward(ctx, x3, mask3, bias3, p, training):
+        out, logits, lse, seed, offset = native().softmax_dropout_logits_fwd(x3, mask3, bias3, float(p), bool(training))
+        ctx.p = float(p) if training else 0.0
+        ctx.rng = (seed, offset)
+        ctx.bias_rows = bias3.shape[0] if (bias3 is not None and bias3.requires_grad) else 0
+        ctx.save_for_backward(logits, lse)
+        return out, logits
+
+    @staticmethod
+    def backward(ctx, dy, dlogits):
+        logits, lse = ctx.saved_tensors
+        if dy is None:
+            dy = torch.zeros_like(logits)
+        dx = native().softmax_dropout_logits_bwd(
+            dy.contiguous(), logits, lse, None if dlogits is None else dlogits.contiguous(), ctx.p, ctx.rng[0], ctx.rng[1]
+        )
+        return dx, None, _bias_grad(dx, ctx.bias_rows), None, None
+
+
+def _kernel_operands(input, mask, bias, may_overwrite):
+    """Bring ``mask`` / ``bias`` into the kernel's 3-D broadcast forms (pre-adding whatever does not fit)."""
+    if input.dim() == 2:
+        input = input.unsqueeze(0)
+        mask = mask.unsqueeze(0) if mask is not None and mask.dim() == 2 else mask
+        bias = bias.unsqueeze(0) if bias is not None and bias.dim() == 2 else bias
+    if mask is not None:
+        if _mask_plan(mask, input):
+            mask = mask.contiguous().view(-1, mask.shape[-2], mask.shape[-1])
+        else:
+            input = input.add_(mask) if may_overwrite and not input.requires_grad else input + mask
+            mask = None
+    if bias is not None:
+        if _bias_plan(bias, input):
+            bias = bias.contiguous().view(-1, bias.shape[-2], bias.shape[-1])
+        else:
+            input = input.add_(bias) if may_overwrite and not input.requires_grad else input + bias
+            bias = None
+    return input.view(-1, input.shape[-2], input.shape[-1]), mask, bias
+
+
+def _kernel_eligible(input, mask, bias):
+    return use_native(input, mask, bias) and input.dim() >= 2 and input.numel() > 0 and input.dtype in (
+        torch.float16, torch.bfloat16, torch.float32
+    )
 
 
 def softmax_dropout(input, dropout_prob, is_training=True, mask=None, bias=None, inplace=True):
@@ -89,27 +146,9 @@ def softmax_dropout(input, dropout_prob, is_training=True, mask=None, bias=None,
     input = input.contiguous()
     if not inplace:
         input = input.clone()
-    if use_native(input, mask, bias) and input.dim() >= 2 and input.dtype in (
-        torch.float16, torch.bfloat16, torch.float32
-    ) and input.numel() > 0:
+    if _kernel_eligible(input, mask, bias):
         shape = input.shape
-        if input.dim() == 2:
-            input = input.unsqueeze(0)
-            mask = mask.unsqueeze(0) if mask is not None and mask.dim() == 2 else mask
-            bias = bias.unsqueeze(0) if bias is not None and bias.dim() == 2 else bias
-        if mask is not None:
-            if _mask_plan(mask, input):
-                mask = mask.contiguous().view(-1, mask.shape[-2], mask.shape[-1])
-            else:
-                input = input + mask if input.requires_grad else input.add_(mask)
-                mask = None
-        if bias is not None:
-            if _bias_plan(bias, input):
-                bias = bias.contiguous().view(-1, bias.shape[-2], bias.shape[-1])
-            else:
-                input = input + bias if input.requires_grad else input.add_(bias)
-                bias = None
-        x3 = input.view(-1, input.shape[-2], input.shape[-1])
+        x3, mask, bias = _kernel_operands(input, mask, bias, may_overwrite=True)
         if x3.requires_grad and x3.is_leaf:
             x3 = x3.clone()  # cannot overwrite a leaf that needs grad
         out = _SoftmaxDropoutFn.apply(x3, mask, bias, dropout_prob, is_training)
@@ -119,3 +158,27 @@ def softmax_dropout(input, dropout_prob, is_training=True, mask=None, bias=None,
     if bias is not None:
         input = input + bias
     return F.dropout(F.softmax(input, dim=-1), p=dropout_prob, training=is_training)
+
+
+def softmax_dropout_with_logits(input, dropout_prob, is_training=True, mask=None, bias=None):
+    """``(dropout(softmax(z)), z)`` with ``z = input + mask + bias`` materialised once.
+
+    The ``return_attn=True`` formulation of the reference (``unicore/modules/multihead_attention.py:98-103``:
+    ``attn_weights += attn_bias`` then ``softmax_dropout(..., inplace=False)``) spends a pass on the bias add,
+    a clone, and - in backward - an add of the two gradients that meet at ``z``.  Here ``z`` is a by-product
+    of the softmax kernel, no probability tensor is kept (backward rebuilds it from ``z`` and the row
+    log-sum-exp) and the gradient arriving for ``z`` is added inside the backward kernel.  ``input`` is not
+    modified.
+    """
+    input = input.contiguous()
+    if _kernel_eligible(input, mask, bias):
+        shape = input.shape
+        x3, mask, bias = _kernel_operands(input, mask, bias, may_overwrite=False)
+        out, logits = _SoftmaxDropoutLogitsFn.apply(x3, mask, bias, dropout_prob, is_training)
+        return out.view(shape), logits.view(shape)
+    logits = input
+    if mask is not None:
+        logits = logits + mask
+    if bias is not None:
+        logits = logits + bias
+    return F.dropout(F.softmax(logits, dim=-1), p=dropout_prob, training=is_training), logits
