@@ -110,6 +110,11 @@ void launch_bias_dropout_add_ln_bwd(const void* dy, const void* summed, const fl
                                     unsigned long long offset, int dtype, cudaStream_t stream);
 // ---- Gaussian radial basis of (mul[edge] * d + bias[edge]) (Uni-Mol pair features), csrc/fused/gaussian.cu ----------
 // y: [n, K] in `dtype` (fp16 / bf16), K a multiple of 8 with K / 8 a power of two <= 32
+// token-major [B, L, T, H, D] <-> T head-major [B, H, L, D] tensors (null head pointer = zeros when gathering);
+// slice 0 is multiplied by scale0 in either direction.  D * sizeof(elem) must be a multiple of 16.
+void launch_head_permute(void* token_major, void* const* head_major, int B, int L, int T, int H, int D, float scale0,
+                         bool to_heads, int dtype, cudaStream_t stream);
+
 void launch_gbf_fwd(const void* d, const long long* edge, const void* mul_w, const void* bias_w, const void* means,
                     const void* stds, void* y, long long n, int K, int dtype, cudaStream_t stream);
 // part: float[gbf_parts(n, K)][2 * K] per-CTA partial (d mean, d std); hist: float[2 * E] zero-initialised (d mul, d bias)

@@ -496,6 +496,64 @@ Tensor softmax_xent_bwd(const Tensor& logits, const Tensor& target, const Tensor
 }
 
 // ---------------------------------------------------------------------------------------------------
+// head split / merge
+// ---------------------------------------------------------------------------------------------------
+static void check_head_geometry(const Tensor& ref, int64_t D) {
+  TORCH_CHECK(ref.scalar_type() == at::kHalf || ref.scalar_type() == at::kBFloat16 || ref.scalar_type() == at::kFloat,
+              "head permute supports fp16 / bf16 / fp32");
+  TORCH_CHECK((D * ref.element_size()) % 16 == 0, "head_dim must span whole 16-byte vectors");
+}
+
+// x: [B, L, T*H*D] contiguous -> T tensors [B, H, L, D] (slices of one allocation); slice 0 scaled by scale0
+std::vector<Tensor> split_heads(const Tensor& x, int64_t T, int64_t H, double scale0) {
+  check_cuda_contig(x, "input");
+  TORCH_CHECK(x.dim() == 3 && T >= 1 && T <= 4 && H >= 1 && x.size(2) % (T * H) == 0, "expected [B, L, T*H*D]");
+  const int64_t B = x.size(0), L = x.size(1), D = x.size(2) / (T * H);
+  check_head_geometry(x, D);
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(x.data_ptr()) & 15) == 0, "input must be 16-byte aligned");
+  const c10::cuda::CUDAGuard guard(x.device());
+  Tensor packed = torch::empty({T, B, H, L, D}, x.options());
+  std::vector<Tensor> out;
+  void* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int64_t t = 0; t < T; ++t) {
+    out.push_back(packed.select(0, t));
+    ptrs[t] = out.back().data_ptr();
+  }
+  ub::launch_head_permute(x.data_ptr(), ptrs, (int)B, (int)L, (int)T, (int)H, (int)D, (float)scale0, true, dtype_tag(x),
+                          cur_stream());
+  check_launch("split_heads");
+  return out;
+}
+
+// heads: T optional tensors [B, H, L, D] (undefined = zeros) -> [B, L, T*H*D]; slice 0 scaled by scale0
+Tensor merge_heads(const std::vector<OptTensor>& heads, double scale0) {
+  const int64_t T = (int64_t)heads.size();
+  TORCH_CHECK(T >= 1 && T <= 4);
+  const Tensor* ref = nullptr;
+  for (const auto& h : heads)
+    if (h.has_value() && h->defined()) ref = &*h;
+  TORCH_CHECK(ref != nullptr, "merge_heads needs at least one defined tensor");
+  TORCH_CHECK(ref->dim() == 4, "expected [B, H, L, D]");
+  const int64_t B = ref->size(0), H = ref->size(1), L = ref->size(2), D = ref->size(3);
+  check_head_geometry(*ref, D);
+  void* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int64_t t = 0; t < T; ++t) {
+    if (!(heads[t].has_value() && heads[t]->defined())) continue;
+    const Tensor& h = *heads[t];
+    check_cuda_contig(h, "head-major tensor");
+    TORCH_CHECK(h.sizes() == ref->sizes() && h.scalar_type() == ref->scalar_type());
+    TORCH_CHECK((reinterpret_cast<uintptr_t>(h.data_ptr()) & 15) == 0, "head-major tensors must be 16-byte aligned");
+    ptrs[t] = h.data_ptr();
+  }
+  const c10::cuda::CUDAGuard guard(ref->device());
+  Tensor out = torch::empty({B, L, T * H * D}, ref->options());
+  ub::launch_head_permute(out.data_ptr(), ptrs, (int)B, (int)L, (int)T, (int)H, (int)D, (float)scale0, false,
+                          dtype_tag(*ref), cur_stream());
+  check_launch("merge_heads");
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Gaussian basis (Uni-Mol)
 // ---------------------------------------------------------------------------------------------------
 Tensor gbf_fwd(const Tensor& d, const Tensor& edge, const Tensor& mul_w, const Tensor& bias_w, const Tensor& means,
@@ -565,6 +623,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bias_dropout_add_ln_bwd", &bias_dropout_add_ln_bwd);
   m.def("softmax_xent_fwd", &softmax_xent_fwd);
   m.def("softmax_xent_bwd", &softmax_xent_bwd);
+  m.def("split_heads", &split_heads);
+  m.def("merge_heads", &merge_heads);
   m.def("gbf_fwd", &gbf_fwd);
   m.def("gbf_bwd", &gbf_bwd);
   register_fmha(m);

@@ -68,6 +68,29 @@ def test_pair_representation_threads_through_layers():
     assert torch.isfinite(pair.grad).all() and pair.grad.abs().sum() > 0
 
 
+def test_unimol_encoder_folds_padding_into_first_layer():
+    """Padding enters through the first layer's softmax mask; result equals the reference's up-front -inf fill."""
+    from unicore_b200.models.unimol import TransformerEncoderWithPair
+
+    torch.manual_seed(4)
+    enc = TransformerEncoderWithPair(encoder_layers=3, embed_dim=32, ffn_embed_dim=64, attention_heads=4, emb_dropout=0.0,
+                                     dropout=0.0, attention_dropout=0.0, max_seq_len=16).eval()
+    emb, pair = torch.randn(2, 8, 32), torch.randn(2 * 4, 8, 8)
+    pad = torch.zeros(2, 8, dtype=torch.bool)
+    pad[0, 5:] = True
+    x, pair_out, delta, x_norm, delta_norm = enc(emb, attn_mask=pair, padding_mask=pad)
+    h = enc.emb_layer_norm(emb) * (1 - pad.unsqueeze(-1).float())
+    b = pair.view(2, 4, 8, 8).masked_fill(pad[:, None, None, :], float("-inf")).view(8, 8, 8)
+    for layer in enc.layers:
+        h, b, _ = layer(h, padding_mask=None, attn_bias=b, return_attn=True)
+    ref_pair = b.view(2, 4, 8, 8).permute(0, 2, 3, 1)
+    assert torch.equal(torch.isinf(pair_out), torch.isinf(ref_pair)) and torch.isinf(pair_out[0, :, 5:]).all()
+    finite = torch.isfinite(ref_pair)
+    assert torch.allclose(pair_out[finite], ref_pair[finite], atol=1e-5)
+    assert torch.allclose(x, enc.final_layer_norm(h), atol=1e-5)
+    assert torch.isfinite(delta).all() and torch.isfinite(x_norm) and torch.isfinite(delta_norm)
+
+
 def test_decoder_is_causal_and_attends_to_encoder():
     from unicore.modules import CrossMultiheadAttention, TransformerDecoder
 

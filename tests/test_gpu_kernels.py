@@ -315,6 +315,37 @@ def test_softmax_dropout_with_logits(dtype, k, p):
 
 
 # ---------------------------------------------------------------------------------------------------
+# head split / merge
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("B,L,H,D", [(3, 37, 64, 8), (2, 128, 12, 64), (1, 1, 5, 16)])
+def test_split_merge_heads(dtype, B, L, H, D):
+    ops = _ops()
+    torch.manual_seed(12)
+    scale = D ** -0.5
+    x = torch.randn(B, L, 3 * H * D, device="cuda").to(dtype).requires_grad_(True)
+    q, k, v = ops.split_heads(x, 3, H, scale)
+    ref = x.detach().view(B, L, 3, H, D).permute(2, 0, 3, 1, 4)
+    assert q.shape == (B, H, L, D) and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    assert maxdiff(q, ref[0].float() * scale) <= TOL[dtype] and torch.equal(k, ref[1]) and torch.equal(v, ref[2])
+    # gradient gathered by one kernel; a slice nobody used reads as zeros
+    gq, gv = torch.randn_like(q), torch.randn_like(v)
+    torch.autograd.backward([q, v], [gq, gv])
+    g = x.grad.view(B, L, 3, H, D)
+    assert maxdiff(g[:, :, 0], gq.permute(0, 2, 1, 3).float() * scale) <= TOL[dtype] * 4
+    assert g[:, :, 1].abs().max().item() == 0 and torch.equal(g[:, :, 2], gv.permute(0, 2, 1, 3))
+    # merge is the inverse (and split its backward)
+    o = torch.randn(B, H, L, D, device="cuda").to(dtype).requires_grad_(True)
+    m = ops.merge_heads(o)
+    assert m.shape == (B, L, H * D) and torch.equal(m, o.detach().permute(0, 2, 1, 3).reshape(B, L, H * D))
+    gm = torch.randn_like(m)
+    m.backward(gm)
+    assert torch.equal(o.grad, gm.view(B, L, H, D).permute(0, 2, 1, 3))
+    back = ops.merge_heads(q.detach(), k.detach(), v.detach(), scale0=1.0 / scale)
+    assert maxdiff(back, x) <= TOL[dtype] * 4
+
+
+# ---------------------------------------------------------------------------------------------------
 # fused element-wise
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])

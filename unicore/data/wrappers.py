@@ -343,14 +343,23 @@ class LMDBDataset:
             self.db_path, subdir=False, readonly=True, lock=False, readahead=False, meminit=False, max_readers=256
         )
 
+    def connect_db(self, lmdb_path=None, save_to_self=False):
+        """Open the environment; keep it on the instance when ``save_to_self`` (``lmdb_dataset.py:26``)."""
+        if lmdb_path is not None:
+            self.db_path = lmdb_path
+        env = self._open()
+        if save_to_self:
+            self.env = env
+            return None
+        return env
+
     def __len__(self):
         return len(self._keys)
 
     def _read(self, idx):
-        env = self.__dict__.get("env")
-        if env is None:
-            env = self.env = self._open()
-        return pickle.loads(env.begin().get(self._keys[idx]))
+        if self.__dict__.get("env") is None:
+            self.connect_db(save_to_self=True)
+        return pickle.loads(self.env.begin().get(self._keys[idx]))
 
     def __getitem__(self, idx):
         return self._memo.get(idx, self._read)

@@ -98,6 +98,9 @@ class BaseProgressBar(object):
     def print(self, stats, tag=None, step=None):
         raise NotImplementedError
 
+    def update_config(self, config):
+        """Hook for sinks that record the run configuration (console bars ignore it)."""
+
     def _str_commas(self, stats):
         return ", ".join("{}={}".format(k, v.strip()) for k, v in stats.items())
 
@@ -292,6 +295,11 @@ class TensorboardProgressBarWrapper(BaseProgressBar):
     def print(self, stats, tag=None, step=None):
         self._forward(stats, tag, step)
         self.wrapped_bar.print(stats, tag=tag, step=step)
+
+    def update_config(self, config):
+        if self.wandb is not None:
+            self.wandb.config.update(config, allow_val_change=True)
+        self.wrapped_bar.update_config(config)
 
     def _forward(self, stats, tag=None, step=None):
         writer = self._writer(tag or "")

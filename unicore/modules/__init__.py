@@ -3,7 +3,7 @@
 import sys as _sys
 import types as _types
 
-from .norm import LayerNorm, RMSNorm
+from .norm import FusedLayerNormFastFunction, FusedRMSNormFastFunction, LayerNorm, RMSNorm
 from .softmax_dropout import softmax_dropout
 from .attention import CrossMultiheadAttention, SelfMultiheadAttention
 from .transformer import (
@@ -12,6 +12,7 @@ from .transformer import (
     TransformerEncoder,
     TransformerEncoderLayer,
     bulid_future_mask,
+    fill_with_neg_inf,
     init_bert_params,
     relative_position_bucket,
 )
@@ -23,13 +24,13 @@ __all__ = [
 ]
 
 _LEGACY = {
-    "layer_norm": ["LayerNorm"],
-    "rms_norm": ["RMSNorm"],
+    "layer_norm": ["LayerNorm", "FusedLayerNormFastFunction"],
+    "rms_norm": ["RMSNorm", "FusedRMSNormFastFunction"],
     "multihead_attention": ["SelfMultiheadAttention", "CrossMultiheadAttention"],
     "transformer_encoder_layer": ["TransformerEncoderLayer"],
     "transformer_encoder": ["TransformerEncoder", "init_bert_params", "relative_position_bucket"],
     "transformer_decoder_layer": ["TransformerDecoderLayer"],
-    "transformer_decoder": ["TransformerDecoder", "bulid_future_mask"],
+    "transformer_decoder": ["TransformerDecoder", "bulid_future_mask", "fill_with_neg_inf"],
 }
 for _mod, _names in _LEGACY.items():
     _full = __name__ + "." + _mod

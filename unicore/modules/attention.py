@@ -35,14 +35,16 @@ def _bias_as_4d(attn_bias: Optional[Tensor], bsz: int, heads: int, tgt: int, src
     raise ValueError("unsupported attn_bias shape {}".format(tuple(attn_bias.shape)))
 
 
-def _materialised_attention(q, k, v, scaling, key_padding_mask, attn_bias4, dropout, training, return_attn):
-    """q,k,v: [B, L, H, D]. Returns (out [B, Lq, H*D], logits?, probs?)."""
-    bsz, tgt_len, heads, dim = q.shape
-    src_len = k.shape[1]
-    qh = (q * scaling).permute(0, 2, 1, 3).reshape(bsz * heads, tgt_len, dim)
-    kh = k.permute(0, 2, 1, 3).reshape(bsz * heads, src_len, dim)
-    vh = v.permute(0, 2, 1, 3).reshape(bsz * heads, src_len, dim)
-    w4 = torch.bmm(qh, kh.transpose(1, 2)).view(bsz, heads, tgt_len, src_len)
+def _materialised_attention(qh, kh, vh, key_padding_mask, attn_bias4, dropout, training, return_attn):
+    """qh, kh, vh: head-major ``[B, H, L, D]`` (contiguous, query already scaled).
+
+    Returns ``(out [B, Lq, H*D], logits?, probs?)``; scores are materialised (``return_attn`` / head dims the
+    tcgen05 kernel does not cover).  Parity: reference ``multihead_attention.py:78-118``.
+    """
+    bsz, heads, tgt_len, dim = qh.shape
+    src_len = kh.shape[2]
+    w4 = torch.bmm(qh.view(bsz * heads, tgt_len, dim), kh.view(bsz * heads, src_len, dim).transpose(1, 2))
+    w4 = w4.view(bsz, heads, tgt_len, src_len)
     pad = None
     if key_padding_mask is not None:
         # additive [B, 1, 1, K] mask: consumed by the softmax kernel's broadcast instead of a masked_fill_ pass
@@ -57,10 +59,8 @@ def _materialised_attention(q, k, v, scaling, key_padding_mask, attn_bias4, drop
         attn, logits = ops.softmax_dropout_with_logits(w4, dropout, training, mask=pad, bias=bias)
         logits = logits.view(bsz * heads, tgt_len, src_len)
         probs = attn.view(bsz * heads, tgt_len, src_len)
-    attn = attn.view(bsz * heads, tgt_len, src_len)
-    out = torch.bmm(attn, vh)
-    out = out.view(bsz, heads, tgt_len, dim).transpose(1, 2).reshape(bsz, tgt_len, heads * dim)
-    return out, logits, probs
+    out = torch.bmm(attn.view(bsz * heads, tgt_len, src_len), vh.view(bsz * heads, src_len, dim))
+    return ops.merge_heads(out.view(bsz, heads, tgt_len, dim)), logits, probs
 
 
 class SelfMultiheadAttention(nn.Module):
@@ -92,9 +92,8 @@ class SelfMultiheadAttention(nn.Module):
                 dropout_p=self.dropout, training=self.training, scale=self.scaling,
             ).reshape(bsz, tgt_len, embed_dim)
             return o, None, None
-        return _materialised_attention(
-            q, k, v, self.scaling, key_padding_mask, bias4, self.dropout, self.training, return_attn
-        )
+        qh, kh, vh = ops.split_heads(qkv.view(bsz, tgt_len, 3 * embed_dim), 3, self.num_heads, self.scaling)
+        return _materialised_attention(qh, kh, vh, key_padding_mask, bias4, self.dropout, self.training, return_attn)
 
     def forward(
         self,
@@ -140,9 +139,10 @@ class CrossMultiheadAttention(nn.Module):
                 q, k, v, bias=bias4, key_padding_mask=key_padding_mask,
                 dropout_p=self.dropout, training=self.training, scale=self.scaling,
             ).reshape(bsz, tgt_len, embed_dim)
-        o, _, _ = _materialised_attention(
-            q, k, v, self.scaling, key_padding_mask, bias4, self.dropout, self.training, False
-        )
+        (qh,) = ops.split_heads(q.view(bsz, tgt_len, embed_dim), 1, self.num_heads, self.scaling)
+        (kh,) = ops.split_heads(k.view(bsz, src_len, embed_dim), 1, self.num_heads)
+        (vh,) = ops.split_heads(v.view(bsz, src_len, embed_dim), 1, self.num_heads)
+        o, _, _ = _materialised_attention(qh, kh, vh, key_padding_mask, bias4, self.dropout, self.training, False)
         return o
 
     def forward(

@@ -57,3 +57,20 @@ class RMSNorm(nn.Module):
 
     def extra_repr(self):
         return "{}, eps={}, elementwise_affine=True".format(tuple(self.normalized_shape), self.eps)
+
+
+class FusedLayerNormFastFunction:
+    """Call-compatible stand-in for the reference autograd Function (``layer_norm.py:22-48``): user code that
+    calls ``FusedLayerNormFastFunction.apply(x, w, b, shape, eps)`` lands on the same kernels as the module."""
+
+    @staticmethod
+    def apply(input, weight, bias, normalized_shape, eps):
+        return ops.layer_norm(input, _as_shape(normalized_shape), weight, bias, eps)
+
+
+class FusedRMSNormFastFunction:
+    """``FusedRMSNormFastFunction.apply(x, w, shape, eps)`` (reference ``rms_norm.py:24-50``)."""
+
+    @staticmethod
+    def apply(input, weight, normalized_shape, eps):
+        return ops.rms_norm(input, _as_shape(normalized_shape), weight, eps)

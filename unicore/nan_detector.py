@@ -18,10 +18,18 @@ class NanDetector:
         self._reported = {"forward": False, "backward": False}
         for name, mod in model.named_modules():
             mod.__dict__["_nan_detector_name"] = name
-            if forward:
-                self.fhooks.append(mod.register_forward_hook(self._fhook))
-            if backward:
-                self.bhooks.append(mod.register_full_backward_hook(self._bhook))
+            self.add_hooks(mod)
+
+    def add_hooks(self, module):
+        """Attach the scanners to one more module (reference ``nan_detector.py:52``)."""
+        if self.forward:
+            self.fhooks.append(module.register_forward_hook(self.fhook_fn))
+        if self.backward:
+            self.bhooks.append(module.register_full_backward_hook(self.bhook_fn))
+
+    def reset(self):
+        """Report again on the next non-finite tensor of either pass."""
+        self._reported = {"forward": False, "backward": False}
 
     def __enter__(self):
         return self
@@ -68,10 +76,10 @@ class NanDetector:
                 self._reported[kind] = True
                 return
 
-    def _fhook(self, module, inp, output):
+    def fhook_fn(self, module, inp, output):
         self._scan(module, output, "forward")
 
-    def _bhook(self, module, grad_in, grad_out):
+    def bhook_fn(self, module, grad_in, grad_out):
         self._scan(module, grad_out, "backward")
 
     def close(self):

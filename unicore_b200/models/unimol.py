@@ -157,9 +157,13 @@ class TransformerEncoderWithPair(nn.Module):
                 pad = None
             return mask, pad
 
-        attn_mask, padding_mask = fill(attn_mask, padding_mask, float("-inf"))
+        # The reference writes -inf into the padded key columns of the pair bias up front (a full pass over
+        # [B, H, L, L] and another in backward).  Here the first layer's softmax kernel adds the [B, 1, 1, L]
+        # padding mask while it forms the logits; those logits ARE the next layer's bias, so the -inf columns
+        # travel with the pair representation from then on.
         for layer in self.layers:
             x, attn_mask, _ = layer(x, padding_mask=padding_mask, attn_bias=attn_mask, return_attn=True)
+            padding_mask = None
 
         def norm_loss(t, eps=1e-10, tolerance=1.0):
             t = t.float()
