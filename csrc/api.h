@@ -115,6 +115,14 @@ void launch_bias_dropout_add_ln_bwd(const void* dy, const void* summed, const fl
 void launch_head_permute(void* token_major, void* const* head_major, int B, int L, int T, int H, int D, float scale0,
                          bool to_heads, int dtype, cudaStream_t stream);
 
+// head-major [B, H, M] <-> pair-major [B, M, H] for 16-bit elements (H % 8 == 0, M % 8 == 0)
+void launch_pair_transpose(const void* in, void* out, int B, int H, long long M, bool to_pair, cudaStream_t stream);
+// encoder tail of pair-bias models: pair = T(z) with -inf -> 0, delta = T(z - z0) with padded keys -> 0 (Lk % 8 == 0)
+void launch_pair_tail_fwd(const void* z, const void* z0, const unsigned char* key_pad, void* pair, void* delta, int B,
+                          int H, int Lq, int Lk, int dtype, cudaStream_t stream);
+void launch_pair_tail_bwd(const void* d_pair, const void* d_delta, const void* z, const unsigned char* key_pad, void* dz,
+                          void* dz0, int B, int H, int Lq, int Lk, int dtype, cudaStream_t stream);
+
 void launch_gbf_fwd(const void* d, const long long* edge, const void* mul_w, const void* bias_w, const void* means,
                     const void* stds, void* y, long long n, int K, int dtype, cudaStream_t stream);
 // part: float[gbf_parts(n, K)][2 * K] per-CTA partial (d mean, d std); hist: float[2 * E] zero-initialised (d mul, d bias)

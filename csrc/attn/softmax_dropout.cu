@@ -22,8 +22,6 @@
 // gradient that arrived for the logits output (`addend`) before its single store.
 #include <math_constants.h>
 
-#include <cstdlib>
-
 #include "../api.h"
 #include "../common.cuh"
 
@@ -69,6 +67,8 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
   const uint32_t thresh = dropout_thresh16(p);
   const bool drop = p > 0.f;
   const bool logits_mode = lse != nullptr;
+  // broadcast row lookups without 64-bit division (~100 emulated instructions each) in the common cases
+  const bool bias_per_row = g.bias_rows >= g.rows, narrow = g.rows < (1ll << 31);
   const long long stride_rows = (long long)gridDim.x * rows_per_cta;
   const long long iters = (g.rows + stride_rows - 1) / stride_rows;
   for (long long it = 0; it < iters; ++it) {
@@ -83,13 +83,17 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
         unpack<T>(ld_global_nc_v4(x + row * g.K + (long long)vi * EPV), v[k]);
         if (mask != nullptr) {
           float t[EPV];
-          unpack<T>(ld_global_v4(mask + (row / g.mask_div) * g.K + (long long)vi * EPV), t);
+          const long long mrow = narrow ? (long long)((unsigned)row / (unsigned)g.mask_div) : row / g.mask_div;
+          unpack<T>(ld_global_v4(mask + mrow * g.K + (long long)vi * EPV), t);
 #pragma unroll
           for (int e = 0; e < EPV; ++e) v[k][e] += t[e];
         }
         if (bias != nullptr) {
           float t[EPV];
-          unpack<T>(ld_global_v4(bias + (row % g.bias_rows) * g.K + (long long)vi * EPV), t);
+          const long long brow = bias_per_row ? row
+                                 : narrow     ? (long long)((unsigned)row % (unsigned)g.bias_rows)
+                                              : row % g.bias_rows;
+          unpack<T>(ld_global_v4(bias + brow * g.K + (long long)vi * EPV), t);
 #pragma unroll
           for (int e = 0; e < EPV; ++e) v[k][e] += t[e];
         }
@@ -203,232 +207,6 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_bwd_kernel(
           if (addend != nullptr) {
             float a[EPV];
             unpack<T>(ld_global_nc_v4(addend + off), a);
-#pragma unroll
-            for (int e = 0; e < EPV; ++e) o[e] += a[e];
-          }
-          st_global_v4(dx + off, pack<T>(o));
-        }
-      }
-    }
-  }
-}
-
-// R rows per group per iteration: their loads are issued back to back before the first dependent reduction,
-// which doubles the bytes in flight per warp (one 16-byte vector per thread per row is too little to cover
-// HBM latency at full occupancy; measured 3.5 TB/s with R = 1 on [2M x 250] bf16 rows).
-template <typename T, int VPT, int R>
-__global__ void __launch_bounds__(kSmThreads, R > 1 ? 4 : 1) softmax_dropout_fwd_rows_kernel(
-    T* __restrict__ x, T* __restrict__ out, const T* __restrict__ mask, const T* __restrict__ bias, SmGeom g, float p,
-    float keep_scale, unsigned long long seed, unsigned long long offset, T* __restrict__ logits,
-    float* __restrict__ lse) {
-  constexpr int EPV = VecTraits<T>::kElems;
-  __shared__ float scratch[8];
-  const int tpr = g.tpr, rows_per_cta = kSmThreads / tpr;
-  const int grp = threadIdx.x / tpr, j = threadIdx.x % tpr;
-  const uint32_t thresh = dropout_thresh16(p);
-  const bool drop = p > 0.f;
-  const bool logits_mode = lse != nullptr;
-  const long long stride_rows = (long long)gridDim.x * rows_per_cta;
-  const long long iters = (g.rows + stride_rows * R - 1) / (stride_rows * R);
-  for (long long it = 0; it < iters; ++it) {
-    long long row[R];
-    bool active[R];
-    // R > 1: every row's loads are issued before the first store (the stores are ordering points for the compiler)
-    Vec16 raw_x[R][VPT], raw_m[R][VPT], raw_b[R][VPT];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      row[r] = ((it * R + r) * gridDim.x + blockIdx.x) * rows_per_cta + grp;
-      active[r] = row[r] < g.rows;
-      if constexpr (R > 1) {
-#pragma unroll
-        for (int k = 0; k < VPT; ++k) {
-          const int vi = j + k * tpr;
-          if (active[r] && vi < g.nvec) {
-            raw_x[r][k] = ld_global_nc_v4(x + row[r] * g.K + (long long)vi * EPV);
-            if (mask != nullptr) raw_m[r][k] = ld_global_v4(mask + (row[r] / g.mask_div) * g.K + (long long)vi * EPV);
-            if (bias != nullptr) raw_b[r][k] = ld_global_v4(bias + (row[r] % g.bias_rows) * g.K + (long long)vi * EPV);
-          }
-        }
-      }
-    }
-    float v[R][VPT][EPV];
-    float mx[R], sum[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      mx[r] = -CUDART_INF_F;
-#pragma unroll
-      for (int k = 0; k < VPT; ++k) {
-        const int vi = j + k * tpr;
-        if (active[r] && vi < g.nvec) {
-          if constexpr (R == 1) {
-            raw_x[r][k] = ld_global_nc_v4(x + row[r] * g.K + (long long)vi * EPV);
-            if (mask != nullptr) raw_m[r][k] = ld_global_v4(mask + (row[r] / g.mask_div) * g.K + (long long)vi * EPV);
-            if (bias != nullptr) raw_b[r][k] = ld_global_v4(bias + (row[r] % g.bias_rows) * g.K + (long long)vi * EPV);
-          }
-          unpack<T>(raw_x[r][k], v[r][k]);
-          if (mask != nullptr) {
-            float t[EPV];
-            unpack<T>(raw_m[r][k], t);
-#pragma unroll
-            for (int e = 0; e < EPV; ++e) v[r][k][e] += t[e];
-          }
-          if (bias != nullptr) {
-            float t[EPV];
-            unpack<T>(raw_b[r][k], t);
-#pragma unroll
-            for (int e = 0; e < EPV; ++e) v[r][k][e] += t[e];
-          }
-          if (logits_mode) {
-            const Vec16 z = pack<T>(v[r][k]);
-            st_global_v4(logits + row[r] * g.K + (long long)vi * EPV, z);
-            unpack<T>(z, v[r][k]);  // the softmax sees the stored (rounded) logits
-          }
-#pragma unroll
-          for (int e = 0; e < EPV; ++e) mx[r] = fmaxf(mx[r], v[r][k][e]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < EPV; ++e) v[r][k][e] = -CUDART_INF_F;
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      mx[r] = group_reduce<true>(mx[r], tpr, scratch);
-      if (mx[r] == -CUDART_INF_F) mx[r] = 0.f;  // fully masked row
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      sum[r] = 0.f;
-#pragma unroll
-      for (int k = 0; k < VPT; ++k) {
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) {
-          v[r][k][e] = exp2f((v[r][k][e] - mx[r]) * 1.4426950408889634f);
-          sum[r] += v[r][k][e];
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) sum[r] = group_reduce<false>(sum[r], tpr, scratch);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (!active[r]) continue;
-      const float inv = sum[r] > 0.f ? 1.f / sum[r] : 0.f;
-      if (logits_mode && j == 0) lse[row[r]] = sum[r] > 0.f ? mx[r] + logf(sum[r]) : CUDART_INF_F;
-#pragma unroll
-      for (int k = 0; k < VPT; ++k) {
-        const int vi = j + k * tpr;
-        if (vi < g.nvec) {
-          const long long off = row[r] * g.K + (long long)vi * EPV;
-          float pr[EPV];
-#pragma unroll
-          for (int e = 0; e < EPV; ++e) pr[e] = v[r][k][e] * inv;
-          const Vec16 packed = pack<T>(pr);
-          if (!logits_mode) st_global_v4(x + off, packed);
-          else if (!drop) st_global_v4(out + off, packed);
-          if (drop) {
-            const uint32_t keep = dropout_keep8(seed, offset, (unsigned long long)off >> 3, thresh) >> (off & 7);
-            float rounded[EPV], o[EPV];
-            unpack<T>(packed, rounded);  // dropout acts on the stored (rounded) probabilities
-#pragma unroll
-            for (int e = 0; e < EPV; ++e) o[e] = ((keep >> e) & 1u) ? rounded[e] * keep_scale : 0.f;
-            st_global_v4(out + off, pack<T>(o));
-          }
-        }
-      }
-    }
-  }
-}
-
-template <typename T, int VPT, int R>
-__global__ void __launch_bounds__(kSmThreads, R > 1 ? 4 : 1) softmax_dropout_bwd_rows_kernel(
-    const T* dy, T* dx, const T* __restrict__ probs, SmGeom g, float p, float keep_scale, unsigned long long seed,
-    unsigned long long offset, const float* __restrict__ lse, const T* __restrict__ addend) {
-  constexpr int EPV = VecTraits<T>::kElems;
-  __shared__ float scratch[8];
-  const int tpr = g.tpr, rows_per_cta = kSmThreads / tpr;
-  const int grp = threadIdx.x / tpr, j = threadIdx.x % tpr;
-  const uint32_t thresh = dropout_thresh16(p);
-  const bool drop = p > 0.f;
-  const long long stride_rows = (long long)gridDim.x * rows_per_cta;
-  const long long iters = (g.rows + stride_rows * R - 1) / (stride_rows * R);
-  for (long long it = 0; it < iters; ++it) {
-    long long row[R];
-    bool active[R];
-    Vec16 raw_d[R][VPT], raw_y[R][VPT], raw_a[R][VPT];
-    float row_lse[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      row[r] = ((it * R + r) * gridDim.x + blockIdx.x) * rows_per_cta + grp;
-      active[r] = row[r] < g.rows;
-      row_lse[r] = (lse != nullptr && active[r]) ? lse[row[r]] : 0.f;
-      if constexpr (R > 1) {
-#pragma unroll
-        for (int k = 0; k < VPT; ++k) {
-          const int vi = j + k * tpr;
-          if (active[r] && vi < g.nvec) {
-            const long long off = row[r] * g.K + (long long)vi * EPV;
-            raw_d[r][k] = ld_global_nc_v4(dy + off);
-            raw_y[r][k] = ld_global_nc_v4(probs + off);
-            if (addend != nullptr) raw_a[r][k] = ld_global_nc_v4(addend + off);
-          }
-        }
-      }
-    }
-    float d[R][VPT][EPV], y[R][VPT][EPV];
-    float dot[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      dot[r] = 0.f;
-#pragma unroll
-      for (int k = 0; k < VPT; ++k) {
-        const int vi = j + k * tpr;
-        if (active[r] && vi < g.nvec) {
-          const long long off = row[r] * g.K + (long long)vi * EPV;
-          if constexpr (R == 1) {
-            raw_d[r][k] = ld_global_nc_v4(dy + off);
-            raw_y[r][k] = ld_global_nc_v4(probs + off);
-          }
-          unpack<T>(raw_d[r][k], d[r][k]);
-          unpack<T>(raw_y[r][k], y[r][k]);
-          if (lse != nullptr) {  // `probs` holds logits: rebuild the (rounded) probabilities forward used
-#pragma unroll
-            for (int e = 0; e < EPV; ++e) y[r][k][e] = exp2f((y[r][k][e] - row_lse[r]) * 1.4426950408889634f);
-            unpack<T>(pack<T>(y[r][k]), y[r][k]);
-          }
-          if (drop) {
-            const uint32_t keep = dropout_keep8(seed, offset, (unsigned long long)off >> 3, thresh) >> (off & 7);
-#pragma unroll
-            for (int e = 0; e < EPV; ++e) d[r][k][e] = ((keep >> e) & 1u) ? d[r][k][e] * keep_scale : 0.f;
-          }
-#pragma unroll
-          for (int e = 0; e < EPV; ++e) {
-            d[r][k][e] *= y[r][k][e];
-            dot[r] += d[r][k][e];
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < EPV; ++e) d[r][k][e] = y[r][k][e] = 0.f;
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) dot[r] = group_reduce<false>(dot[r], tpr, scratch);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (!active[r]) continue;
-#pragma unroll
-      for (int k = 0; k < VPT; ++k) {
-        const int vi = j + k * tpr;
-        if (vi < g.nvec) {
-          const long long off = row[r] * g.K + (long long)vi * EPV;
-          float o[EPV];
-#pragma unroll
-          for (int e = 0; e < EPV; ++e) o[e] = d[r][k][e] - y[r][k][e] * dot[r];
-          if (addend != nullptr) {
-            float a[EPV];
-            if constexpr (R == 1) raw_a[r][k] = ld_global_nc_v4(addend + off);
-            unpack<T>(raw_a[r][k], a);
 #pragma unroll
             for (int e = 0; e < EPV; ++e) o[e] += a[e];
           }
@@ -554,16 +332,6 @@ static bool make_sm_geom(SmGeom& g, long long rows, int K, int epv, int& vpt) {
   return vpt <= 4;
 }
 
-// rows per iteration: 2 while a row is one vector per thread (64 registers, 4 CTAs/SM), 1 above (register
-// budget).  UNICORE_SOFTMAX_ROWS=1 forces the single-row variant (A/B measurements).
-static bool two_rows_per_iter() {
-  static const bool two = [] {
-    const char* e = std::getenv("UNICORE_SOFTMAX_ROWS");
-    return e == nullptr || e[0] != '1';
-  }();
-  return two;
-}
-
 #define UB_SM_VPT(VPT_VALUE, ...)                              \
   switch (VPT_VALUE) {                                         \
     case 1: { constexpr int VPT = 1; __VA_ARGS__; break; }     \
@@ -591,13 +359,8 @@ static void run_sm_fwd(void* x, void* out, const void* mask, const void* bias, l
     long long need = (rows + rows_per_cta - 1) / rows_per_cta;
     const long long cap = (long long)sm_count2() * 8;
     const int grid = (int)(need < cap ? need : cap);
-    if (vpt == 1 && two_rows_per_iter()) {
-      softmax_dropout_fwd_rows_kernel<T, 1, 2><<<grid, kSmThreads, 0, stream>>>(
-          (T*)x, (T*)out, (const T*)mask, (const T*)bias, g, p, keep_scale, seed, offset, (T*)logits, lse);
-    } else {
-      UB_SM_VPT(vpt, (softmax_dropout_fwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>(
-                         (T*)x, (T*)out, (const T*)mask, (const T*)bias, g, p, keep_scale, seed, offset, (T*)logits, lse)));
-    }
+    UB_SM_VPT(vpt, (softmax_dropout_fwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>(
+                       (T*)x, (T*)out, (const T*)mask, (const T*)bias, g, p, keep_scale, seed, offset, (T*)logits, lse)));
   } else {
     long long need = (rows + 7) / 8;
     const long long cap = (long long)sm_count2() * 8;
@@ -623,13 +386,8 @@ static void run_sm_bwd(const void* dy, void* dx, const void* probs, long long ro
     long long need = (rows + rows_per_cta - 1) / rows_per_cta;
     const long long cap = (long long)sm_count2() * 8;
     const int grid = (int)(need < cap ? need : cap);
-    if (vpt == 1 && two_rows_per_iter()) {
-      softmax_dropout_bwd_rows_kernel<T, 1, 2><<<grid, kSmThreads, 0, stream>>>(
-          (const T*)dy, (T*)dx, (const T*)probs, g, p, keep_scale, seed, offset, lse, (const T*)addend);
-    } else {
-      UB_SM_VPT(vpt, (softmax_dropout_bwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>(
-                         (const T*)dy, (T*)dx, (const T*)probs, g, p, keep_scale, seed, offset, lse, (const T*)addend)));
-    }
+    UB_SM_VPT(vpt, (softmax_dropout_bwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>(
+                       (const T*)dy, (T*)dx, (const T*)probs, g, p, keep_scale, seed, offset, lse, (const T*)addend)));
   } else {
     long long need = (rows + 7) / 8;
     const long long cap = (long long)sm_count2() * 8;

@@ -554,6 +554,72 @@ Tensor merge_heads(const std::vector<OptTensor>& heads, double scale0) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// pair representation relayout
+// ---------------------------------------------------------------------------------------------------
+static void check_pair_operand(const Tensor& t, const char* what) {
+  check_cuda_contig(t, what);
+  TORCH_CHECK(t.dim() == 4, what, " must be 4-D");
+  TORCH_CHECK(t.scalar_type() == at::kHalf || t.scalar_type() == at::kBFloat16, what, " must be fp16 / bf16");
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(t.data_ptr()) & 15) == 0, what, " must be 16-byte aligned");
+}
+
+static const unsigned char* key_pad_ptr(const OptTensor& key_pad, int64_t B, int64_t Lk) {
+  if (!(key_pad.has_value() && key_pad->defined())) return nullptr;
+  check_cuda_contig(*key_pad, "key_padding_mask");
+  TORCH_CHECK(key_pad->element_size() == 1 && key_pad->dim() == 2 && key_pad->size(0) == B && key_pad->size(1) == Lk,
+              "key_padding_mask must be a [B, Lk] bool / uint8 tensor");
+  return reinterpret_cast<const unsigned char*>(key_pad->data_ptr());
+}
+
+// to_pair: [B, H, Lq, Lk] -> [B, Lq, Lk, H];  otherwise the inverse
+Tensor pair_transpose(const Tensor& x, bool to_pair) {
+  check_pair_operand(x, "input");
+  const int64_t B = x.size(0);
+  const int64_t H = to_pair ? x.size(1) : x.size(3);
+  const int64_t Lq = to_pair ? x.size(2) : x.size(1), Lk = to_pair ? x.size(3) : x.size(2);
+  TORCH_CHECK(H % 8 == 0 && (Lq * Lk) % 8 == 0, "pair_transpose needs H % 8 == 0 and Lq * Lk % 8 == 0");
+  const c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = to_pair ? torch::empty({B, Lq, Lk, H}, x.options()) : torch::empty({B, H, Lq, Lk}, x.options());
+  ub::launch_pair_transpose(x.data_ptr(), out.data_ptr(), (int)B, (int)H, Lq * Lk, to_pair, cur_stream());
+  check_launch("pair_transpose");
+  return out;
+}
+
+std::tuple<Tensor, Tensor> pair_tail_fwd(const Tensor& z, const Tensor& z0, const OptTensor& key_pad) {
+  check_pair_operand(z, "logits");
+  check_pair_operand(z0, "input bias");
+  TORCH_CHECK(z.sizes() == z0.sizes() && z.scalar_type() == z0.scalar_type());
+  const int64_t B = z.size(0), H = z.size(1), Lq = z.size(2), Lk = z.size(3);
+  TORCH_CHECK(H % 8 == 0 && Lk % 8 == 0, "pair_tail needs H % 8 == 0 and Lk % 8 == 0");
+  const unsigned char* pad = key_pad_ptr(key_pad, B, Lk);
+  const c10::cuda::CUDAGuard guard(z.device());
+  Tensor pair = torch::empty({B, Lq, Lk, H}, z.options()), delta = torch::empty({B, Lq, Lk, H}, z.options());
+  ub::launch_pair_tail_fwd(z.data_ptr(), z0.data_ptr(), pad, pair.data_ptr(), delta.data_ptr(), (int)B, (int)H, (int)Lq,
+                           (int)Lk, dtype_tag(z), cur_stream());
+  check_launch("pair_tail_fwd");
+  return {pair, delta};
+}
+
+std::tuple<Tensor, Tensor> pair_tail_bwd(const OptTensor& d_pair, const OptTensor& d_delta, const Tensor& z,
+                                         const OptTensor& key_pad) {
+  check_pair_operand(z, "logits");
+  const int64_t B = z.size(0), H = z.size(1), Lq = z.size(2), Lk = z.size(3);
+  for (const OptTensor* g : {&d_pair, &d_delta}) {
+    if (!(g->has_value() && (*g)->defined())) continue;
+    check_pair_operand(**g, "gradient");
+    TORCH_CHECK((*g)->size(0) == B && (*g)->size(1) == Lq && (*g)->size(2) == Lk && (*g)->size(3) == H &&
+                (*g)->scalar_type() == z.scalar_type());
+  }
+  const unsigned char* pad = key_pad_ptr(key_pad, B, Lk);
+  const c10::cuda::CUDAGuard guard(z.device());
+  Tensor dz = torch::empty_like(z), dz0 = torch::empty_like(z);
+  ub::launch_pair_tail_bwd(opt_ptr(d_pair), opt_ptr(d_delta), z.data_ptr(), pad, dz.data_ptr(), dz0.data_ptr(), (int)B,
+                           (int)H, (int)Lq, (int)Lk, dtype_tag(z), cur_stream());
+  check_launch("pair_tail_bwd");
+  return {dz, dz0};
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Gaussian basis (Uni-Mol)
 // ---------------------------------------------------------------------------------------------------
 Tensor gbf_fwd(const Tensor& d, const Tensor& edge, const Tensor& mul_w, const Tensor& bias_w, const Tensor& means,
@@ -625,6 +691,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("softmax_xent_bwd", &softmax_xent_bwd);
   m.def("split_heads", &split_heads);
   m.def("merge_heads", &merge_heads);
+  m.def("pair_transpose", &pair_transpose);
+  m.def("pair_tail_fwd", &pair_tail_fwd);
+  m.def("pair_tail_bwd", &pair_tail_bwd);
   m.def("gbf_fwd", &gbf_fwd);
   m.def("gbf_bwd", &gbf_bwd);
   register_fmha(m);

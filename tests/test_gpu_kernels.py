@@ -345,6 +345,48 @@ def test_split_merge_heads(dtype, B, L, H, D):
     assert maxdiff(back, x) <= TOL[dtype] * 4
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,L", [(3, 64, 40), (2, 8, 24), (1, 16, 8)])
+def test_pair_layout_kernels(dtype, B, H, L):
+    """Register-tile transposes between head-major and pair-major, and the fused encoder tail."""
+    ops = _ops()
+    torch.manual_seed(13)
+    x = torch.randn(B, H, L, L, device="cuda").to(dtype).requires_grad_(True)
+    y = ops.heads_to_pair(x)
+    assert y.shape == (B, L, L, H) and y.is_contiguous() and torch.equal(y, x.detach().permute(0, 2, 3, 1))
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    assert torch.equal(x.grad, gy.permute(0, 3, 1, 2))
+    assert torch.equal(ops.pair_to_heads(y.detach()), x.detach())
+    # encoder tail: z carries -inf in padded key columns (and a stray one elsewhere), z0 is finite
+    pad = torch.zeros(B, L, dtype=torch.bool, device="cuda")
+    pad[0, L - 3:] = True
+    z0 = torch.randn(B, H, L, L, device="cuda").to(dtype).requires_grad_(True)
+    z = (z0.detach().float() + torch.randn(B, H, L, L, device="cuda")).to(dtype)
+    z = z.masked_fill(pad[:, None, None, :], float("-inf"))
+    z[-1, 0, 1, 2] = float("-inf")
+    z.requires_grad_(True)
+    pair, delta = ops.pair_tail(z, z0, pad)
+    zr, z0r = z.detach().float().requires_grad_(True), z0.detach().float().requires_grad_(True)
+    pair_ref = zr.masked_fill(zr == float("-inf"), 0).permute(0, 2, 3, 1)
+    delta_ref = (zr - z0r).masked_fill(pad[:, None, None, :], 0).permute(0, 2, 3, 1)
+    assert torch.equal(pair.float(), pair_ref.detach())
+    stray = torch.isinf(delta_ref.detach())
+    assert stray.sum().item() == 1 and torch.equal(torch.isinf(delta), stray)
+    assert maxdiff(delta.masked_fill(stray, 0), delta_ref.detach().masked_fill(stray, 0)) <= TOL[dtype] * 4
+    gp, gd = torch.randn_like(pair), torch.randn_like(delta)
+    gd = gd.masked_fill(stray, 0)
+    torch.autograd.backward([pair, delta], [gp, gd])
+    torch.autograd.backward([pair_ref, delta_ref], [gp.float(), gd.float()])
+    assert maxdiff(z.grad, zr.grad) <= TOL[dtype] * 4 and maxdiff(z0.grad, z0r.grad) <= TOL[dtype]
+    # one of the two outputs unused
+    z2 = z.detach().clone().requires_grad_(True)
+    p2, _ = ops.pair_tail(z2, z0.detach(), None)
+    p2.backward(gp)
+    live = ~torch.isinf(z.detach())
+    assert maxdiff(z2.grad, gp.float().permute(0, 3, 1, 2) * live) <= TOL[dtype]
+
+
 # ---------------------------------------------------------------------------------------------------
 # fused element-wise
 # ---------------------------------------------------------------------------------------------------

@@ -149,14 +149,6 @@ class TransformerEncoderWithPair(nn.Module):
         input_attn_mask = attn_mask
         input_padding_mask = padding_mask
 
-        def fill(mask, pad, value):
-            if mask is not None and pad is not None:
-                mask = mask.view(bsz, -1, seq_len, seq_len)
-                mask = mask.masked_fill(pad.unsqueeze(1).unsqueeze(2).to(torch.bool), value)
-                mask = mask.view(-1, seq_len, seq_len)
-                pad = None
-            return mask, pad
-
         # The reference writes -inf into the padded key columns of the pair bias up front (a full pass over
         # [B, H, L, L] and another in backward).  Here the first layer's softmax kernel adds the [B, 1, 1, L]
         # padding mask while it forms the logits; those logits ARE the next layer's bias, so the -inf columns
@@ -165,10 +157,10 @@ class TransformerEncoderWithPair(nn.Module):
             x, attn_mask, _ = layer(x, padding_mask=padding_mask, attn_bias=attn_mask, return_attn=True)
             padding_mask = None
 
-        def norm_loss(t, eps=1e-10, tolerance=1.0):
-            t = t.float()
-            err = torch.abs(torch.sqrt(torch.sum(t ** 2, dim=-1) + eps) - math.sqrt(t.shape[-1]))
-            return F.relu(err - tolerance)
+        def norm_loss(t, tolerance=1.0):
+            # |t|_2 accumulated in fp32 by the reduction itself (no fp32 copy of the pair tensor)
+            norm = torch.linalg.vector_norm(t, dim=-1, dtype=torch.float32)
+            return F.relu(torch.abs(norm - math.sqrt(t.shape[-1])) - tolerance)
 
         def masked_mean(mask, value, dim=-1, eps=1e-10):
             return (torch.sum(mask * value, dim=dim) / (eps + torch.sum(mask, dim=dim))).mean()
@@ -179,10 +171,11 @@ class TransformerEncoderWithPair(nn.Module):
         if self.final_layer_norm is not None:
             x = self.final_layer_norm(x)
 
-        delta = attn_mask - input_attn_mask
-        delta, _ = fill(delta, input_padding_mask, 0)
-        attn_mask = attn_mask.view(bsz, -1, seq_len, seq_len).permute(0, 2, 3, 1).contiguous()
-        delta = delta.view(bsz, -1, seq_len, seq_len).permute(0, 2, 3, 1).contiguous()
+        # pair-major outputs in one pass: pair = logits with -inf -> 0 (what the heads consume), delta = change of
+        # the pair representation through the stack with padded key columns zeroed
+        attn_mask, delta = ops.pair_tail(
+            attn_mask.view(bsz, -1, seq_len, seq_len), input_attn_mask.view(bsz, -1, seq_len, seq_len), input_padding_mask
+        )
         pair_mask = token_mask[..., None] * token_mask[..., None, :]
         delta_norm = masked_mean(pair_mask, norm_loss(delta), dim=(-1, -2))
         if self.final_head_layer_norm is not None:
@@ -250,9 +243,9 @@ class UniMolModel(BaseUnicoreModel):
         x = self.embed_tokens(src_tokens)
         n_node = src_distance.size(-1)
         gbf_feature = self.gbf(src_distance, src_edge_type)
-        graph_attn_bias = self.gbf_proj(gbf_feature).permute(0, 3, 1, 2).contiguous().view(-1, n_node, n_node)
+        graph_attn_bias = ops.pair_to_heads(self.gbf_proj(gbf_feature)).view(-1, n_node, n_node)
         enc, pair, delta_pair, x_norm, delta_norm = self.encoder(x, padding_mask=padding_mask, attn_mask=graph_attn_bias)
-        pair = pair.masked_fill(pair == float("-inf"), 0)
+        # (the encoder already returns the pair representation with its -inf entries zeroed)
         logits = coord = dist = None
         if not features_only:
             if self.args.masked_token_loss > 0:

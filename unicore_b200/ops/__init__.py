@@ -22,5 +22,5 @@ from .optim_ops import (  # noqa: F401
     multi_tensor_l2norm,
     multi_tensor_scale_,
 )
-from .layout_ops import merge_heads, split_heads  # noqa: F401
+from .layout_ops import heads_to_pair, merge_heads, pair_tail, pair_to_heads, split_heads  # noqa: F401
 from .softmax_ops import softmax_dropout, softmax_dropout_with_logits  # noqa: F401

@@ -84,3 +84,82 @@ def merge_heads(*heads: torch.Tensor, scale0: float = 1.0) -> torch.Tensor:
     if 1 <= len(heads) <= 4 and _eligible(ref, ref.shape[-1]):
         return _MergeHeadsFn.apply(float(scale0), *[h.contiguous() for h in heads])
     return _merge_reference(list(heads), float(scale0))
+
+
+# ------------------------------------------------------------------------------------------------
+# pair representation: head-major [B, H, Lq, Lk] <-> pair-major [B, Lq, Lk, H]
+# ------------------------------------------------------------------------------------------------
+def _pair_eligible(x: torch.Tensor, heads: int, lq: int, lk: int, need_lk8: bool) -> bool:
+    return (
+        use_native(x)
+        and x.dtype in (torch.float16, torch.bfloat16)
+        and heads % 8 == 0
+        and (lq * lk) % 8 == 0
+        and (lk % 8 == 0 or not need_lk8)
+        and x.numel() > 0
+    )
+
+
+class _PairTransposeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, to_pair):
+        ctx.to_pair = to_pair
+        return native().pair_transpose(x, to_pair)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return native().pair_transpose(grad.contiguous(), not ctx.to_pair), None
+
+
+def heads_to_pair(x: torch.Tensor) -> torch.Tensor:
+    """``[B, H, Lq, Lk] -> [B, Lq, Lk, H]`` (contiguous) - register-tile transpose, see ``csrc/fused/pair_layout.cu``."""
+    if x.dim() == 4 and _pair_eligible(x, x.shape[1], x.shape[2], x.shape[3], False):
+        return _PairTransposeFn.apply(x.contiguous(), True)
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def pair_to_heads(x: torch.Tensor) -> torch.Tensor:
+    """``[B, Lq, Lk, H] -> [B, H, Lq, Lk]`` (contiguous)."""
+    if x.dim() == 4 and _pair_eligible(x, x.shape[3], x.shape[1], x.shape[2], False):
+        return _PairTransposeFn.apply(x.contiguous(), False)
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+class _PairTailFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, z0, key_pad):
+        pair, delta = native().pair_tail_fwd(z, z0, key_pad)
+        ctx.save_for_backward(z, key_pad)
+        ctx.need_z0 = z0.requires_grad
+        return pair, delta
+
+    @staticmethod
+    def backward(ctx, d_pair, d_delta):
+        z, key_pad = ctx.saved_tensors
+        dz, dz0 = native().pair_tail_bwd(
+            None if d_pair is None else d_pair.contiguous(), None if d_delta is None else d_delta.contiguous(), z, key_pad
+        )
+        return dz, (dz0 if ctx.need_z0 else None), None
+
+
+def pair_tail(logits: torch.Tensor, input_bias: torch.Tensor, key_padding_mask: Optional[torch.Tensor] = None):
+    """Tail of a pair-bias encoder in one pass over the ``[B, H, Lq, Lk]`` logits.
+
+    Returns ``(pair, delta)``, both pair-major ``[B, Lq, Lk, H]``:
+    ``pair = logits`` with ``-inf -> 0`` and ``delta = logits - input_bias`` with padded key columns set to 0
+    (Uni-Mol's ``TransformerEncoderWithPair`` computes them with a subtraction, two ``masked_fill``, an equality
+    pass and two ``permute().contiguous()`` copies - and the mirror image of all that in backward).
+    """
+    if logits.shape != input_bias.shape or logits.dim() != 4:
+        raise ValueError("pair_tail expects two [B, H, Lq, Lk] tensors")
+    bsz, heads, lq, lk = logits.shape
+    if key_padding_mask is not None:
+        key_padding_mask = key_padding_mask.to(torch.bool)
+    if _pair_eligible(logits, heads, lq, lk, True) and input_bias.dtype == logits.dtype:
+        pad = None if key_padding_mask is None else key_padding_mask.contiguous()
+        return _PairTailFn.apply(logits.contiguous(), input_bias.contiguous(), pad)
+    delta = logits - input_bias
+    if key_padding_mask is not None:
+        delta = delta.masked_fill(key_padding_mask[:, None, None, :], 0)
+    pair = logits.masked_fill(logits == float("-inf"), 0)
+    return pair.permute(0, 2, 3, 1).contiguous(), delta.permute(0, 2, 3, 1).contiguous()
