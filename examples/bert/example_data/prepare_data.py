@@ -7,7 +7,10 @@ Writes ``<out>/train.lmdb`` and ``<out>/valid.lmdb`` (one pickled text line per 
 decimal record index) and, with ``--build-dict``, a WordPiece-less whitespace vocabulary
 ``<out>/dict.txt`` headed by the BERT specials.  For real pre-training use the published
 ``bert-base-uncased`` ``vocab.txt`` as ``dict.txt`` instead (30522 types; one token per line).
-Needs the ``lmdb`` package (not a dependency of the framework itself).
+
+``--format lmdb`` needs the ``lmdb`` package (not a dependency of the framework itself); ``--format records``
+writes the dependency-free ``unicore.data.record_store`` file under the same name (the reader recognises
+either); ``auto`` picks LMDB when it is importable.
 """
 import argparse
 import collections
@@ -21,6 +24,28 @@ def iter_lines(path, min_chars):
             line = line.strip()
             if len(line) >= min_chars and not line.startswith("="):
                 yield line
+
+
+def write_records(lines, out_path):
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", ".."))
+    from unicore.data.record_store import RecordStoreWriter
+
+    n = 0
+    with RecordStoreWriter(out_path) as w:
+        for line in lines:
+            w.append(line)
+            n += 1
+    return n
+
+
+def have_lmdb():
+    try:
+        import lmdb  # noqa: F401
+    except ImportError:
+        return False
+    return True
 
 
 def write_store(lines, out_path, map_gb):
@@ -65,11 +90,15 @@ def main():
     ap.add_argument("--map-gb", type=float, default=64)
     ap.add_argument("--build-dict", action="store_true")
     ap.add_argument("--min-count", type=int, default=5)
+    ap.add_argument("--format", choices=["auto", "lmdb", "records"], default="auto")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
+    fmt = a.format if a.format != "auto" else ("lmdb" if have_lmdb() else "records")
     for split, src in (("train", a.train), ("valid", a.valid)):
-        n = write_store(iter_lines(src, a.min_chars), os.path.join(a.out, split + ".lmdb"), a.map_gb)
-        print("{}: {} records".format(split, n))
+        dst = os.path.join(a.out, split + ".lmdb")
+        lines = iter_lines(src, a.min_chars)
+        n = write_store(lines, dst, a.map_gb) if fmt == "lmdb" else write_records(lines, dst)
+        print("{}: {} records ({})".format(split, n, fmt))
     if a.build_dict:
         build_dict([a.train], os.path.join(a.out, "dict.txt"), a.min_count, a.min_chars)
 

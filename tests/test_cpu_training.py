@@ -138,3 +138,52 @@ def test_object_collectives_and_legacy_ddp_gloo():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_object_collectives_worker, args=(2, port), nprocs=2, join=True)
+
+
+def test_bert_example_on_text_corpus(tmp_path):
+    """The real (non-synthetic) example pipeline: text -> record store -> WordPiece -> BERT masking -> padded
+    batches -> train + validate + checkpoint, through the CLI, without the optional ``lmdb`` dependency."""
+    pytest.importorskip("tokenizers")
+    import random
+
+    rng = random.Random(0)
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta", "iota", "kappa", "lambda", "mu"]
+    for split, n in (("train", 96), ("valid", 24)):
+        with open(tmp_path / (split + ".txt"), "w") as f:
+            for _ in range(n):
+                f.write(" ".join(rng.choice(words) for _ in range(rng.randint(6, 14))) + " .\n")
+    data = tmp_path / "data"
+    prep = os.path.join(ROOT, "examples", "bert", "example_data", "prepare_data.py")
+    out = subprocess.run([PY, prep, "--train", str(tmp_path / "train.txt"), "--valid", str(tmp_path / "valid.txt"),
+                          "--out", str(data), "--build-dict", "--min-count", "1", "--format", "records"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "train: 96 records (records)" in out.stdout
+
+    sys.path.insert(0, ROOT)
+    from unicore.data import LMDBDataset
+    from unicore.data.record_store import RecordStoreReader, is_record_store
+    import pickle
+
+    path = str(data / "train.lmdb")
+    assert is_record_store(path)
+    ds = LMDBDataset(path)
+    assert len(ds) == 96 and isinstance(ds[0], str) and ds[95].endswith(".")
+    clone = pickle.loads(pickle.dumps(RecordStoreReader(path)))  # what a DataLoader worker receives
+    assert clone[7] == ds[7]
+    with pytest.raises(IndexError):
+        clone.read_bytes(96)
+
+    save = str(tmp_path / "ck")
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="1")
+    cmd = [PY, os.path.join(ROOT, "unicore_cli", "train.py"), str(data), "--user-dir", os.path.join(ROOT, "examples", "bert"),
+           "--task", "bert", "--loss", "masked_lm", "--arch", "bert_base", "--encoder-layers", "2",
+           "--encoder-embed-dim", "32", "--encoder-ffn-embed-dim", "64", "--encoder-attention-heads", "4",
+           "--max-seq-len", "32", "--optimizer", "adam", "--lr", "1e-3", "--lr-scheduler", "fixed", "--batch-size", "8",
+           "--max-update", "6", "--log-format", "simple", "--log-interval", "1", "--num-workers", "1", "--cpu",
+           "--valid-subset", "valid", "--validate-interval-updates", "3", "--save-interval-updates", "3",
+           "--save-dir", save, "--distributed-world-size", "1", "--seed", "1"]
+    run = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout[-4000:]
+    assert "valid" in run.stdout and len(losses_of(run.stdout)) >= 5
+    assert os.path.isfile(os.path.join(save, "checkpoint_last.pt"))

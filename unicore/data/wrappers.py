@@ -18,6 +18,7 @@ from torch.utils.data import default_collate
 from . import data_utils
 from .base import BaseWrapperDataset, UnicoreDataset
 from .dictionary import Dictionary
+from .record_store import RecordStoreReader, is_record_store
 
 logger = logging.getLogger(__name__)
 
@@ -325,20 +326,30 @@ class LMDBDataset:
 
     ``lmdb`` is imported on first use, so the package imports without it. The
     environment handle is opened lazily per process, which keeps the object picklable for
-    DataLoader workers.
+    DataLoader workers.  Files written by ``unicore.data.record_store`` (the dependency-free
+    fallback format) are recognised by their magic and read through a memory map instead.
     """
 
     def __init__(self, db_path):
         self.db_path = db_path
         if not os.path.isfile(db_path):
             raise FileNotFoundError("{} not found".format(db_path))
-        with self._open().begin() as txn:
-            self._keys = list(txn.cursor().iternext(values=False))
+        self._store = RecordStoreReader(db_path) if is_record_store(db_path) else None
+        if self._store is None:
+            with self._open().begin() as txn:
+                self._keys = list(txn.cursor().iternext(values=False))
+        else:
+            self._keys = range(len(self._store))
         self._memo = _Memo()
 
     def _open(self):
-        import lmdb
-
+        try:
+            import lmdb
+        except ImportError as e:
+            raise ImportError(
+                "{} is an LMDB file but the `lmdb` package is not installed; install it or rewrite the corpus "
+                "with unicore.data.record_store.RecordStoreWriter".format(self.db_path)
+            ) from e
         return lmdb.open(
             self.db_path, subdir=False, readonly=True, lock=False, readahead=False, meminit=False, max_readers=256
         )
@@ -357,6 +368,8 @@ class LMDBDataset:
         return len(self._keys)
 
     def _read(self, idx):
+        if self._store is not None:
+            return self._store[idx]
         if self.__dict__.get("env") is None:
             self.connect_db(save_to_self=True)
         return pickle.loads(self.env.begin().get(self._keys[idx]))
