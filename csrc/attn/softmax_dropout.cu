@@ -31,10 +31,17 @@ constexpr int kSmThreads = 256;
 
 template <bool kMax>
 UB_DEVICE float group_reduce(float v, int tpr, float* scratch) {
-  const int lim = tpr < 32 ? tpr : 32;
-  for (int o = lim >> 1; o > 0; o >>= 1) {
-    const float other = __shfl_xor_sync(0xffffffffu, v, o);
-    v = kMax ? fmaxf(v, other) : v + other;
+  if (tpr >= 32) {  // the common case, fully unrolled (the generic loop costs 7 instructions per step)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float other = __shfl_xor_sync(0xffffffffu, v, o);
+      v = kMax ? fmaxf(v, other) : v + other;
+    }
+  } else {
+    for (int o = tpr >> 1; o > 0; o >>= 1) {
+      const float other = __shfl_xor_sync(0xffffffffu, v, o);
+      v = kMax ? fmaxf(v, other) : v + other;
+    }
   }
   if (tpr > 32) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -64,7 +71,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
   __shared__ float scratch[8];
   const int tpr = g.tpr, rows_per_cta = kSmThreads / tpr;
   const int grp = threadIdx.x / tpr, j = threadIdx.x % tpr;
-  const uint32_t thresh = dropout_thresh16(p);
+  const uint32_t thresh = dropout_thresh14(p);
   const bool drop = p > 0.f;
   const bool logits_mode = lse != nullptr;
   // broadcast row lookups without 64-bit division (~100 emulated instructions each) in the common cases
@@ -136,12 +143,22 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
           if (!logits_mode) st_global_v4(x + off, packed);
           else if (!drop) st_global_v4(out + off, packed);
           if (drop) {
-            const uint32_t keep = dropout_keep8(seed, offset, (unsigned long long)off >> 3, thresh) >> (off & 7);
-            float rounded[EPV], o[EPV];
-            unpack<T>(packed, rounded);  // dropout acts on the stored (rounded) probabilities
+            // out = keep ? p * keep_scale : 0, the scale applied in fp32 ahead of the single rounding
 #pragma unroll
-            for (int e = 0; e < EPV; ++e) o[e] = ((keep >> e) & 1u) ? rounded[e] * keep_scale : 0.f;
-            st_global_v4(out + off, pack<T>(o));
+            for (int e = 0; e < EPV; ++e) pr[e] *= keep_scale;
+            Vec16 o = pack<T>(pr);
+            if constexpr (EPV == 8) {
+              uint32_t m[4];
+              dropout_lane_masks8(seed, offset, (unsigned long long)off >> 3, thresh, m);
+#pragma unroll
+              for (int w = 0; w < 4; ++w) o.w[w] &= m[w];
+            } else {
+              const uint32_t keep = dropout_keep8_14(seed, offset, (unsigned long long)off >> 3, thresh) >> (off & 7);
+#pragma unroll
+              for (int e = 0; e < EPV; ++e)
+                if (!((keep >> e) & 1u)) o.w[e] = 0u;
+            }
+            st_global_v4(out + off, o);
           }
         }
       }
@@ -157,7 +174,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_bwd_kernel(
   __shared__ float scratch[8];
   const int tpr = g.tpr, rows_per_cta = kSmThreads / tpr;
   const int grp = threadIdx.x / tpr, j = threadIdx.x % tpr;
-  const uint32_t thresh = dropout_thresh16(p);
+  const uint32_t thresh = dropout_thresh14(p);
   const bool drop = p > 0.f;
   const long long stride_rows = (long long)gridDim.x * rows_per_cta;
   const long long iters = (g.rows + stride_rows - 1) / stride_rows;
@@ -172,21 +189,30 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_bwd_kernel(
       const int vi = j + k * tpr;
       if (active && vi < g.nvec) {
         const long long off = row * g.K + (long long)vi * EPV;
-        unpack<T>(ld_global_nc_v4(dy + off), d[k]);
+        Vec16 dyv = ld_global_nc_v4(dy + off);
+        if (drop) {
+          if constexpr (EPV == 8) {
+            uint32_t m[4];
+            dropout_lane_masks8(seed, offset, (unsigned long long)off >> 3, thresh, m);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) dyv.w[w] &= m[w];
+          } else {
+            const uint32_t keep = dropout_keep8_14(seed, offset, (unsigned long long)off >> 3, thresh) >> (off & 7);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+              if (!((keep >> e) & 1u)) dyv.w[e] = 0u;
+          }
+        }
+        unpack<T>(dyv, d[k]);
         unpack<T>(ld_global_nc_v4(probs + off), y[k]);
         if (lse != nullptr) {  // `probs` holds logits: rebuild the (rounded) probabilities forward used
 #pragma unroll
           for (int e = 0; e < EPV; ++e) y[k][e] = exp2f((y[k][e] - row_lse) * 1.4426950408889634f);
           unpack<T>(pack<T>(y[k]), y[k]);
         }
-        if (drop) {
-          const uint32_t keep = dropout_keep8(seed, offset, (unsigned long long)off >> 3, thresh) >> (off & 7);
-#pragma unroll
-          for (int e = 0; e < EPV; ++e) d[k][e] = ((keep >> e) & 1u) ? d[k][e] * keep_scale : 0.f;
-        }
 #pragma unroll
         for (int e = 0; e < EPV; ++e) {
-          d[k][e] *= y[k][e];
+          d[k][e] = d[k][e] * keep_scale * y[k][e];  // keep_scale is 1 without dropout
           dot += d[k][e];
         }
       } else {
@@ -225,7 +251,7 @@ __global__ void softmax_dropout_fwd_scalar(T* x, T* out, const T* mask, const T*
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const uint32_t thresh = dropout_thresh16(p);
+  const uint32_t thresh = dropout_thresh14(p);
   const bool logits_mode = lse != nullptr;
   for (long long row = warp; row < g.rows; row += nwarps) {
     T* xr = x + row * g.K;
@@ -256,8 +282,8 @@ __global__ void softmax_dropout_fwd_scalar(T* x, T* out, const T* mask, const T*
       else if (p <= 0.f) out[row * g.K + c] = pr;
       if (p > 0.f) {
         const unsigned long long idx = (unsigned long long)(row * g.K + c);
-        const uint32_t keep = dropout_keep8(seed, offset, idx >> 3, thresh);
-        out[row * g.K + c] = ((keep >> (idx & 7)) & 1u) ? from_f32<T>(to_f32<T>(pr) * keep_scale) : from_f32<T>(0.f);
+        const uint32_t keep = dropout_keep8_14(seed, offset, idx >> 3, thresh);
+        out[row * g.K + c] = ((keep >> (idx & 7)) & 1u) ? from_f32<T>(expf(v - mx) * inv * keep_scale) : from_f32<T>(0.f);
       }
     }
   }
@@ -270,7 +296,7 @@ __global__ void softmax_dropout_bwd_scalar(const T* dy, T* dx, const T* probs, S
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const uint32_t thresh = dropout_thresh16(p);
+  const uint32_t thresh = dropout_thresh14(p);
   for (long long row = warp; row < g.rows; row += nwarps) {
     const float row_lse = lse != nullptr ? lse[row] : 0.f;
     auto prob = [&](unsigned long long idx) {
@@ -280,7 +306,7 @@ __global__ void softmax_dropout_bwd_scalar(const T* dy, T* dx, const T* probs, S
     auto grad = [&](unsigned long long idx) {
       float d = to_f32<T>(dy[idx]);
       if (p > 0.f) {
-        const uint32_t keep = dropout_keep8(seed, offset, idx >> 3, thresh);
+        const uint32_t keep = dropout_keep8_14(seed, offset, idx >> 3, thresh);
         d = ((keep >> (idx & 7)) & 1u) ? d * keep_scale : 0.f;
       }
       return d;
@@ -341,6 +367,14 @@ static bool make_sm_geom(SmGeom& g, long long rows, int K, int epv, int& vpt) {
     default: break;                                            \
   }
 
+// 1 / P(keep) for the 14-bit threshold the kernels compare against (mirrors dropout_thresh14)
+static float keep_scale_for(float p) {
+  if (!(p > 0.f)) return 1.f;
+  const float t = p * 16384.f + 0.5f;
+  const float t14 = t >= 16383.f ? 16383.f : (float)(unsigned)t;
+  return 16384.f / (16384.f - t14);
+}
+
 template <typename T>
 static void run_sm_fwd(void* x, void* out, const void* mask, const void* bias, long long rows, int K,
                        long long mask_div, long long bias_rows, float p, unsigned long long seed,
@@ -353,7 +387,7 @@ static void run_sm_fwd(void* x, void* out, const void* mask, const void* bias, l
                      reinterpret_cast<uintptr_t>(logits)) & 15) == 0;
   g.mask_div = mask_div > 0 ? mask_div : 1;
   g.bias_rows = bias_rows > 0 ? bias_rows : 1;
-  const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const float keep_scale = keep_scale_for(p);
   if (vec) {
     const int rows_per_cta = kSmThreads / g.tpr;
     long long need = (rows + rows_per_cta - 1) / rows_per_cta;
@@ -380,7 +414,7 @@ static void run_sm_bwd(const void* dy, void* dx, const void* probs, long long ro
                      reinterpret_cast<uintptr_t>(addend)) & 15) == 0;
   g.mask_div = 1;
   g.bias_rows = 1;
-  const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const float keep_scale = keep_scale_for(p);
   if (vec) {
     const int rows_per_cta = kSmThreads / g.tpr;
     long long need = (rows + rows_per_cta - 1) / rows_per_cta;

@@ -285,6 +285,29 @@ UB_DEVICE uint32_t dropout_keep8(uint64_t seed, uint64_t offset, uint64_t idx8, 
   return m;
 }
 
+// 14-bit variant of dropout_keep8 (keep iff (u16 & 0x3fff) >= thresh14), in two forms that agree bit for bit:
+// an 8-bit keep mask for scalar code, and four AND-masks (0xffff per kept 16-bit lane, one word per element
+// pair - one HSET2 each) that are applied straight to packed fp16 / bf16 data.
+UB_DEVICE uint32_t dropout_keep8_14(uint64_t seed, uint64_t offset, uint64_t idx8, uint32_t thresh14) {
+  const Philox4 r = philox4x32<7>(seed, offset, idx8);
+  uint32_t m = 0;
+  const uint32_t ws[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m |= ((ws[i] & 0x3fffu) >= thresh14 ? 1u : 0u) << (2 * i);
+    m |= (((ws[i] >> 16) & 0x3fffu) >= thresh14 ? 1u : 0u) << (2 * i + 1);
+  }
+  return m;
+}
+UB_DEVICE void dropout_lane_masks8(uint64_t seed, uint64_t offset, uint64_t idx8, uint32_t thresh14, uint32_t (&m)[4]) {
+  const Philox4 r = philox4x32<7>(seed, offset, idx8);
+  const uint32_t t14x2 = thresh14 | (thresh14 << 16);
+  m[0] = keep_mask2(r.x, t14x2);
+  m[1] = keep_mask2(r.y, t14x2);
+  m[2] = keep_mask2(r.z, t14x2);
+  m[3] = keep_mask2(r.w, t14x2);
+}
+
 UB_DEVICE uint32_t dropout_thresh16(float p) {
   float t = p * 65536.f + 0.5f;
   return t >= 65535.f ? 65535u : (uint32_t)t;
