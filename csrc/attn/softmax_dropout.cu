@@ -367,6 +367,15 @@ static bool make_sm_geom(SmGeom& g, long long rows, int K, int epv, int& vpt) {
     default: break;                                            \
   }
 
+// The kernels are grid-stride loops over rows: launch exactly as many CTAs as fit on the machine at once.  (A fixed
+// "8 per SM" left the register-limited kernels with 1.6 waves: the second wave ran on 60 % of the SMs.)
+template <typename Kernel>
+static int resident_blocks(Kernel kernel) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSmThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  return per_sm * sm_count2();
+}
+
 // 1 / P(keep) for the 14-bit threshold the kernels compare against (mirrors dropout_thresh14)
 static float keep_scale_for(float p) {
   if (!(p > 0.f)) return 1.f;
@@ -390,11 +399,13 @@ static void run_sm_fwd(void* x, void* out, const void* mask, const void* bias, l
   const float keep_scale = keep_scale_for(p);
   if (vec) {
     const int rows_per_cta = kSmThreads / g.tpr;
-    long long need = (rows + rows_per_cta - 1) / rows_per_cta;
-    const long long cap = (long long)sm_count2() * 8;
-    const int grid = (int)(need < cap ? need : cap);
-    UB_SM_VPT(vpt, (softmax_dropout_fwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>(
-                       (T*)x, (T*)out, (const T*)mask, (const T*)bias, g, p, keep_scale, seed, offset, (T*)logits, lse)));
+    const long long need = (rows + rows_per_cta - 1) / rows_per_cta;
+    UB_SM_VPT(vpt, {
+      static const int resident = resident_blocks(softmax_dropout_fwd_kernel<T, VPT>);
+      const int grid = (int)(need < resident ? need : resident);
+      softmax_dropout_fwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>(
+          (T*)x, (T*)out, (const T*)mask, (const T*)bias, g, p, keep_scale, seed, offset, (T*)logits, lse);
+    });
   } else {
     long long need = (rows + 7) / 8;
     const long long cap = (long long)sm_count2() * 8;
@@ -417,11 +428,13 @@ static void run_sm_bwd(const void* dy, void* dx, const void* probs, long long ro
   const float keep_scale = keep_scale_for(p);
   if (vec) {
     const int rows_per_cta = kSmThreads / g.tpr;
-    long long need = (rows + rows_per_cta - 1) / rows_per_cta;
-    const long long cap = (long long)sm_count2() * 8;
-    const int grid = (int)(need < cap ? need : cap);
-    UB_SM_VPT(vpt, (softmax_dropout_bwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>(
-                       (const T*)dy, (T*)dx, (const T*)probs, g, p, keep_scale, seed, offset, lse, (const T*)addend)));
+    const long long need = (rows + rows_per_cta - 1) / rows_per_cta;
+    UB_SM_VPT(vpt, {
+      static const int resident = resident_blocks(softmax_dropout_bwd_kernel<T, VPT>);
+      const int grid = (int)(need < resident ? need : resident);
+      softmax_dropout_bwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>(
+          (const T*)dy, (T*)dx, (const T*)probs, g, p, keep_scale, seed, offset, lse, (const T*)addend);
+    });
   } else {
     long long need = (rows + 7) / 8;
     const long long cap = (long long)sm_count2() * 8;
