@@ -7,8 +7,10 @@ SURVEY.md Appendix A) so existing launch scripts work unchanged. The flag tables
 declarative: ``(names, kwargs)`` rows consumed by ``_add_rows``.
 
 B200 additions (all optional, defaults preserve reference behaviour):
-``--ddp-backend b200`` (symmetric-memory fused reduce+optimizer engine, falls back to c10d when
-NVLink peer memory is unavailable) and ``--pin-memory`` / ``--cuda-graph`` data/step options.
+``--ddp-backend b200`` (gradient all-reduce kernels over NVLink symmetric memory, bucketed and overlapped with
+backward, gradient norm accumulated in the same pass; falls back to c10d when peer memory is unavailable),
+``--pin-memory`` (pinned batches + non-blocking H2D) and ``--deferred-overflow-check`` (fp16: the overflow
+decision stays on the device, no host read between backward and the optimizer).
 """
 import argparse
 from typing import Callable, List, Optional
@@ -120,7 +122,7 @@ def _distributed_rows():
         _flag("--distributed-no-spawn", action="store_true",
               help="do not spawn multiple processes even if multiple GPUs are visible"),
         _flag("--ddp-backend", default="c10d", type=str, choices=["c10d", "apex", "no_c10d", "legacy_ddp", "b200"],
-              help="DistributedDataParallel backend (b200 = fused symmetric-memory reduce+optimizer)"),
+              help="DistributedDataParallel backend (b200 = all-reduce kernels over NVLink symmetric memory)"),
         _flag("--bucket-cap-mb", default=25, type=int, metavar="MB", help="bucket size for reduction"),
         _flag("--fix-batches-to-gpus", action="store_true",
               help="don't shuffle batches between GPUs; this reduces overall randomness"),
