@@ -96,6 +96,8 @@ void launch_bias_gelu_fwd(const void* x, const void* bias, void* y, long long ro
                           cudaStream_t stream);
 // dbias (nullable) = column sums of dx; part = float[bias_gelu_parts(rows, cols) * cols] scratch
 int bias_gelu_parts(long long rows, int cols);
+// out[cols] (16-bit) = column sums of x[rows, cols] (cols % 8 == 0), fp32 accumulation; same scratch size
+void launch_column_sum(const void* x, void* out, float* part, long long rows, int cols, int dtype, cudaStream_t stream);
 void launch_bias_gelu_bwd(const void* dy, const void* x, const void* bias, void* dx, void* dbias, float* part,
                           long long rows, int cols, int dtype, cudaStream_t stream);
 // y = LN(residual + dropout(x + bias)); summed = residual + dropout(x + bias) (saved for backward)

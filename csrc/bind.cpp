@@ -407,6 +407,22 @@ std::tuple<Tensor, OptTensor> bias_gelu_bwd(const Tensor& dy, const Tensor& x, c
   return {dx, dbias};
 }
 
+// column sums over all leading dims: x [..., cols] -> [cols] (bias gradient of a Linear layer)
+Tensor column_sum(const Tensor& x) {
+  check_cuda_contig(x, "x");
+  TORCH_CHECK(x.scalar_type() == at::kHalf || x.scalar_type() == at::kBFloat16, "column_sum supports fp16 / bf16");
+  const int cols = (int)x.size(-1);
+  TORCH_CHECK(cols % 8 == 0 && (reinterpret_cast<uintptr_t>(x.data_ptr()) & 15) == 0, "column_sum needs 16-byte rows");
+  const long long rows = x.numel() / cols;
+  TORCH_CHECK(rows < (1ll << 31), "too many rows");
+  const c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = torch::empty({cols}, x.options());
+  Tensor part = torch::empty({ub::bias_gelu_parts(rows, cols), cols}, x.options().dtype(at::kFloat));
+  ub::launch_column_sum(x.data_ptr(), out.data_ptr(), part.data_ptr<float>(), rows, cols, dtype_tag(x), cur_stream());
+  check_launch("column_sum");
+  return out;
+}
+
 std::tuple<Tensor, Tensor, Tensor, Tensor, int64_t, int64_t> bias_dropout_add_ln_fwd(
     const Tensor& x, const OptTensor& bias, const Tensor& residual, const Tensor& gamma, const Tensor& beta, double p,
     double eps) {
@@ -685,6 +701,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("softmax_dropout_logits_bwd", &softmax_dropout_logits_bwd);
   m.def("bias_gelu_fwd", &bias_gelu_fwd);
   m.def("bias_gelu_bwd", &bias_gelu_bwd);
+  m.def("column_sum", &column_sum);
   m.def("bias_dropout_add_ln_fwd", &bias_dropout_add_ln_fwd);
   m.def("bias_dropout_add_ln_bwd", &bias_dropout_add_ln_bwd);
   m.def("softmax_xent_fwd", &softmax_xent_fwd);

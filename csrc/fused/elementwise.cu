@@ -167,6 +167,54 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
   }
 }
 
+// Column sums of a [rows, cols] 16-bit matrix (bias gradient of a Linear layer: ATen runs a generic reduce at
+// ~2 TB/s for these shapes).  Same geometry as bias_gelu_kernel: a thread owns one 16-byte column vector, two row
+// lanes per CTA, kGeluUnroll rows in flight; fp32 partial rows, finished by colsum_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) column_sum_kernel(const T* __restrict__ x, float* __restrict__ part, int rows,
+                                                           int nvec) {
+  constexpr int EPV = 8;
+  __shared__ float red[kGeluColsPerCta][EPV + 1];
+  const int c = threadIdx.x & (kGeluColsPerCta - 1);
+  const int cv = blockIdx.x * kGeluColsPerCta + c;
+  const int rl = threadIdx.x / kGeluColsPerCta;
+  const bool col_ok = cv < nvec;
+  const int cols = nvec * EPV;
+  float acc[EPV];
+#pragma unroll
+  for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
+  const int row_step = gridDim.y * 2;
+  if (col_ok) {
+    for (int r0 = blockIdx.y * 2 + rl; r0 < rows; r0 += row_step * kGeluUnroll) {
+      Vec16 xv[kGeluUnroll];
+#pragma unroll
+      for (int u = 0; u < kGeluUnroll; ++u) {
+        const int r = r0 + u * row_step;
+        if (r < rows) xv[u] = ld_global_nc_v4(x + (size_t)r * cols + (size_t)cv * EPV);
+      }
+#pragma unroll
+      for (int u = 0; u < kGeluUnroll; ++u) {
+        if (r0 + u * row_step < rows) {
+          float xs[EPV];
+          unpack<T>(xv[u], xs);
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) acc[e] += xs[e];
+        }
+      }
+    }
+  }
+  if (rl == 1) {
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) red[c][e] = acc[e];
+  }
+  __syncthreads();
+  if (rl == 0 && col_ok) {
+    float* dst = part + (size_t)blockIdx.y * cols + (size_t)cv * EPV;
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) dst[e] = acc[e] + red[c][e];
+  }
+}
+
 int bias_gelu_parts(long long rows, int cols) {
   const int col_blocks = (cols / 8 + kGeluColsPerCta - 1) / kGeluColsPerCta;
   long long slices = ((long long)sm_count3() * 6 + col_blocks - 1) / col_blocks;
@@ -185,6 +233,21 @@ static void run_bias_gelu_t(const void* dy, const void* x, const void* bias, voi
   bias_gelu_kernel<T, kBwd><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, (const T*)bias, (T*)out,
                                                       want ? part : nullptr, (int)rows, nvec);
   if (want) colsum_kernel<T><<<(cols + 31) / 32, 1024, 0, stream>>>(part, slices, cols, (T*)dbias);
+}
+
+// out[cols] = column sums of x[rows, cols]; part = float[bias_gelu_parts(rows, cols) * cols] scratch
+void launch_column_sum(const void* x, void* out, float* part, long long rows, int cols, int dtype, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return;
+  const int nvec = cols / 8;
+  const int slices = bias_gelu_parts(rows, cols);
+  dim3 grid((nvec + kGeluColsPerCta - 1) / kGeluColsPerCta, slices);
+  if (dtype == kF16) {
+    column_sum_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)x, part, (int)rows, nvec);
+    colsum_kernel<__half><<<(cols + 31) / 32, 1024, 0, stream>>>(part, slices, cols, (__half*)out);
+  } else {
+    column_sum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, part, (int)rows, nvec);
+    colsum_kernel<__nv_bfloat16><<<(cols + 31) / 32, 1024, 0, stream>>>(part, slices, cols, (__nv_bfloat16*)out);
+  }
 }
 
 void launch_bias_gelu_fwd(const void* x, const void* bias, void* y, long long rows, int cols, int dtype,

@@ -409,6 +409,28 @@ def test_bias_gelu(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("rows,din,dout", [(16384, 768, 2304), (4001, 512, 512), (37, 64, 256)])
+def test_linear_with_column_sum_bias_grad(dtype, rows, din, dout):
+    ops = _ops()
+    torch.manual_seed(14)
+    x = (torch.randn(rows, din, device="cuda") * 0.5).to(dtype).requires_grad_(True)
+    w = (torch.randn(dout, din, device="cuda") * 0.05).to(dtype).requires_grad_(True)
+    b = torch.randn(dout, device="cuda").to(dtype).requires_grad_(True)
+    dy = torch.randn(rows, dout, device="cuda").to(dtype)
+    y = ops.linear(x.view(1, rows, din), w, b)
+    assert y.shape == (1, rows, dout)
+    y.backward(dy.view(1, rows, dout))
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    yr = F.linear(xr, wr, br)
+    yr.backward(dy.float())
+    assert maxdiff(y[0], yr) < TOL[dtype] * 8
+    # the bias gradient is accumulated in fp32 and rounded once: error relative to its magnitude (~sqrt(rows))
+    assert maxdiff(b.grad, br.grad) <= TOL[dtype] * max(1.0, br.grad.abs().max().item())
+    assert maxdiff(x.grad, xr.grad) < TOL[dtype] * 8
+    assert maxdiff(w.grad, wr.grad) <= TOL[dtype] * 2 * max(1.0, wr.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("p", [0.0, 0.1])
 def test_bias_dropout_add_layer_norm(dtype, p):
     ops = _ops()

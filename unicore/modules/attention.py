@@ -83,7 +83,8 @@ class SelfMultiheadAttention(nn.Module):
             raise ValueError("query dim {} != embed_dim {}".format(embed_dim, self.embed_dim))
         if key_padding_mask is not None and key_padding_mask.dim() == 0:
             key_padding_mask = None
-        qkv = self.in_proj(query).view(bsz, tgt_len, 3, self.num_heads, self.head_dim)
+        qkv = ops.linear(query, self.in_proj.weight, self.in_proj.bias)
+        qkv = qkv.view(bsz, tgt_len, 3, self.num_heads, self.head_dim)
         q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]  # strided views [B, L, H, D]
         bias4 = _bias_as_4d(attn_bias, bsz, self.num_heads, tgt_len, tgt_len)
         if not return_attn and ops.fused_attention_supported(q, k, v, bias4, key_padding_mask):

@@ -115,7 +115,7 @@ class _BlockMixin:
                 self.dropout, norm.eps, self.training,
             )
             return out, extra
-        out = residual + F.dropout(proj(o), p=self.dropout, training=self.training)
+        out = residual + F.dropout(ops.linear(o, proj.weight, proj.bias), p=self.dropout, training=self.training)
         if self.post_ln:
             out = norm(out)
         return out, extra
@@ -132,7 +132,7 @@ class _BlockMixin:
                     self.final_layer_norm.weight, self.final_layer_norm.bias,
                     self.dropout, self.final_layer_norm.eps, self.training,
                 )
-            h = self.fc2(h)
+            h = ops.linear(h, self.fc2.weight, self.fc2.bias)
             return residual + F.dropout(h, p=self.dropout, training=self.training)
         h = x if self.post_ln else self.final_layer_norm(x)
         h = self.activation_fn(self.fc1(h))

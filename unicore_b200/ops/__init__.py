@@ -11,6 +11,7 @@ from .fused_ops import (  # noqa: F401
     bias_gelu,
     gaussian_basis,
     gaussian_basis_reference,
+    linear,
     softmax_cross_entropy,
     vocab_projection,
 )

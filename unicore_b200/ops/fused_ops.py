@@ -45,6 +45,48 @@ def bias_gelu(x: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# Linear with a fast bias gradient
+# ------------------------------------------------------------------------------------------------
+class _LinearFn(torch.autograd.Function):
+    """``x @ W^T + b`` - cuBLAS GEMMs both ways; the bias gradient is our column-sum kernel (fp32 accumulation,
+    one pass at copy bandwidth) instead of ATen's generic reduction."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return F.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dy2 = dy.view(-1, dy.shape[-1])
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = dy.matmul(weight)
+        if ctx.needs_input_grad[1]:
+            dw = dy2.t().mm(x.reshape(-1, x.shape[-1]))
+        if ctx.needs_input_grad[2]:
+            db = native().column_sum(dy2) if dy2.data_ptr() % 16 == 0 else dy2.sum(dim=0)
+        return dx, dw, db
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``F.linear`` whose backward computes the bias gradient with ``column_sum`` (``csrc/fused/elementwise.cu``)."""
+    if (
+        bias is not None
+        and use_native(x, weight, bias)
+        and x.dtype in (torch.float16, torch.bfloat16)
+        and weight.dtype == x.dtype and bias.dtype == x.dtype
+        and weight.shape[0] % 8 == 0 and weight.shape[0] >= 256  # narrow outputs leave the column kernel's CTAs idle
+        and torch.is_grad_enabled()
+        and (x.requires_grad or weight.requires_grad or bias.requires_grad)
+    ):
+        return _LinearFn.apply(x, weight, bias)
+    return F.linear(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------
 # bias + dropout + residual add (+ LayerNorm)
 # ------------------------------------------------------------------------------------------------
 class _BiasDropoutAddLNFn(torch.autograd.Function):
