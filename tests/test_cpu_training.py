@@ -187,3 +187,45 @@ def test_bert_example_on_text_corpus(tmp_path):
     assert run.returncode == 0, run.stdout[-4000:]
     assert "valid" in run.stdout and len(losses_of(run.stdout)) >= 5
     assert os.path.isfile(os.path.join(save, "checkpoint_last.pt"))
+
+
+def test_checkpoint_retention_finetune_and_ema_flags(tmp_path):
+    """Retention policies, epoch checkpoints, `--finetune-from-model`, `--load-from-ema`, `--validate-with-ema`,
+    reset flags and the stop conditions (reference `checkpoint_utils.py:83-215`, `unicore_cli/train.py:251-330`)."""
+    save = str(tmp_path / "ck")
+    common = ["--synthetic-num-samples", "32", "--ema-decay", "0.9", "--validate-with-ema"]  # 4 updates per epoch
+    log = run_cli(common + ["--save-dir", save, "--tmp-save-dir", str(tmp_path / "tmp"), "--max-epoch", "3",
+                            "--save-interval-updates", "2", "--keep-interval-updates", "2", "--keep-last-epochs", "1",
+                            "--keep-best-checkpoints", "1", "--best-checkpoint-metric", "loss"])
+    assert len(losses_of(log)) == 12 and "valid" in log
+    files = sorted(os.listdir(save))
+    interval = [f for f in files if f.startswith("checkpoint_") and f.count("_") == 2]  # checkpoint_<epoch>_<updates>.pt
+    epochs = [f for f in files if f.startswith("checkpoint") and f[len("checkpoint")].isdigit()]
+    best = [f for f in files if f.startswith("checkpoint.best_")]
+    assert len(interval) == 2 and len(epochs) == 1 and epochs[0] == "checkpoint3.pt" and len(best) == 1, files
+    assert {"checkpoint_best.pt", "checkpoint_last.pt"} <= set(files)
+    last = torch.load(os.path.join(save, "checkpoint_last.pt"), map_location="cpu", weights_only=False)
+    assert last["optimizer_history"][-1]["num_updates"] == 12 and last["extra_state"]["train_iterator"]["epoch"] == 4
+
+    # fine-tune from the model weights only: fresh optimizer, meters, iterator and update counter
+    save_ft = str(tmp_path / "ft")
+    log_ft = run_cli(common + ["--save-dir", save_ft, "--tmp-save-dir", save_ft, "--max-update", "2",
+                               "--finetune-from-model", os.path.join(save, "checkpoint_last.pt"), "--disable-validation"])
+    assert "finetune" in log_ft.lower() or "loaded checkpoint" in log_ft.lower()
+    ft = torch.load(os.path.join(save_ft, "checkpoint_last.pt"), map_location="cpu", weights_only=False)
+    assert ft["optimizer_history"][-1]["num_updates"] == 2
+    assert losses_of(log_ft)[0] < losses_of(log)[0]  # starts from trained weights, not from scratch
+
+    # restore the EMA weights into the model, and drop the optimizer / scheduler / meter state on resume
+    save_ema = str(tmp_path / "ema")
+    log_ema = run_cli(common + ["--save-dir", save_ema, "--tmp-save-dir", save_ema, "--max-update", "3",
+                                "--restore-file", os.path.join(save, "checkpoint_last.pt"), "--load-from-ema",
+                                "--reset-optimizer", "--reset-lr-scheduler", "--reset-meters", "--reset-dataloader",
+                                "--disable-validation"])
+    assert "loading ema state to model" in log_ema and len(losses_of(log_ema)) == 3  # counters restart with the optimizer
+    assert losses_of(log_ema)[0] < losses_of(log)[0]
+
+    # wall-clock stop condition and "no checkpoints at all"
+    log_stop = run_cli(common + ["--save-dir", str(tmp_path / "none"), "--no-save", "--disable-validation",
+                                 "--max-update", "1000", "--stop-time-hours", "0.0000001"])
+    assert len(losses_of(log_stop)) < 50 and not os.path.exists(str(tmp_path / "none" / "checkpoint_last.pt"))
