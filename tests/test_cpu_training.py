@@ -229,3 +229,17 @@ def test_checkpoint_retention_finetune_and_ema_flags(tmp_path):
     log_stop = run_cli(common + ["--save-dir", str(tmp_path / "none"), "--no-save", "--disable-validation",
                                  "--max-update", "1000", "--stop-time-hours", "0.0000001"])
     assert len(losses_of(log_stop)) < 50 and not os.path.exists(str(tmp_path / "none" / "checkpoint_last.pt"))
+
+
+def test_fp16_overflow_skips_updates_and_lowers_the_scale(tmp_path):
+    """A loss scale far too large: the first steps overflow, are skipped (not counted as updates), and the dynamic
+    scaler backs off until training proceeds (reference `fp16_optimizer.py:262-283`, `trainer.py:700-760`)."""
+    save = str(tmp_path / "ck")
+    log = run_cli(["--save-dir", save, "--tmp-save-dir", save, "--disable-validation", "--max-update", "3", "--fp16",
+                   "--fp16-init-scale", str(2 ** 40), "--fp16-scale-window", "1000"])
+    assert "overflow" in log.lower()
+    assert len(losses_of(log)) >= 3
+    ck = torch.load(os.path.join(save, "checkpoint_last.pt"), map_location="cpu", weights_only=False)
+    assert ck["optimizer_history"][-1]["num_updates"] == 3
+    assert ck["last_optimizer_state"]["loss_scale"] < 2 ** 40
+    assert all(torch.isfinite(v).all() for v in ck["model"].values())
