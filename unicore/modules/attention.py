@@ -76,18 +76,14 @@ class SelfMultiheadAttention(nn.Module):
         self.in_proj = nn.Linear(embed_dim, embed_dim * 3, bias=bias)
         self.out_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
 
-    def attend(self, query, key_padding_mask=None, attn_bias=None, return_attn=False, qkv=None):
-        """Everything up to (not including) ``out_proj``: returns ``(o [B, L, E], logits, probs)``.
-
-        ``qkv`` (optional) is the packed in-projection of ``query`` when the caller has already computed it
-        (the encoder layer does, through ``ops.linear_fork``, to fold the residual gradient into that GEMM)."""
+    def attend(self, query, key_padding_mask=None, attn_bias=None, return_attn=False):
+        """Everything up to (not including) ``out_proj``: returns ``(o [B, L, E], logits, probs)``."""
         bsz, tgt_len, embed_dim = query.size()
         if embed_dim != self.embed_dim:
             raise ValueError("query dim {} != embed_dim {}".format(embed_dim, self.embed_dim))
         if key_padding_mask is not None and key_padding_mask.dim() == 0:
             key_padding_mask = None
-        if qkv is None:
-            qkv = ops.linear(query, self.in_proj.weight, self.in_proj.bias)
+        qkv = ops.linear(query, self.in_proj.weight, self.in_proj.bias)
         qkv = qkv.view(bsz, tgt_len, 3, self.num_heads, self.head_dim)
         q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]  # strided views [B, L, H, D]
         bias4 = _bias_as_4d(attn_bias, bsz, self.num_heads, tgt_len, tgt_len)

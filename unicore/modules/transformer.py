@@ -102,14 +102,7 @@ class _BlockMixin:
         h = attn_in if self.post_ln else norm(attn_in)
         extra = None
         if isinstance(attn_module, SelfMultiheadAttention):
-            qkv = None
-            if self.post_ln and residual is attn_in and self._fused_ok(h):
-                # the block input feeds the in-projection AND the skip connection: fork it so that the skip
-                # gradient is accumulated by the in-projection's input-gradient GEMM
-                qkv, residual = ops.linear_fork(h, attn_module.in_proj.weight, attn_module.in_proj.bias)
-            o, logits, probs = attn_module.attend(
-                h, kw.get("key_padding_mask"), kw.get("attn_bias"), return_attn, qkv=qkv
-            )
+            o, logits, probs = attn_module.attend(h, kw.get("key_padding_mask"), kw.get("attn_bias"), return_attn)
             if return_attn:
                 extra = (logits, probs)
         else:
@@ -130,11 +123,8 @@ class _BlockMixin:
     def _ffn_residual(self, x):
         residual = x
         if self._fused_ok(x):
-            if self.post_ln:
-                h, residual = ops.linear_fork(x, self.fc1.weight)  # skip gradient folded into fc1's dgrad GEMM
-            else:
-                h = _linear_no_bias(self.fc1, self.final_layer_norm(x))
-            h = ops.bias_gelu(h, self.fc1.bias)
+            h = x if self.post_ln else self.final_layer_norm(x)
+            h = ops.bias_gelu(_linear_no_bias(self.fc1, h), self.fc1.bias)
             h = F.dropout(h, p=self.activation_dropout, training=self.training)
             if self.post_ln:
                 return ops.bias_dropout_add_layer_norm(

@@ -12,7 +12,6 @@ from .fused_ops import (  # noqa: F401
     gaussian_basis,
     gaussian_basis_reference,
     linear,
-    linear_fork,
     softmax_cross_entropy,
     vocab_projection,
 )

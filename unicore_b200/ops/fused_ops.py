@@ -86,45 +86,6 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return F.linear(x, weight, bias)
 
 
-class _LinearForkFn(torch.autograd.Function):
-    """``(x @ W^T + b, x)``: the start of a residual block, where ``x`` feeds both the sublayer's first GEMM and the
-    skip connection.  Autograd would compute the GEMM's input gradient and then add the skip gradient with a
-    separate element-wise kernel (three passes over the activation); here the skip gradient is the ``beta = 1``
-    operand of that GEMM (``addmm``), so the sum is formed in the GEMM epilogue."""
-
-    @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
-        ctx.has_bias = bias is not None
-        return F.linear(x, weight, bias), x
-
-    @staticmethod
-    def backward(ctx, dy, dskip):
-        x, weight = ctx.saved_tensors
-        dy2 = dy.contiguous().view(-1, dy.shape[-1])
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            if dskip is None:
-                dx = dy2.mm(weight).view(x.shape)
-            else:
-                dx = torch.addmm(dskip.contiguous().view(-1, x.shape[-1]), dy2, weight).view(x.shape)
-        if ctx.needs_input_grad[1]:
-            dw = dy2.t().mm(x.reshape(-1, x.shape[-1]))
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            fast = use_native(dy2) and dy2.dtype in (torch.float16, torch.bfloat16) and dy2.shape[-1] % 8 == 0 \
-                and dy2.shape[-1] >= 256 and dy2.data_ptr() % 16 == 0
-            db = native().column_sum(dy2) if fast else dy2.sum(dim=0)
-        return dx, dw, db
-
-
-def linear_fork(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None):
-    """Returns ``(F.linear(x, weight, bias), skip)`` where ``skip`` aliases ``x``; use ``skip`` for the residual
-    connection so that its gradient is accumulated inside the input-gradient GEMM (see ``_LinearForkFn``)."""
-    if torch.is_grad_enabled() and x.requires_grad and x.dim() >= 2:
-        return _LinearForkFn.apply(x, weight, bias)
-    return F.linear(x, weight, bias), x
-
-
 # ------------------------------------------------------------------------------------------------
 # bias + dropout + residual add (+ LayerNorm)
 # ------------------------------------------------------------------------------------------------
