@@ -161,3 +161,58 @@ def test_self_attention_module_matches_materialised_path():
     o, logits, probs = attn(x, key_padding_mask=mask, attn_bias=bias, return_attn=True)
     assert (fused.float() - o.float()).abs().max().item() < 2e-2
     assert probs.shape == (24, 128, 128)
+
+
+@pytest.mark.parametrize("post_ln", [False])
+def test_encoder_layer_matches_fp32_formulation(post_ln):
+    """Whole pre-LN layer (tcgen05 attention, bias-GELU, column-sum bias gradients) against the plain fp32
+    formulation of the same layer, forward and all gradients (dropout off)."""
+    import copy
+
+    import torch.nn.functional as F
+
+    from unicore.modules import TransformerEncoderLayer
+
+    torch.manual_seed(21)
+    E, H, L, B = 256, 4, 128, 3
+    layer = TransformerEncoderLayer(embed_dim=E, ffn_embed_dim=4 * E, attention_heads=H, dropout=0.0,
+                                    attention_dropout=0.0, activation_dropout=0.0, post_ln=post_ln).cuda()
+    ref = copy.deepcopy(layer).float()
+    layer = layer.half().train()
+    x = torch.randn(B, L, E, device="cuda").half().requires_grad_(True)
+    bias = (torch.randn(1, H, L, L, device="cuda") * 0.5).half()
+    pad = torch.zeros(B, L, dtype=torch.bool, device="cuda")
+    pad[2, 100:] = True
+    y = layer(x, attn_bias=bias, padding_mask=pad)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+
+    def plain(m, x):
+        def attn(h):
+            qkv = F.linear(h, m.self_attn.in_proj.weight, m.self_attn.in_proj.bias).view(B, L, 3, H, E // H)
+            q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
+            s = q @ k.transpose(-1, -2) * m.self_attn.scaling + bias.float()
+            s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+            o = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, L, E)
+            return F.linear(o, m.self_attn.out_proj.weight, m.self_attn.out_proj.bias)
+
+        def ffn(h):
+            return F.linear(F.gelu(F.linear(h, m.fc1.weight, m.fc1.bias)), m.fc2.weight, m.fc2.bias)
+
+        ln1 = lambda t: F.layer_norm(t, (E,), m.self_attn_layer_norm.weight, m.self_attn_layer_norm.bias)  # noqa: E731
+        ln2 = lambda t: F.layer_norm(t, (E,), m.final_layer_norm.weight, m.final_layer_norm.bias)  # noqa: E731
+        if post_ln:
+            x = ln1(x + attn(x))
+            return ln2(x + ffn(x))
+        x = x + attn(ln1(x))
+        return x + ffn(ln2(x))
+
+    xr = x.detach().float().requires_grad_(True)
+    yr = plain(ref, xr)
+    yr.backward(dy.float())
+    assert (y.float() - yr).abs().max().item() < 3e-2
+    assert (x.grad.float() - xr.grad).abs().max().item() < 3e-2 * max(1.0, xr.grad.abs().max().item())
+    for (name, p), (_, pr) in zip(layer.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, name
+        tol = 4e-2 * max(1.0, pr.grad.abs().max().item())
+        assert (p.grad.float() - pr.grad).abs().max().item() < tol, name
