@@ -22,7 +22,6 @@ import statistics
 import subprocess
 import sys
 import threading
-import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 

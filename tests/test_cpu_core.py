@@ -1,7 +1,6 @@
 """CPU tests of the Python layers: registries, options, schedulers, loss scaler, flat arenas,
 metrics, data pipeline, EMA, modules (fallback paths)."""
 import argparse
-import io
 import math
 import os
 import sys

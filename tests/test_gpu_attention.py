@@ -1,5 +1,4 @@
 """tcgen05 fused attention (forward + backward) against an fp32 PyTorch reference."""
-import math
 
 import pytest
 import torch

@@ -13,12 +13,10 @@ batch on a side CUDA stream while the current step computes.
 import itertools
 import logging
 import math
-import operator
 import os
 import queue
 import threading
 import time
-from typing import Callable, Iterable, Optional
 
 import numpy as np
 import torch

@@ -26,7 +26,6 @@ import socket
 import struct
 import subprocess
 import warnings
-from argparse import Namespace
 from collections import OrderedDict
 from dataclasses import dataclass
 from datetime import timedelta

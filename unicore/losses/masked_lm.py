@@ -8,9 +8,6 @@ B200 path: the fp32 log-softmax + NLL over the ``[n_masked, vocab]`` logits is o
 """
 import math
 
-import torch
-import torch.nn.functional as F
-
 from unicore import metrics, ops, utils
 from unicore.losses import UnicoreLoss, register_loss
 

@@ -7,7 +7,6 @@ from typing import Any, Dict, List
 
 from torch.nn.modules.loss import _Loss
 
-from unicore import metrics
 
 
 class UnicoreLoss(_Loss):

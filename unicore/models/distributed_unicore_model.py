@@ -12,7 +12,6 @@ All engines are wrapped in ``ModuleProxyWrapper``.  Parity: reference
 """
 import logging
 
-import torch
 import torch.nn as nn
 
 from unicore.distributed import LegacyDistributedDataParallel, ModuleProxyWrapper

@@ -20,8 +20,8 @@ no fp32 gradient buffer exists at all in that mode.  Bitwise result is identical
 path because fp16/bf16 -> fp32 conversion is exact and all math is fp32.
 """
 import logging
-from collections import OrderedDict, defaultdict
-from typing import Callable, Dict, List, Optional
+from collections import OrderedDict
+from typing import Callable, Optional
 
 import torch
 

@@ -17,7 +17,6 @@ from typing import Callable, List, Optional
 
 import torch
 
-from unicore import utils
 from unicore.utils import csv_str_list, eval_bool, eval_str_dict, eval_str_list, import_user_module  # noqa: F401
 
 

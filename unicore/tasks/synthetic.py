@@ -12,7 +12,7 @@ import os
 import numpy as np
 import torch
 
-from unicore.data import Dictionary, UnicoreDataset, data_utils
+from unicore.data import Dictionary, UnicoreDataset
 from unicore.tasks import UnicoreTask, register_task
 
 logger = logging.getLogger(__name__)

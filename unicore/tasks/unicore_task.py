@@ -13,7 +13,7 @@ from typing import Any, Callable, Dict, List
 
 import torch
 
-from unicore import metrics, utils
+from unicore import metrics
 from unicore.data import UnicoreDataset, data_utils, iterators
 
 logger = logging.getLogger(__name__)

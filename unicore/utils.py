@@ -20,9 +20,8 @@ import os
 import sys
 import weakref
 from functools import partial
-from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
+from typing import Any, Callable, Dict, List, Sequence
 
-import numpy as np
 import torch
 import torch.nn.functional as F
 import torch.utils.checkpoint

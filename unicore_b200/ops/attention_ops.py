@@ -11,7 +11,6 @@ Backward recomputes P from the saved log-sum-exp (flash-attention style) and reg
 dropout mask from the same Philox counters.
 """
 import math
-from typing import Optional
 
 import torch
 import torch.nn.functional as F

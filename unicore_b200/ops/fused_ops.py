@@ -13,7 +13,6 @@ every one of them is HBM-bound, so they are merged into the minimum number of pa
   logits' dtype in place of the logits buffer.
 Kernels: ``csrc/fused/*.cu``.  PyTorch fallbacks are bit-for-bit the reference formulation.
 """
-import math
 from typing import Optional
 
 import torch

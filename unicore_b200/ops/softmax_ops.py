@@ -13,7 +13,6 @@ length (dropout included for K > 1024, which the reference cannot fuse), current
 and **no stored dropout mask**: keep/drop decisions are a pure function of
 ``(philox seed, offset, element index)`` and are regenerated in backward.
 """
-from typing import Optional
 
 import torch
 import torch.nn.functional as F

@@ -15,7 +15,6 @@ import logging
 import math
 import os
 import sys
-import time
 from multiprocessing.pool import ThreadPool
 from typing import Callable, Dict, List, Optional, Tuple
 
