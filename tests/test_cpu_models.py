@@ -225,3 +225,33 @@ def test_progress_bars_emit_stats(fmt, caplog):
         assert rec and json.loads(rec[-1])["train_loss"] in ("0.25", 0.25)
     if fmt == "simple":
         assert any("loss" in r.getMessage() for r in caplog.records)
+
+
+def test_trainer_recovers_from_oom_in_forward_backward():
+    """Single process: an out-of-memory error inside fwd/bwd skips that step (gradients cleared, no update counted)
+    and training continues; any other RuntimeError propagates (reference `trainer.py:630-645,959-965`)."""
+    trainer, model, batches = _unimol_trainer()
+    real = trainer.task.train_step
+    calls = {"n": 0}
+
+    def flaky(**kw):
+        calls["n"] += 1
+        if calls["n"] == 2:
+            raise RuntimeError("CUDA out of memory. Tried to allocate 1.00 GiB")
+        return real(**kw)
+
+    trainer.task.train_step = flaky
+    assert trainer.train_step([batches[0]]) is not None
+    before = [p.detach().clone() for p in model.parameters()]
+    assert trainer.train_step([batches[1]]) is None  # the OOM step
+    assert trainer.get_num_updates() == 1
+    assert all(torch.equal(a, p.detach()) for a, p in zip(before, model.parameters()))
+    assert all(p.grad is None or not p.grad.abs().sum().item() for p in model.parameters())
+    assert trainer.train_step([batches[2]]) is not None and trainer.get_num_updates() == 2
+
+    def broken(**kw):
+        raise RuntimeError("shape mismatch")
+
+    trainer.task.train_step = broken
+    with pytest.raises(RuntimeError, match="shape mismatch"):
+        trainer.train_step([batches[0]])
