@@ -40,7 +40,6 @@ def apply_unimol_arch(args):
             setattr(args, k, v)
 
 
-@torch.jit.script
 def _gaussian(x, mean, std):
     a = (2 * 3.14159) ** 0.5
     return torch.exp(-0.5 * (((x - mean) / std) ** 2)) / (a * std)
