@@ -260,6 +260,92 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_nvls_kernel(CommPeers 
   block_barrier(peers, true);
 }
 
+// ---- sharded Adam + parameter all-gather ----------------------------------------------------------------------------
+UB_DEVICE void shard_adam_math(float& p, float& m, float& v, float g, const ShardAdam& a) {
+  m = a.beta1 * m + (1.f - a.beta1) * g;
+  v = a.beta2 * v + (1.f - a.beta2) * g * g;
+  p = p * a.decay_mul - a.step_size * (m / (sqrtf(v) + a.eps));
+}
+UB_DEVICE uint32_t shard_bf16_sr(float x, uint32_t rnd16) {
+  uint32_t bits = __float_as_uint(x);
+  if ((bits & 0x7f800000u) != 0x7f800000u) bits += rnd16;  // inf / nan stay as they are
+  return bits >> 16;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCommThreads) sharded_adam_kernel(CommPeers params, ShardAdam a) {
+  const float sdev = a.scale_dev ? __ldg(a.scale_dev) : 1.f;
+  const bool skip = a.scale_dev != nullptr && !(isfinite(sdev) && sdev != 0.f);
+  if (!skip) {
+    const float gmul = a.inv_scale / sdev;
+    const T* G = reinterpret_cast<const T*>(a.grad);
+    const bool sr = a.stochastic_rounding != 0 && sizeof(T) == 2;
+    const long long vend = a.lo + ((a.hi - a.lo) & ~7ll);
+    const long long stride = (long long)gridDim.x * kCommThreads * 8;
+    for (long long i = a.lo + ((long long)blockIdx.x * kCommThreads + threadIdx.x) * 8; i < vend; i += stride) {
+      float g[8], p[8], m[8], v[8];
+      unpack<T>(ld_global_nc_v4(G + i), g);
+      const Vec16 p0 = ld_global_v4(a.master + i), p1 = ld_global_v4(a.master + i + 4);
+      const Vec16 m0 = ld_global_v4(a.exp_avg + i), m1 = ld_global_v4(a.exp_avg + i + 4);
+      const Vec16 v0 = ld_global_v4(a.exp_avg_sq + i), v1 = ld_global_v4(a.exp_avg_sq + i + 4);
+      unpack<float>(p0, p);
+      unpack<float>(p1, p + 4);
+      unpack<float>(m0, m);
+      unpack<float>(m1, m + 4);
+      unpack<float>(v0, v);
+      unpack<float>(v1, v + 4);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) shard_adam_math(p[k], m[k], v[k], g[k] * gmul, a);
+      st_global_v4(a.master + i, pack<float>(p));
+      st_global_v4(a.master + i + 4, pack<float>(p + 4));
+      st_global_v4(a.exp_avg + i, pack<float>(m));
+      st_global_v4(a.exp_avg + i + 4, pack<float>(m + 4));
+      st_global_v4(a.exp_avg_sq + i, pack<float>(v));
+      st_global_v4(a.exp_avg_sq + i + 4, pack<float>(v + 4));
+      Vec16 o;
+      if (sr) {
+        const Philox4 r = philox4x32_10(a.seed, a.offset, (a.elem_base + (unsigned long long)i) >> 3);
+        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          o.w[k] = shard_bf16_sr(p[2 * k], rw[k] & 0xffffu) | (shard_bf16_sr(p[2 * k + 1], rw[k] >> 16) << 16);
+      } else {
+        o = pack<T>(p);
+      }
+      // the all-gather IS this store: one instruction through the switch, or one store per peer
+      if (params.multicast != nullptr) {
+        multimem_st(reinterpret_cast<T*>(params.multicast) + i, o);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+          if (r < params.world) st_global_v4(reinterpret_cast<T*>(params.buf[r]) + i, o);
+        }
+      }
+    }
+    // scalar tail of the last shard (group length not a multiple of 8): plain peer stores
+    if (blockIdx.x == 0) {
+      for (long long i = vend + threadIdx.x; i < a.hi; i += kCommThreads) {
+        float p = a.master[i], m = a.exp_avg[i], v = a.exp_avg_sq[i];
+        shard_adam_math(p, m, v, to_f32<T>(G[i]) * gmul, a);
+        a.master[i] = p;
+        a.exp_avg[i] = m;
+        a.exp_avg_sq[i] = v;
+        const T out = from_f32<T>(p);
+        for (int r = 0; r < params.world; ++r) reinterpret_cast<T*>(params.buf[r])[i] = out;
+      }
+    }
+  }
+  block_barrier(params, /*release_first=*/true);  // every shard has landed everywhere before anyone proceeds
+}
+
+void launch_sharded_adam(const CommPeers& params, const ShardAdam& a, int dtype, int blocks, cudaStream_t stream) {
+  if (blocks <= 0) blocks = 48;
+  if (blocks > kMaxCommBlocks - 1) blocks = kMaxCommBlocks - 1;
+  symm_handshake_kernel<<<1, 32, 0, stream>>>(params);  // nobody still reads the old parameters
+  if (dtype == kF16) sharded_adam_kernel<__half><<<blocks, kCommThreads, 0, stream>>>(params, a);
+  else if (dtype == kBF16) sharded_adam_kernel<__nv_bfloat16><<<blocks, kCommThreads, 0, stream>>>(params, a);
+}
+
 // ---- host --------------------------------------------------------------------------------------------------------------
 template <typename T>
 static void run_allreduce(const CommPeers& peers, long long begin_vec, long long end_vec, float scale, int algo,

@@ -28,4 +28,25 @@ int pick_allreduce_algo(long long bytes, int world, bool has_multicast);
 void launch_allreduce(const CommPeers& peers, long long byte_offset, long long bytes, int dtype, float scale, int algo,
                       int blocks, float* sq_acc, cudaStream_t stream);
 
+// ---- optimizer step fused with the parameter all-gather (experimental: UNICORE_B200_SHARD_OPTIMIZER=1) --------
+// Rank r owns elements [lo, hi) of a flat parameter group: it runs Adam on that shard of the fp32 master / moment
+// arrays (reading the already reduced 16-bit gradients of its local arena) and stores the new 16-bit parameters
+// into EVERY rank's parameter arena - one multimem.st per 16-byte vector through the NVLS alias when there is one,
+// peer stores otherwise.  `params` describes the symmetric PARAMETER arena.  A handshake ahead of the kernel keeps
+// a fast rank from overwriting parameters a slower rank's backward still reads; a flag barrier at the end makes
+// every shard visible everywhere before the next forward.
+struct ShardAdam {
+  float* master;            // fp32 master weights of the group (full length, indexed by absolute element)
+  float* exp_avg;
+  float* exp_avg_sq;
+  const void* grad;         // local, reduced 16-bit gradient arena of the group
+  long long lo, hi;         // this rank's shard (lo % 8 == 0)
+  float beta1, beta2, eps, step_size, decay_mul;
+  float inv_scale;          // gradients are multiplied by inv_scale / (*scale_dev if given)
+  const float* scale_dev;   // non-finite or zero => the update is skipped on every rank (overflow)
+  int stochastic_rounding;  // bf16 parameters only
+  unsigned long long seed, offset, elem_base;
+};
+void launch_sharded_adam(const CommPeers& params, const ShardAdam& a, int dtype, int blocks, cudaStream_t stream);
+
 }  // namespace ub

@@ -54,3 +54,17 @@ def test_b200_backend_trains_like_c10d():
         assert res["value"] > 0 and res["e2e"]["value"] > 0
         losses[backend] = res
     assert losses["b200"]["gpu_launches"] > 0
+
+
+@needs_two
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_sharded_optimizer_matches_replicated(precision):
+    """UNICORE_B200_SHARD_OPTIMIZER=1 (Adam on a 1/N shard + parameter all-gather in one kernel): parameters, fp32
+    master weights and Adam moments identical to the replicated fused Adam after a few updates."""
+    n = 2 if torch.cuda.device_count() < 4 else 4
+    log = _torchrun(n, [os.path.join(ROOT, "bench", "sharded_optimizer_check.py"), "--steps", "4",
+                        "--precision", precision])
+    line = [l for l in log.splitlines() if l.startswith('{"summary"')][-1]
+    res = json.loads(line)
+    assert res["sharded_active"] and not res["replicated_was_sharded"], res
+    assert res["max_abs_diff"] == 0.0, res

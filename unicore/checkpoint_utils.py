@@ -96,6 +96,8 @@ def save_checkpoint(args, trainer, epoch_itr, val_loss, ckp_copy_thread, do_save
 
     if args.no_save or not do_save:
         return
+    if hasattr(trainer, "consolidate_optimizer_state"):
+        trainer.consolidate_optimizer_state()  # every rank takes part; only the master writes below
     if not trainer.should_save_checkpoint_on_current_rank:
         return
 

@@ -91,12 +91,15 @@ def _slots(params):
 
 
 @torch.no_grad()
-def flatten_parameters(params, grad_alloc: Optional[Callable[[int, torch.dtype, torch.device], torch.Tensor]] = None):
+def flatten_parameters(params, grad_alloc: Optional[Callable[[int, torch.dtype, torch.device], torch.Tensor]] = None,
+                       param_alloc: Optional[Callable[[int, torch.dtype, torch.device], Optional[torch.Tensor]]] = None):
     """Re-point ``p.data`` / ``p.grad`` of every param into one flat buffer per dtype.
 
     ``grad_alloc(numel, dtype, device)`` lets a communication engine provide the gradient buffer
     (e.g. NVLink peer-mapped symmetric memory) so gradients are produced in place where the
-    reduction kernels read them - no staging copies.
+    reduction kernels read them - no staging copies.  ``param_alloc`` does the same for the flat
+    parameter buffer (it may return ``None`` to decline): the sharded optimizer step stores new
+    parameters straight into every rank's arena.
     Returns the flat ``nn.Parameter`` per dtype (with ``.grad`` = the flat grad buffer).
     """
     by_dtype, order, _ = flatten_orders(params)
@@ -105,7 +108,11 @@ def flatten_parameters(params, grad_alloc: Optional[Callable[[int, torch.dtype, 
         members = by_dtype[dtype]
         total = sum(pad_numel(p.data.numel()) for p in members)
         device = members[0].device
-        flat = torch.zeros(total, dtype=dtype, device=device)
+        flat = param_alloc(total, dtype, device) if param_alloc is not None else None
+        if flat is None:
+            flat = torch.zeros(total, dtype=dtype, device=device)
+        else:
+            flat.zero_()
         for p, off, n in _slots(members):
             flat[off:off + n].copy_(p.data.reshape(-1))
             p.data = flat[off:off + n].view(p.shape)
@@ -144,13 +151,13 @@ def flatten_parameters_fp32(params, set_to_param=False, set_grad=True):
     return flat
 
 
-def get_fp16_params(args, params, grad_alloc=None, fp32_grads=True):
+def get_fp16_params(args, params, grad_alloc=None, fp32_grads=True, param_alloc=None):
     """Build the per-group flat 16-bit params (+grads) and fp32 masters."""
     fp16_groups, fp32_groups = [], []
     for group in separate_decay_params(args, params):
         members = group["params"]
         check_param_device(members)
-        flats16 = flatten_parameters(members, grad_alloc=grad_alloc)
+        flats16 = flatten_parameters(members, grad_alloc=grad_alloc, param_alloc=param_alloc)
         master = flatten_parameters_fp32(members, set_grad=fp32_grads)
         fp16_groups.append({"params": flats16})
         group = dict(group)
@@ -170,6 +177,27 @@ class _FP16OptimizerMixin(object):
         self._grads_zeroed = False
 
     # -- state ----------------------------------------------------------------------------------
+    # -- sharded step (experimental, --ddp-backend b200 with UNICORE_B200_SHARD_OPTIMIZER=1) -----------------
+    def enable_sharded_step(self, stepper) -> bool:
+        """``stepper`` (``unicore_b200.parallel.symm_dp.ShardedAdamStepper``) runs Adam on this rank's 1/N shard
+        of every flat group and all-gathers the new parameters inside the same kernel.  Only the shard of the fp32
+        master / moments is current on a rank afterwards; ``consolidate_state`` (a collective) refreshes the rest."""
+        if not self._fused or any(len(g["params"]) != 1 for g in self.fp16_params):
+            return False
+        self._sharded = stepper
+        return True
+
+    def consolidate_state(self):
+        """All ranks: gather the shards of master / exp_avg / exp_avg_sq so that ``state_dict()`` is complete."""
+        stepper = getattr(self, "_sharded", None)
+        if stepper is None:
+            return
+        inner = self.fp32_optimizer.optimizer
+        for _, master in self._pairs():
+            state = inner._state_for(master)
+            for t in (master.data, state["exp_avg"], state["exp_avg_sq"]):
+                stepper.gather_(t)
+
     def state_dict(self):
         self.resolve_pending_overflow()
         state = self.fp32_optimizer.state_dict()
@@ -375,6 +403,8 @@ class _FP16OptimizerMixin(object):
         """unscale+clip, Adam on fp32 master, 16-bit write-back (+SR) and grad zeroing: one launch."""
         from unicore import ops
 
+        if getattr(self, "_sharded", None) is not None:
+            return self._sharded_fused_step()
         inner = self.fp32_optimizer.optimizer
         work = []
         for (flats16, master), group in zip(self._pairs(), inner.param_groups):
@@ -403,6 +433,28 @@ class _FP16OptimizerMixin(object):
             zero_grad=True,
             stochastic_rounding=self.bf16_sr,
         )
+        self._grads_zeroed = True
+        self._needs_sync = False
+
+    def _sharded_fused_step(self):
+        """Same contract as ``_fused_step``; the kernel touches only this rank's shard and broadcasts the result."""
+        inner = self.fp32_optimizer.optimizer
+        factor = self._multiply_factor
+        grad_scale = getattr(self, "_device_grad_scale", None)
+        self._device_grad_scale = None
+        if grad_scale is None:
+            grad_scale = (1.0 / factor) if not torch.is_tensor(factor) else factor.reciprocal()
+        for (flats16, master), group in zip(self._pairs(), inner.param_groups):
+            flat = flats16[0]
+            state = inner._state_for(master)
+            state["step"] += 1
+            beta1, beta2 = group["betas"]
+            self._sharded.step(
+                flat, master.data, state["exp_avg"], state["exp_avg_sq"], lr=group["lr"], beta1=beta1, beta2=beta2,
+                eps=group["eps"], step=state["step"], bias_correction=bool(group.get("bias_correction", True)),
+                weight_decay=group["weight_decay"], grad_scale=grad_scale, stochastic_rounding=self.bf16_sr,
+            )
+            flat.grad.zero_()
         self._grads_zeroed = True
         self._needs_sync = False
 
@@ -458,7 +510,7 @@ class FP16Optimizer(_FP16OptimizerMixin, UnicoreOptimizer):
             self.scaler = None  # bf16 has fp32's exponent range: no loss scaling
 
     @classmethod
-    def build_optimizer(cls, args, params, grad_alloc=None, **kwargs):
+    def build_optimizer(cls, args, params, grad_alloc=None, param_alloc=None, **kwargs):
         """``params``: list of ``(name, param)`` of the (already 16-bit) model."""
         from unicore import ops, optim
 
@@ -473,7 +525,9 @@ class FP16Optimizer(_FP16OptimizerMixin, UnicoreOptimizer):
             and getattr(args, "per_sample_clip_norm", 0) <= 0
             and not getattr(args, "no_fused_optimizer_tail", False)
         )
-        fp16_params, fp32_params = get_fp16_params(args, params, grad_alloc=grad_alloc, fp32_grads=not want_fused)
+        fp16_params, fp32_params = get_fp16_params(
+            args, params, grad_alloc=grad_alloc, fp32_grads=not want_fused, param_alloc=param_alloc if want_fused else None
+        )
         fp32_optimizer = optim.build_optimizer(args, fp32_params, separate=False)
         fused = want_fused and hasattr(fp32_optimizer.optimizer, "_state_for")
         if want_fused and not fused:  # inner optimizer is not FusedAdam after all

@@ -193,7 +193,10 @@ class Trainer(object):
             raise ValueError("--per-sample-clip-norm only supports --ddp-backend no_c10d")
         if self.args.fp16 or self.args.bf16:
             grad_alloc = getattr(self._dp_engine(), "alloc_grad_buffer", None)
-            self._optimizer = optim.FP16Optimizer.build_optimizer(self.args, named, grad_alloc=grad_alloc)
+            param_alloc = getattr(self._dp_engine(), "alloc_param_buffer", None)
+            self._optimizer = optim.FP16Optimizer.build_optimizer(
+                self.args, named, grad_alloc=grad_alloc, param_alloc=param_alloc
+            )
             if self.args.allreduce_fp32_grad and self.args.ddp_backend not in ("no_c10d", "legacy_ddp"):
                 raise ValueError("--allreduce-fp32-grad requires --ddp-backend no_c10d")
             engine = self._dp_engine()
@@ -237,6 +240,13 @@ class Trainer(object):
         if self.ema is not None:
             state["ema"] = self.ema.state_dict()
         return state
+
+    def consolidate_optimizer_state(self):
+        """Collective, called on EVERY rank before a checkpoint is written: a sharded optimizer gathers its state
+        (no-op for the replicated optimizers)."""
+        consolidate = getattr(self._optimizer, "consolidate_state", None)
+        if consolidate is not None:
+            consolidate()
 
     def save_checkpoint(self, filename, extra_state):
         """Write the full training state (rank 0 only); tensors are stored as fp32 on CPU."""

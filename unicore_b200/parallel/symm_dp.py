@@ -20,6 +20,7 @@ checkpoints, tiny statistics).
 """
 import contextlib
 import logging
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -111,6 +112,59 @@ class SymmAllReduce:
         )
 
 
+class ShardedAdamStepper:
+    """Optimizer step fused with the parameter all-gather (``csrc/comm/allreduce.cu::sharded_adam_kernel``).
+
+    EXPERIMENTAL - enabled with ``UNICORE_B200_SHARD_OPTIMIZER=1``; written in round 1 without access to a
+    multi-GPU box for validation.  Rank ``r`` owns elements ``[r*per, (r+1)*per)`` of every
+    flat parameter group (``per`` a multiple of 8): one kernel runs Adam on that shard of the fp32 master /
+    moments and stores the new 16-bit parameters into every rank's (symmetric) parameter arena with
+    ``multimem.st`` (NVLS) or peer stores, closing with a flag barrier.
+    """
+
+    def __init__(self, reducer: SymmAllReduce, param_buffers: List[SymmBuffer], seed: int = 0):
+        self.reducer = reducer
+        self.rank, self.world = reducer.rank, reducer.world
+        self.group = reducer.group
+        self._by_ptr = {buf.tensor.data_ptr(): buf for buf in param_buffers}
+        self.seed = int(seed)
+        self._calls = 0
+
+    def bounds(self, numel: int):
+        per = -(-(-(-numel // 8)) // self.world) * 8
+        lo = min(numel, self.rank * per)
+        return per, lo, min(numel, lo + per)
+
+    def covers(self, flat: torch.Tensor) -> bool:
+        return flat.data_ptr() in self._by_ptr
+
+    def step(self, flat, master, exp_avg, exp_avg_sq, *, lr, beta1, beta2, eps, step, bias_correction, weight_decay,
+             grad_scale, stochastic_rounding=False):
+        buf = self._by_ptr[flat.data_ptr()]
+        _, lo, hi = self.bounds(master.numel())
+        scale_f, scale_dev = 1.0, None
+        if torch.is_tensor(grad_scale):
+            scale_dev = grad_scale.detach().float().reshape(1)
+        else:
+            scale_f = float(grad_scale)
+        self._calls += 1
+        self.reducer.native.symm_sharded_adam(
+            buf.ptrs, self.reducer.flags.ptrs, buf.multicast_ptr, self.rank, flat.grad, master, exp_avg, exp_avg_sq,
+            lo, hi, float(lr), float(beta1), float(beta2), float(eps), int(step), bool(bias_correction),
+            float(weight_decay), scale_f, scale_dev, bool(stochastic_rounding), self.seed, self._calls, 0,
+        )
+
+    @torch.no_grad()
+    def gather_(self, t: torch.Tensor) -> None:
+        """Refresh the full-length fp32 tensor ``t`` from the shards every rank keeps current (NCCL, cold path)."""
+        per, lo, hi = self.bounds(t.numel())
+        mine = torch.zeros(per, dtype=t.dtype, device=t.device)
+        mine[: hi - lo].copy_(t[lo:hi])
+        full = torch.empty(per * self.world, dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(full, mine, group=self.group)
+        t.copy_(full[: t.numel()])
+
+
 class _Bucket:
     __slots__ = ("buffer", "lo", "hi", "pending", "total", "launched")
 
@@ -142,6 +196,9 @@ class SymmDataParallel(nn.Module):
         self._sq.tensor.zero_()
         self._sq_valid = False
         self._covers_all_params = False
+        # experimental: Adam on a 1/N shard + parameter all-gather in one kernel (see ShardedAdamStepper)
+        self.shard_optimizer = os.environ.get("UNICORE_B200_SHARD_OPTIMIZER", "0") == "1"
+        self._param_buffers: List[SymmBuffer] = []
         # replicas must start identical (reference: DDP broadcasts from rank 0 at construction)
         with torch.no_grad():
             for t in list(module.parameters()) + list(module.buffers()):
@@ -167,8 +224,30 @@ class SymmDataParallel(nn.Module):
         self._buffers.append(buf)
         return buf.tensor[:numel]
 
+    def alloc_param_buffer(self, numel: int, dtype: torch.dtype, device: torch.device) -> Optional[torch.Tensor]:
+        """Called by ``flatten_parameters``: with the sharded optimizer the flat PARAMETER arena is symmetric too
+        (every rank stores its shard of the new parameters into all of them); otherwise decline."""
+        if not self.shard_optimizer:
+            return None
+        padded = -(-numel // 8) * 8
+        buf = self.reducer.allocate(padded, dtype)
+        self._param_buffers.append(buf)
+        return buf.tensor[:numel]
+
+    def _maybe_enable_sharded_step(self, optimizer) -> None:
+        if not (self.shard_optimizer and self._param_buffers and hasattr(optimizer, "enable_sharded_step")):
+            return
+        if getattr(getattr(optimizer, "args", None), "ema_decay", -1) > 0:
+            logger.warning("UNICORE_B200_SHARD_OPTIMIZER ignored: the EMA update reads the full fp32 master weights")
+            return
+        stepper = ShardedAdamStepper(self.reducer, self._param_buffers, seed=getattr(optimizer.args, "seed", 0))
+        flats = [f for g in optimizer.fp16_params for f in g["params"]]
+        if all(stepper.covers(f) for f in flats) and optimizer.enable_sharded_step(stepper):
+            logger.info("optimizer step sharded over %d ranks and fused with the parameter all-gather", self.world_size)
+
     def attach_optimizer(self, optimizer) -> None:
         """Build buckets over the flat gradient arenas and install gradient-ready hooks."""
+        self._maybe_enable_sharded_step(optimizer)
         for h in self._hooks:
             h.remove()
         self._hooks, self._buckets, self._param_bucket = [], [], {}
