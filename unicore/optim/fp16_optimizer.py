@@ -176,7 +176,6 @@ class _FP16OptimizerMixin(object):
         self.bf16_sr = getattr(args, "bf16_sr", False)
         self._grads_zeroed = False
 
-    # -- state ----------------------------------------------------------------------------------
     # -- sharded step (experimental, --ddp-backend b200 with UNICORE_B200_SHARD_OPTIMIZER=1) -----------------
     def enable_sharded_step(self, stepper) -> bool:
         """``stepper`` (``unicore_b200.parallel.symm_dp.ShardedAdamStepper``) runs Adam on this rank's 1/N shard
@@ -198,6 +197,7 @@ class _FP16OptimizerMixin(object):
             for t in (master.data, state["exp_avg"], state["exp_avg_sq"]):
                 stepper.gather_(t)
 
+    # -- state ----------------------------------------------------------------------------------
     def state_dict(self):
         self.resolve_pending_overflow()
         state = self.fp32_optimizer.state_dict()
