@@ -47,6 +47,7 @@ USE_NATIVE = HAS_CUDA_EXT and _is_blackwell() and os.environ.get("UNICORE_DISABL
 # kernels launched per binding call (used for the benchmark's ``gpu_launches`` figure)
 _LAUNCHES_PER_CALL = {
     "layernorm_bwd": 2, "rmsnorm_bwd": 2, "bias_dropout_add_ln_bwd": 2, "fmha_bwd": 4, "bias_gelu_bwd": 2, "symm_allreduce": 2,
+    "column_sum": 2, "symm_sharded_adam": 2,
 }
 _launch_count = 0
 
