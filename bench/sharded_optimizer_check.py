@@ -4,7 +4,9 @@
 Trains the same tiny BERT twice from the same seed - once with the stock fused Adam on every rank, once with
 ``UNICORE_B200_SHARD_OPTIMIZER=1`` (Adam on a 1/N shard + parameter all-gather in one kernel) - and compares the
 16-bit parameters, the fp32 master weights and the Adam moments after ``consolidate_state``.  The per-element
-arithmetic is identical, so the two runs must agree bit for bit.  Prints one JSON line on rank 0.
+arithmetic is the same formula in two kernels (FMA contraction may differ), so fp32 state must agree to ~1e-6 and
+the 16-bit parameters to one rounding step; a shard that was not updated or not gathered shows up as ~lr * steps.
+Prints one JSON line on rank 0.
 """
 import argparse
 import importlib
@@ -82,11 +84,13 @@ def main():
     for k in s0:
         for n in s0[k]:
             diffs["state_{}_{}".format(k, n)] = float((s0[k][n] - s1[k][n]).abs().max())
-    worst = torch.tensor([max(diffs.values())], device="cuda")
+    fp32_worst = max(v for k, v in diffs.items() if k != "params")
+    worst = torch.tensor([diffs["params"], fp32_worst], device="cuda")
     dist.all_reduce(worst, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"summary": "sharded_optimizer_check", "world": world, "replicated_was_sharded": sharded0,
-                          "sharded_active": sharded1, "max_abs_diff": float(worst.item()), "diffs": diffs}))
+                          "sharded_active": sharded1, "max_param_diff": float(worst[0].item()),
+                          "max_fp32_state_diff": float(worst[1].item()), "diffs": diffs}))
     dist.barrier()
     dist.destroy_process_group()
     return 0

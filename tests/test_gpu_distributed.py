@@ -67,4 +67,5 @@ def test_sharded_optimizer_matches_replicated(precision):
     line = [l for l in log.splitlines() if l.startswith('{"summary"')][-1]
     res = json.loads(line)
     assert res["sharded_active"] and not res["replicated_was_sharded"], res
-    assert res["max_abs_diff"] == 0.0, res
+    # 4 updates at lr 1e-3: a shard that missed its update or its all-gather is off by ~4e-3
+    assert res["max_fp32_state_diff"] < 2e-5 and res["max_param_diff"] < 1e-3, res
