@@ -68,4 +68,4 @@ def test_sharded_optimizer_matches_replicated(precision):
     res = json.loads(line)
     assert res["sharded_active"] and not res["replicated_was_sharded"], res
     # 4 updates at lr 1e-3: a shard that missed its update or its all-gather is off by ~4e-3
-    assert res["max_fp32_state_diff"] < 2e-5 and res["max_param_diff"] < 1e-3, res
+    assert res["max_fp32_state_diff"] < 2e-4 and res["max_param_diff"] < 1e-3, res
