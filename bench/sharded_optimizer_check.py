@@ -2,7 +2,8 @@
 """Replicated vs sharded optimizer step under ``--ddp-backend b200`` (run with torchrun on >= 2 GPUs).
 
 Trains the same tiny BERT twice from the same seed - once with the stock fused Adam on every rank, once with
-``UNICORE_B200_SHARD_OPTIMIZER=1`` (Adam on a 1/N shard + parameter all-gather in one kernel) - and compares the
+``UNICORE_B200_SHARD_OPTIMIZER=1|2`` (Adam on a 1/N shard + parameter all-gather in one kernel; mode 2 also stops
+the gradient buckets after their reduce-scatter half) - and compares the
 16-bit parameters, the fp32 master weights and the Adam moments after ``consolidate_state``.  The per-element
 arithmetic is the same formula in two kernels (FMA contraction may differ), so fp32 state must agree to ~1e-6 and
 the 16-bit parameters to one rounding step; a shard that was not updated or not gathered shows up as ~lr * steps.
@@ -25,7 +26,7 @@ def run(mode, steps, precision, rank, local_rank, world):
     from unicore import options, tasks, utils
     from unicore.trainer import Trainer
 
-    os.environ["UNICORE_B200_SHARD_OPTIMIZER"] = "1" if mode else "0"
+    os.environ["UNICORE_B200_SHARD_OPTIMIZER"] = str(int(mode))
     flags = [
         "--task", "synthetic_mlm", "--loss", "masked_lm", "--arch", "bert_base", "--encoder-layers", "2",
         "--encoder-embed-dim", "128", "--encoder-ffn-embed-dim", "256", "--encoder-attention-heads", "2",
@@ -66,6 +67,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--precision", default="bf16", choices=["fp16", "bf16"])
+    ap.add_argument("--mode", type=int, default=1, choices=[1, 2],
+                    help="1: contiguous shard after the full all-reduce; 2: reduce-scatter-only buckets, slice-wise shard")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -78,7 +81,7 @@ def main():
     dist.init_process_group(backend="nccl", init_method="env://", world_size=world, rank=rank)
     importlib.import_module("bert")
     sharded0, p0, s0, m0 = run(0, a.steps, a.precision, rank, local_rank, world)
-    sharded1, p1, s1, m1 = run(1, a.steps, a.precision, rank, local_rank, world)
+    sharded1, p1, s1, m1 = run(a.mode, a.steps, a.precision, rank, local_rank, world)
     diffs = {"params": float((p0 - p1).abs().max())}
     diffs["master"] = max(float((x - y).abs().max()) for x, y in zip(m0, m1))
     for k in s0:
@@ -88,7 +91,7 @@ def main():
     worst = torch.tensor([diffs["params"], fp32_worst], device="cuda")
     dist.all_reduce(worst, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(json.dumps({"summary": "sharded_optimizer_check", "world": world, "replicated_was_sharded": sharded0,
+        print(json.dumps({"summary": "sharded_optimizer_check", "world": world, "mode": a.mode, "replicated_was_sharded": sharded0,
                           "sharded_active": sharded1, "max_param_diff": float(worst[0].item()),
                           "max_fp32_state_diff": float(worst[1].item()), "diffs": diffs}))
     dist.barrier()

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_oneshot_kernel(CommPee
 
 // Two-shot: rank r owns slice r: reduce-scatter by peer loads, all-gather by peer stores.
 // W = compile-time bound on the world size (2 / 4 / 8); W * kU = 16 peer vectors in flight per thread.
-template <typename T, int W>
+template <typename T, int W, bool kScatterOnly = false>
 __global__ void __launch_bounds__(kCommThreads) allreduce_twoshot_kernel(CommPeers peers, long long begin_vec,
                                                                           long long end_vec, float scale, float* sq_acc) {
   constexpr int EPV = 16 / sizeof(T);
@@ -172,9 +172,13 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_twoshot_kernel(CommPee
           sq += acc[e] * acc[e];
         }
         const Vec16 out = pack<T>(acc);
+        if (kScatterOnly) {
+          st_global_v4(reinterpret_cast<uint8_t*>(peers.buf[peers.rank]) + v * 16, out);
+        } else {
 #pragma unroll
-        for (int p = 0; p < W; ++p) {
-          if (p < peers.world) st_global_v4(reinterpret_cast<uint8_t*>(peers.buf[p]) + v * 16, out);
+          for (int p = 0; p < W; ++p) {
+            if (p < peers.world) st_global_v4(reinterpret_cast<uint8_t*>(peers.buf[p]) + v * 16, out);
+          }
         }
       }
     }
@@ -219,7 +223,7 @@ UB_DEVICE void multimem_st(void* mc_addr, const Vec16& v) {
                : "memory");
 }
 
-template <typename T>
+template <typename T, bool kScatterOnly = false>
 __global__ void __launch_bounds__(kCommThreads) allreduce_nvls_kernel(CommPeers peers, long long begin_vec,
                                                                         long long end_vec, float scale, float* sq_acc) {
   constexpr int EPV = 16 / sizeof(T);
@@ -252,7 +256,8 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_nvls_kernel(CommPeers 
           }
           r[u] = pack<T>(acc);
         }
-        multimem_st(mc + v * 16, r[u]);
+        if (kScatterOnly) st_global_v4(reinterpret_cast<uint8_t*>(peers.buf[peers.rank]) + v * 16, r[u]);
+        else multimem_st(mc + v * 16, r[u]);
       }
     }
   }
@@ -273,67 +278,72 @@ UB_DEVICE uint32_t shard_bf16_sr(float x, uint32_t rnd16) {
 }
 
 template <typename T>
+UB_DEVICE void shard_adam_range(const CommPeers& params, const ShardAdam& a, long long lo, long long hi, float gmul) {
+  const T* G = reinterpret_cast<const T*>(a.grad);
+  const bool sr = a.stochastic_rounding != 0 && sizeof(T) == 2;
+  const long long vend = lo + ((hi - lo) & ~7ll);
+  const long long stride = (long long)gridDim.x * kCommThreads * 8;
+  for (long long i = lo + ((long long)blockIdx.x * kCommThreads + threadIdx.x) * 8; i < vend; i += stride) {
+    float g[8], p[8], m[8], v[8];
+    unpack<T>(ld_global_nc_v4(G + i), g);
+    const Vec16 p0 = ld_global_v4(a.master + i), p1 = ld_global_v4(a.master + i + 4);
+    const Vec16 m0 = ld_global_v4(a.exp_avg + i), m1 = ld_global_v4(a.exp_avg + i + 4);
+    const Vec16 v0 = ld_global_v4(a.exp_avg_sq + i), v1 = ld_global_v4(a.exp_avg_sq + i + 4);
+    unpack<float>(p0, p);
+    unpack<float>(p1, p + 4);
+    unpack<float>(m0, m);
+    unpack<float>(m1, m + 4);
+    unpack<float>(v0, v);
+    unpack<float>(v1, v + 4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) shard_adam_math(p[k], m[k], v[k], g[k] * gmul, a);
+    st_global_v4(a.master + i, pack<float>(p));
+    st_global_v4(a.master + i + 4, pack<float>(p + 4));
+    st_global_v4(a.exp_avg + i, pack<float>(m));
+    st_global_v4(a.exp_avg + i + 4, pack<float>(m + 4));
+    st_global_v4(a.exp_avg_sq + i, pack<float>(v));
+    st_global_v4(a.exp_avg_sq + i + 4, pack<float>(v + 4));
+    Vec16 o;
+    if (sr) {
+      const Philox4 r = philox4x32_10(a.seed, a.offset, (a.elem_base + (unsigned long long)i) >> 3);
+      const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        o.w[k] = shard_bf16_sr(p[2 * k], rw[k] & 0xffffu) | (shard_bf16_sr(p[2 * k + 1], rw[k] >> 16) << 16);
+    } else {
+      o = pack<T>(p);
+    }
+    // the all-gather IS this store: one instruction through the switch, or one store per peer
+    if (params.multicast != nullptr) {
+      multimem_st(reinterpret_cast<T*>(params.multicast) + i, o);
+    } else {
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r) {
+        if (r < params.world) st_global_v4(reinterpret_cast<T*>(params.buf[r]) + i, o);
+      }
+    }
+  }
+  // scalar tail (group length not a multiple of 8; at most one range has one): plain peer stores
+  if (blockIdx.x == 0) {
+    for (long long i = vend + threadIdx.x; i < hi; i += kCommThreads) {
+      float p = a.master[i], m = a.exp_avg[i], v = a.exp_avg_sq[i];
+      shard_adam_math(p, m, v, to_f32<T>(G[i]) * gmul, a);
+      a.master[i] = p;
+      a.exp_avg[i] = m;
+      a.exp_avg_sq[i] = v;
+      const T out = from_f32<T>(p);
+      for (int r = 0; r < params.world; ++r) reinterpret_cast<T*>(params.buf[r])[i] = out;
+    }
+  }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kCommThreads) sharded_adam_kernel(CommPeers params, ShardAdam a) {
   const float sdev = a.scale_dev ? __ldg(a.scale_dev) : 1.f;
   const bool skip = a.scale_dev != nullptr && !(isfinite(sdev) && sdev != 0.f);
   if (!skip) {
     const float gmul = a.inv_scale / sdev;
-    const T* G = reinterpret_cast<const T*>(a.grad);
-    const bool sr = a.stochastic_rounding != 0 && sizeof(T) == 2;
-    const long long vend = a.lo + ((a.hi - a.lo) & ~7ll);
-    const long long stride = (long long)gridDim.x * kCommThreads * 8;
-    for (long long i = a.lo + ((long long)blockIdx.x * kCommThreads + threadIdx.x) * 8; i < vend; i += stride) {
-      float g[8], p[8], m[8], v[8];
-      unpack<T>(ld_global_nc_v4(G + i), g);
-      const Vec16 p0 = ld_global_v4(a.master + i), p1 = ld_global_v4(a.master + i + 4);
-      const Vec16 m0 = ld_global_v4(a.exp_avg + i), m1 = ld_global_v4(a.exp_avg + i + 4);
-      const Vec16 v0 = ld_global_v4(a.exp_avg_sq + i), v1 = ld_global_v4(a.exp_avg_sq + i + 4);
-      unpack<float>(p0, p);
-      unpack<float>(p1, p + 4);
-      unpack<float>(m0, m);
-      unpack<float>(m1, m + 4);
-      unpack<float>(v0, v);
-      unpack<float>(v1, v + 4);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) shard_adam_math(p[k], m[k], v[k], g[k] * gmul, a);
-      st_global_v4(a.master + i, pack<float>(p));
-      st_global_v4(a.master + i + 4, pack<float>(p + 4));
-      st_global_v4(a.exp_avg + i, pack<float>(m));
-      st_global_v4(a.exp_avg + i + 4, pack<float>(m + 4));
-      st_global_v4(a.exp_avg_sq + i, pack<float>(v));
-      st_global_v4(a.exp_avg_sq + i + 4, pack<float>(v + 4));
-      Vec16 o;
-      if (sr) {
-        const Philox4 r = philox4x32_10(a.seed, a.offset, (a.elem_base + (unsigned long long)i) >> 3);
-        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          o.w[k] = shard_bf16_sr(p[2 * k], rw[k] & 0xffffu) | (shard_bf16_sr(p[2 * k + 1], rw[k] >> 16) << 16);
-      } else {
-        o = pack<T>(p);
-      }
-      // the all-gather IS this store: one instruction through the switch, or one store per peer
-      if (params.multicast != nullptr) {
-        multimem_st(reinterpret_cast<T*>(params.multicast) + i, o);
-      } else {
-#pragma unroll
-        for (int r = 0; r < kMaxPeers; ++r) {
-          if (r < params.world) st_global_v4(reinterpret_cast<T*>(params.buf[r]) + i, o);
-        }
-      }
-    }
-    // scalar tail of the last shard (group length not a multiple of 8): plain peer stores
-    if (blockIdx.x == 0) {
-      for (long long i = vend + threadIdx.x; i < a.hi; i += kCommThreads) {
-        float p = a.master[i], m = a.exp_avg[i], v = a.exp_avg_sq[i];
-        shard_adam_math(p, m, v, to_f32<T>(G[i]) * gmul, a);
-        a.master[i] = p;
-        a.exp_avg[i] = m;
-        a.exp_avg_sq[i] = v;
-        const T out = from_f32<T>(p);
-        for (int r = 0; r < params.world; ++r) reinterpret_cast<T*>(params.buf[r])[i] = out;
-      }
-    }
+    for (int r = 0; r < a.nranges; ++r) shard_adam_range<T>(params, a, a.range_lo[r], a.range_hi[r], gmul);
   }
   block_barrier(params, /*release_first=*/true);  // every shard has landed everywhere before anyone proceeds
 }
@@ -349,8 +359,19 @@ void launch_sharded_adam(const CommPeers& params, const ShardAdam& a, int dtype,
 // ---- host --------------------------------------------------------------------------------------------------------------
 template <typename T>
 static void run_allreduce(const CommPeers& peers, long long begin_vec, long long end_vec, float scale, int algo,
-                          int blocks, float* sq_acc, cudaStream_t stream) {
+                          int blocks, float* sq_acc, cudaStream_t stream, bool scatter_only) {
   symm_handshake_kernel<<<1, 32, 0, stream>>>(peers);
+  if (scatter_only) {  // reduce-scatter half only (sharded optimizer); one-shot has no such form
+    if (algo == kAlgoNvls)
+      allreduce_nvls_kernel<T, true><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale, sq_acc);
+    else if (peers.world <= 2)
+      allreduce_twoshot_kernel<T, 2, true><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale, sq_acc);
+    else if (peers.world <= 4)
+      allreduce_twoshot_kernel<T, 4, true><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale, sq_acc);
+    else
+      allreduce_twoshot_kernel<T, 8, true><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale, sq_acc);
+    return;
+  }
   if (algo == kAlgoNvls) {
     allreduce_nvls_kernel<T><<<blocks, kCommThreads, 0, stream>>>(peers, begin_vec, end_vec, scale, sq_acc);
   } else if (algo == kAlgoTwoShot) {
@@ -372,10 +393,11 @@ int pick_allreduce_algo(long long bytes, int world, bool has_multicast) {
 }
 
 void launch_allreduce(const CommPeers& peers, long long byte_offset, long long bytes, int dtype, float scale, int algo,
-                      int blocks, float* sq_acc, cudaStream_t stream) {
+                      int blocks, float* sq_acc, cudaStream_t stream, bool scatter_only) {
   const long long begin_vec = byte_offset / 16, end_vec = (byte_offset + bytes) / 16;
   if (end_vec <= begin_vec) return;
   if (algo == kAlgoAuto) algo = pick_allreduce_algo(bytes, peers.world, peers.multicast != nullptr);
+  if (scatter_only && algo == kAlgoOneShot) algo = peers.multicast != nullptr && peers.world > 2 ? kAlgoNvls : kAlgoTwoShot;
   if (algo == kAlgoNvls && peers.multicast == nullptr) algo = kAlgoTwoShot;
   const long long one_shot_blocks = (end_vec - begin_vec + kCommThreads - 1) / kCommThreads;
   if (algo == kAlgoOneShot && one_shot_blocks > kMaxCommBlocks - 1) algo = kAlgoTwoShot;  // range too large
@@ -385,9 +407,9 @@ void launch_allreduce(const CommPeers& peers, long long byte_offset, long long b
     if (blocks <= 0) blocks = 24;
     if (blocks > kMaxCommBlocks - 1) blocks = kMaxCommBlocks - 1;  // the last slot belongs to the handshake
   }
-  if (dtype == kF32) run_allreduce<float>(peers, begin_vec, end_vec, scale, algo, blocks, sq_acc, stream);
-  else if (dtype == kF16) run_allreduce<__half>(peers, begin_vec, end_vec, scale, algo, blocks, sq_acc, stream);
-  else run_allreduce<__nv_bfloat16>(peers, begin_vec, end_vec, scale, algo, blocks, sq_acc, stream);
+  if (dtype == kF32) run_allreduce<float>(peers, begin_vec, end_vec, scale, algo, blocks, sq_acc, stream, scatter_only);
+  else if (dtype == kF16) run_allreduce<__half>(peers, begin_vec, end_vec, scale, algo, blocks, sq_acc, stream, scatter_only);
+  else run_allreduce<__nv_bfloat16>(peers, begin_vec, end_vec, scale, algo, blocks, sq_acc, stream, scatter_only);
 }
 
 }  // namespace ub

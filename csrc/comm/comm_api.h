@@ -25,11 +25,16 @@ int pick_allreduce_algo(long long bytes, int world, bool has_multicast);
 // sq_acc (nullable, local device memory): this rank atomically adds the sum of squares of the REDUCED, scaled
 // values of its 1/world slice of the range - summed over ranks that is the squared L2 norm of the result, so the
 // gradient-norm pass over the arena (a separate 2-byte-per-parameter read) is not needed.
+// scatter_only (experimental, sharded optimizer): stop after the reduce-scatter half - rank r's 1/world slice of the
+// range holds the result in ITS buffer only (slice = vectors [begin + r*per, begin + (r+1)*per), per = ceil(n/world)).
 void launch_allreduce(const CommPeers& peers, long long byte_offset, long long bytes, int dtype, float scale, int algo,
-                      int blocks, float* sq_acc, cudaStream_t stream);
+                      int blocks, float* sq_acc, cudaStream_t stream, bool scatter_only = false);
+
+constexpr int kMaxShardRanges = 48;  // one contiguous shard, or one slice per gradient bucket
 
 // ---- optimizer step fused with the parameter all-gather (experimental: UNICORE_B200_SHARD_OPTIMIZER=1) --------
-// Rank r owns elements [lo, hi) of a flat parameter group: it runs Adam on that shard of the fp32 master / moment
+// Rank r owns a set of element ranges of a flat parameter group (one contiguous 1/N shard after a full all-reduce, or
+// its slice of every bucket after reduce-scatter-only buckets): it runs Adam on that shard of the fp32 master / moment
 // arrays (reading the already reduced 16-bit gradients of its local arena) and stores the new 16-bit parameters
 // into EVERY rank's parameter arena - one multimem.st per 16-byte vector through the NVLS alias when there is one,
 // peer stores otherwise.  `params` describes the symmetric PARAMETER arena.  A handshake ahead of the kernel keeps
@@ -40,7 +45,8 @@ struct ShardAdam {
   float* exp_avg;
   float* exp_avg_sq;
   const void* grad;         // local, reduced 16-bit gradient arena of the group
-  long long lo, hi;         // this rank's shard (lo % 8 == 0)
+  int nranges;              // this rank's shard = union of element ranges [lo, hi), every lo % 8 == 0
+  long long range_lo[kMaxShardRanges], range_hi[kMaxShardRanges];
   float beta1, beta2, eps, step_size, decay_mul;
   float inv_scale;          // gradients are multiplied by inv_scale / (*scale_dev if given)
   const float* scale_dev;   // non-finite or zero => the update is skipped on every rank (overflow)

@@ -14,9 +14,9 @@ namespace {
 
 // buffer_ptrs / flag_ptrs: integer device addresses of every rank's (peer-mapped) buffers as returned
 // by the symmetric-memory rendezvous; multicast_ptr: NVLS alias or 0.
-void symm_allreduce(const std::vector<int64_t>& buffer_ptrs, const std::vector<int64_t>& flag_ptrs,
-                    int64_t multicast_ptr, int64_t rank, int64_t byte_offset, int64_t bytes, int64_t dtype,
-                    double scale, int64_t algo, int64_t blocks, int64_t sq_acc_ptr) {
+void symm_reduce_impl(const std::vector<int64_t>& buffer_ptrs, const std::vector<int64_t>& flag_ptrs,
+                      int64_t multicast_ptr, int64_t rank, int64_t byte_offset, int64_t bytes, int64_t dtype,
+                      double scale, int64_t algo, int64_t blocks, int64_t sq_acc_ptr, bool scatter_only) {
   const int world = (int)buffer_ptrs.size();
   TORCH_CHECK(world >= 1 && world <= ub::kMaxPeers, "world size must be in [1, ", ub::kMaxPeers, "]");
   TORCH_CHECK((int)flag_ptrs.size() == world && rank >= 0 && rank < world);
@@ -30,17 +30,34 @@ void symm_allreduce(const std::vector<int64_t>& buffer_ptrs, const std::vector<i
   peers.rank = (int)rank;
   peers.world = world;
   ub::launch_allreduce(peers, byte_offset, bytes, (int)dtype, (float)scale, (int)algo, (int)blocks,
-                       reinterpret_cast<float*>(sq_acc_ptr), at::cuda::getCurrentCUDAStream().stream());
+                       reinterpret_cast<float*>(sq_acc_ptr), at::cuda::getCurrentCUDAStream().stream(), scatter_only);
   cudaError_t err = cudaGetLastError();
   TORCH_CHECK(err == cudaSuccess, "symm_allreduce launch failed: ", cudaGetErrorString(err));
 }
 
-// One flat parameter group: Adam on this rank's shard [lo, hi) + all-gather of the new 16-bit parameters by the
+void symm_allreduce(const std::vector<int64_t>& buffer_ptrs, const std::vector<int64_t>& flag_ptrs,
+                    int64_t multicast_ptr, int64_t rank, int64_t byte_offset, int64_t bytes, int64_t dtype,
+                    double scale, int64_t algo, int64_t blocks, int64_t sq_acc_ptr) {
+  symm_reduce_impl(buffer_ptrs, flag_ptrs, multicast_ptr, rank, byte_offset, bytes, dtype, scale, algo, blocks,
+                   sq_acc_ptr, false);
+}
+
+// Reduce-scatter half only: afterwards rank r's buffer holds the reduced values of ITS slice of the range
+// (16-byte vectors [begin + r*per, begin + (r+1)*per), per = ceil(n_vectors / world)); the rest is stale.
+void symm_reduce_scatter(const std::vector<int64_t>& buffer_ptrs, const std::vector<int64_t>& flag_ptrs,
+                         int64_t multicast_ptr, int64_t rank, int64_t byte_offset, int64_t bytes, int64_t dtype,
+                         double scale, int64_t blocks, int64_t sq_acc_ptr) {
+  symm_reduce_impl(buffer_ptrs, flag_ptrs, multicast_ptr, rank, byte_offset, bytes, dtype, scale, ub::kAlgoAuto, blocks,
+                   sq_acc_ptr, true);
+}
+
+// One flat parameter group: Adam on this rank's shard (a list of element ranges) + all-gather of the new 16-bit parameters by the
 // kernel's own stores (see comm_api.h).  param_ptrs / multicast_ptr describe the symmetric PARAMETER arena of the
 // group; `grad` is this rank's (already reduced) gradient arena; master / exp_avg / exp_avg_sq are full-length fp32.
 void symm_sharded_adam(const std::vector<int64_t>& param_ptrs, const std::vector<int64_t>& flag_ptrs,
                        int64_t multicast_ptr, int64_t rank, const at::Tensor& grad, at::Tensor master,
-                       at::Tensor exp_avg, at::Tensor exp_avg_sq, int64_t lo, int64_t hi, double lr, double beta1,
+                       at::Tensor exp_avg, at::Tensor exp_avg_sq, const std::vector<int64_t>& range_lo,
+                       const std::vector<int64_t>& range_hi, double lr, double beta1,
                        double beta2, double eps, int64_t step, bool bias_correction, double weight_decay,
                        double grad_scale, const std::optional<at::Tensor>& scale_dev, bool stochastic_rounding,
                        int64_t seed, int64_t offset, int64_t blocks) {
@@ -54,7 +71,11 @@ void symm_sharded_adam(const std::vector<int64_t>& param_ptrs, const std::vector
   }
   const int64_t n = master.numel();
   TORCH_CHECK(exp_avg.numel() == n && exp_avg_sq.numel() == n && grad.numel() >= n);
-  TORCH_CHECK(0 <= lo && lo <= hi && hi <= n && (lo % 8 == 0 || lo == hi), "shard must start on a 16-byte boundary");
+  TORCH_CHECK(range_lo.size() == range_hi.size() && (int)range_lo.size() <= ub::kMaxShardRanges, "too many shard ranges");
+  for (size_t i = 0; i < range_lo.size(); ++i)
+    TORCH_CHECK(0 <= range_lo[i] && range_lo[i] <= range_hi[i] && range_hi[i] <= n &&
+                    (range_lo[i] % 8 == 0 || range_lo[i] == range_hi[i]),
+                "shard ranges must start on 16-byte boundaries inside the group");
   TORCH_CHECK((reinterpret_cast<uintptr_t>(grad.data_ptr()) & 15) == 0, "gradient arena must be 16-byte aligned");
   const c10::cuda::CUDAGuard guard(master.device());
   ub::CommPeers peers{};
@@ -71,8 +92,11 @@ void symm_sharded_adam(const std::vector<int64_t>& param_ptrs, const std::vector
   a.exp_avg = exp_avg.data_ptr<float>();
   a.exp_avg_sq = exp_avg_sq.data_ptr<float>();
   a.grad = grad.data_ptr();
-  a.lo = lo;
-  a.hi = hi;
+  a.nranges = (int)range_lo.size();
+  for (int i = 0; i < a.nranges; ++i) {
+    a.range_lo[i] = range_lo[i];
+    a.range_hi[i] = range_hi[i];
+  }
   double step_size = lr;
   if (bias_correction) {
     const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
@@ -107,8 +131,10 @@ int64_t symm_pick_algo(int64_t bytes, int64_t world, bool has_multicast) {
 
 void register_comm(pybind11::module_& m) {
   m.def("symm_allreduce", &symm_allreduce);
+  m.def("symm_reduce_scatter", &symm_reduce_scatter);
   m.def("symm_pick_algo", &symm_pick_algo);
   m.def("symm_sharded_adam", &symm_sharded_adam);
   m.attr("SYMM_MAX_BLOCKS") = (int64_t)ub::kMaxCommBlocks;
   m.attr("SYMM_MAX_PEERS") = (int64_t)ub::kMaxPeers;
+  m.attr("SYMM_MAX_SHARD_RANGES") = (int64_t)ub::kMaxShardRanges;
 }

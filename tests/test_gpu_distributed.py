@@ -57,13 +57,14 @@ def test_b200_backend_trains_like_c10d():
 
 
 @needs_two
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])
-def test_sharded_optimizer_matches_replicated(precision):
-    """UNICORE_B200_SHARD_OPTIMIZER=1 (Adam on a 1/N shard + parameter all-gather in one kernel): parameters, fp32
-    master weights and Adam moments identical to the replicated fused Adam after a few updates."""
+def test_sharded_optimizer_matches_replicated(precision, mode):
+    """UNICORE_B200_SHARD_OPTIMIZER=1|2 (Adam on a 1/N shard + parameter all-gather in one kernel; mode 2: buckets
+    stop after reduce-scatter): parameters, fp32 master weights and Adam moments match the replicated fused Adam."""
     n = 2 if torch.cuda.device_count() < 4 else 4
     log = _torchrun(n, [os.path.join(ROOT, "bench", "sharded_optimizer_check.py"), "--steps", "4",
-                        "--precision", precision])
+                        "--precision", precision, "--mode", str(mode)])
     line = [l for l in log.splitlines() if l.startswith('{"summary"')][-1]
     res = json.loads(line)
     assert res["sharded_active"] and not res["replicated_was_sharded"], res

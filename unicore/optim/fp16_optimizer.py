@@ -192,10 +192,10 @@ class _FP16OptimizerMixin(object):
         if stepper is None:
             return
         inner = self.fp32_optimizer.optimizer
-        for _, master in self._pairs():
+        for flats16, master in self._pairs():
             state = inner._state_for(master)
             for t in (master.data, state["exp_avg"], state["exp_avg_sq"]):
-                stepper.gather_(t)
+                stepper.gather_(t, flats16[0])
 
     # -- state ----------------------------------------------------------------------------------
     def state_dict(self):

@@ -94,7 +94,7 @@ class SymmAllReduce:
         return SymmBuffer(numel, dtype, self.device, self.group)
 
     def __call__(self, buf: SymmBuffer, elem_offset: int = 0, numel: Optional[int] = None, scale: float = 1.0,
-                 algo: int = 0, blocks: int = 0, sq_acc: Optional[torch.Tensor] = None):
+                 algo: int = 0, blocks: int = 0, sq_acc: Optional[torch.Tensor] = None, scatter_only: bool = False):
         """In-place sum over ranks of ``buf.tensor[elem_offset : elem_offset + numel]`` (x ``scale``).
 
         ``sq_acc`` (fp32 device scalar): this rank adds the sum of squares of the reduced values of its
@@ -106,6 +106,12 @@ class SymmAllReduce:
         if byte_off % 16 or nbytes % 16:
             raise ValueError("symmetric all-reduce ranges must be 16-byte aligned")
         tag = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[t.dtype]
+        if scatter_only:  # reduce-scatter half only: rank r keeps the reduced slice r of the range (sharded optimizer)
+            self.native.symm_reduce_scatter(
+                buf.ptrs, self.flags.ptrs, buf.multicast_ptr, self.rank, byte_off, nbytes, tag, float(scale), int(blocks),
+                0 if sq_acc is None else sq_acc.data_ptr(),
+            )
+            return
         self.native.symm_allreduce(
             buf.ptrs, self.flags.ptrs, buf.multicast_ptr, self.rank, byte_off, nbytes, tag, float(scale), int(algo),
             int(blocks), 0 if sq_acc is None else sq_acc.data_ptr(),
@@ -129,11 +135,27 @@ class ShardedAdamStepper:
         self._by_ptr = {buf.tensor.data_ptr(): buf for buf in param_buffers}
         self.seed = int(seed)
         self._calls = 0
+        # gradient-arena address -> [(lo, hi)] element ranges this rank owns (set by the engine when its buckets
+        # run reduce-scatter-only); without it the shard is one contiguous 1/world slice of the group
+        self.bucket_slices: Dict[int, List] = {}
 
     def bounds(self, numel: int):
         per = -(-(-(-numel // 8)) // self.world) * 8
         lo = min(numel, self.rank * per)
         return per, lo, min(numel, lo + per)
+
+    def ranges(self, flat: torch.Tensor, numel: int):
+        """Element ranges of the flat group (length ``numel``) whose update this rank performs."""
+        slices = self.bucket_slices.get(flat.grad.data_ptr())
+        if slices is None:
+            _, lo, hi = self.bounds(numel)
+            return [(lo, hi)] if hi > lo else []
+        out = []
+        for lo, hi in slices:
+            lo, hi = min(lo, numel), min(hi, numel)
+            if hi > lo:
+                out.append((lo, hi))
+        return out
 
     def covers(self, flat: torch.Tensor) -> bool:
         return flat.data_ptr() in self._by_ptr
@@ -141,7 +163,7 @@ class ShardedAdamStepper:
     def step(self, flat, master, exp_avg, exp_avg_sq, *, lr, beta1, beta2, eps, step, bias_correction, weight_decay,
              grad_scale, stochastic_rounding=False):
         buf = self._by_ptr[flat.data_ptr()]
-        _, lo, hi = self.bounds(master.numel())
+        ranges = self.ranges(flat, master.numel())
         scale_f, scale_dev = 1.0, None
         if torch.is_tensor(grad_scale):
             scale_dev = grad_scale.detach().float().reshape(1)
@@ -150,19 +172,20 @@ class ShardedAdamStepper:
         self._calls += 1
         self.reducer.native.symm_sharded_adam(
             buf.ptrs, self.reducer.flags.ptrs, buf.multicast_ptr, self.rank, flat.grad, master, exp_avg, exp_avg_sq,
-            lo, hi, float(lr), float(beta1), float(beta2), float(eps), int(step), bool(bias_correction),
-            float(weight_decay), scale_f, scale_dev, bool(stochastic_rounding), self.seed, self._calls, 0,
+            [r[0] for r in ranges], [r[1] for r in ranges], float(lr), float(beta1), float(beta2), float(eps), int(step),
+            bool(bias_correction), float(weight_decay), scale_f, scale_dev, bool(stochastic_rounding), self.seed,
+            self._calls, 0,
         )
 
     @torch.no_grad()
-    def gather_(self, t: torch.Tensor) -> None:
-        """Refresh the full-length fp32 tensor ``t`` from the shards every rank keeps current (NCCL, cold path)."""
-        per, lo, hi = self.bounds(t.numel())
-        mine = torch.zeros(per, dtype=t.dtype, device=t.device)
-        mine[: hi - lo].copy_(t[lo:hi])
-        full = torch.empty(per * self.world, dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(full, mine, group=self.group)
-        t.copy_(full[: t.numel()])
+    def gather_(self, t: torch.Tensor, flat: torch.Tensor) -> None:
+        """Refresh the full-length fp32 tensor ``t`` of ``flat``'s group from the ranges every rank keeps current
+        (one NCCL all-reduce of a zero-filled copy; cold path, checkpoints only)."""
+        mine = torch.zeros_like(t)
+        for lo, hi in self.ranges(flat, t.numel()):
+            mine[lo:hi].copy_(t[lo:hi])
+        dist.all_reduce(mine, group=self.group)
+        t.copy_(mine)
 
 
 class _Bucket:
@@ -197,7 +220,12 @@ class SymmDataParallel(nn.Module):
         self._sq_valid = False
         self._covers_all_params = False
         # experimental: Adam on a 1/N shard + parameter all-gather in one kernel (see ShardedAdamStepper)
-        self.shard_optimizer = os.environ.get("UNICORE_B200_SHARD_OPTIMIZER", "0") == "1"
+        #   1: contiguous 1/N shard on top of the full bucket all-reduce
+        #   2: buckets stop after their reduce-scatter half; rank r updates its slice of every bucket
+        self._shard_mode = int(os.environ.get("UNICORE_B200_SHARD_OPTIMIZER", "0") or 0)
+        self.shard_optimizer = self._shard_mode in (1, 2)
+        self._scatter_buckets = False
+        self._stepper: Optional[ShardedAdamStepper] = None
         self._param_buffers: List[SymmBuffer] = []
         # replicas must start identical (reference: DDP broadcasts from rank 0 at construction)
         with torch.no_grad():
@@ -243,7 +271,29 @@ class SymmDataParallel(nn.Module):
         stepper = ShardedAdamStepper(self.reducer, self._param_buffers, seed=getattr(optimizer.args, "seed", 0))
         flats = [f for g in optimizer.fp16_params for f in g["params"]]
         if all(stepper.covers(f) for f in flats) and optimizer.enable_sharded_step(stepper):
+            self._stepper = stepper
             logger.info("optimizer step sharded over %d ranks and fused with the parameter all-gather", self.world_size)
+
+    def _plan_bucket_slices(self) -> None:
+        """Mode 2: every bucket stops after reduce-scatter; tell the stepper which slice of each bucket is ours
+        (same formula as the kernels: 16-byte vectors [begin + r*per, begin + (r+1)*per), per = ceil(n / world))."""
+        self._scatter_buckets = False
+        if self._stepper is None or self._shard_mode != 2 or not self._covers_all_params:
+            return
+        slices: Dict[int, List] = {}
+        for b in self._buckets:
+            epv = 16 // b.buffer.tensor.element_size()
+            nvec = (b.hi - b.lo) // epv
+            per = -(-nvec // self.world_size)
+            lo = b.lo + min(nvec, per * self.reducer.rank) * epv
+            hi = b.lo + min(nvec, per * (self.reducer.rank + 1)) * epv
+            slices.setdefault(b.buffer.tensor.data_ptr(), []).append((lo, hi))
+        max_ranges = int(getattr(self.reducer.native, "SYMM_MAX_SHARD_RANGES", 48))
+        if any(len(v) > max_ranges for v in slices.values()):
+            logger.warning("too many buckets for slice-wise sharding; keeping the full all-reduce (raise --bucket-cap-mb)")
+            return
+        self._stepper.bucket_slices = slices
+        self._scatter_buckets = True
 
     def attach_optimizer(self, optimizer) -> None:
         """Build buckets over the flat gradient arenas and install gradient-ready hooks."""
@@ -284,6 +334,7 @@ class SymmDataParallel(nn.Module):
         self._covers_all_params = len(self._buckets) > 0 and all(p in self._param_bucket for p in trainable)
         if self._covers_all_params and hasattr(optimizer, "set_external_grad_sq_norm"):
             optimizer.set_external_grad_sq_norm(self.grad_sq_norm)
+        self._plan_bucket_slices()
 
     def grad_sq_norm(self):
         """Squared L2 norm of the (averaged) gradients of the step just reduced, or None if unavailable."""
@@ -311,7 +362,8 @@ class SymmDataParallel(nn.Module):
                 self._started = True
                 self._sq_valid = False
                 self._sq.tensor.zero_()
-            self.reducer(b.buffer, b.lo, b.hi - b.lo, scale=1.0 / self.world_size, sq_acc=self._sq.tensor)
+            self.reducer(b.buffer, b.lo, b.hi - b.lo, scale=1.0 / self.world_size, sq_acc=self._sq.tensor,
+                         scatter_only=self._scatter_buckets)
         b.launched = True
 
     def all_reduce_grads(self):
