@@ -405,3 +405,44 @@ def test_torch_seed_is_scoped_and_reproducible():
     with utils.torch_seed(5, 1, 3):
         inside_c = torch.rand(3)
     assert torch.equal(outside_a, outside_b) and torch.equal(inside_a, inside_b) and not torch.equal(inside_a, inside_c)
+
+
+def test_sharded_optimizer_range_planning():
+    """Pure-Python part of the (experimental) sharded optimizer step: every element of a flat group is owned by
+    exactly one rank, every range starts on a 16-byte boundary, for the contiguous shard and for bucket slices."""
+    from unicore_b200.parallel.symm_dp import ShardedAdamStepper
+
+    class _Flat:  # stands in for the flat parameter: only ``.grad.data_ptr()`` is consulted
+        class grad:  # noqa: N801
+            @staticmethod
+            def data_ptr():
+                return 4096
+
+    def stepper(rank, world):
+        s = ShardedAdamStepper.__new__(ShardedAdamStepper)
+        s.rank, s.world, s.bucket_slices = rank, world, {}
+        return s
+
+    for world in (2, 3, 8):
+        for numel in (8, 17, 1000003, 85056):
+            owned = []
+            for rank in range(world):
+                owned += stepper(rank, world).ranges(_Flat, numel)
+            owned.sort()
+            assert all(lo % 8 == 0 for lo, _ in owned)
+            assert [lo for lo, _ in owned] == [0] + [hi for _, hi in owned[:-1]] and owned[-1][1] == numel
+            # bucket slices (the kernels' formula: per = ceil(vectors / world) per bucket), clipped to the group
+            padded = -(-numel // 8) * 8
+            edges = list(range(0, padded, 4096)) + [padded]
+            owned = []
+            for rank in range(world):
+                s = stepper(rank, world)
+                s.bucket_slices[4096] = []
+                for lo, hi in zip(edges[:-1], edges[1:]):
+                    nvec = (hi - lo) // 8
+                    per = -(-nvec // world)
+                    s.bucket_slices[4096].append((lo + min(nvec, per * rank) * 8, lo + min(nvec, per * (rank + 1)) * 8))
+                owned += s.ranges(_Flat, numel)
+            owned.sort()
+            assert all(lo % 8 == 0 for lo, _ in owned)
+            assert [lo for lo, _ in owned] == [0] + [hi for _, hi in owned[:-1]] and owned[-1][1] == numel
