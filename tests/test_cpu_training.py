@@ -243,3 +243,26 @@ def test_fp16_overflow_skips_updates_and_lowers_the_scale(tmp_path):
     assert ck["optimizer_history"][-1]["num_updates"] == 3
     assert ck["last_optimizer_state"]["loss_scale"] < 2 ** 40
     assert all(torch.isfinite(v).all() for v in ck["model"].values())
+
+
+def test_loss_trajectory_matches_the_reference_trainer(tmp_path):
+    """Same initial weights (the state_dict loads into either implementation), same batches, dropout off: the
+    logged loss of six Adam updates (clipping, weight decay, polynomial schedule) is the reference trainer's."""
+    import json
+
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "unicore")):
+        pytest.skip("reference not installed under baseline/_ref")
+    tool = os.path.join(ROOT, "tools", "loss_parity.py")
+    init = str(tmp_path / "init.pt")
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    runs = {}
+    for impl in ("ours", "reference"):
+        out = subprocess.run([PY, tool, "--impl", impl, "--init", init, "--steps", "6"], env=env,
+                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-3000:]
+        runs[impl] = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    if "unavailable" in runs["reference"]:
+        pytest.skip(runs["reference"]["unavailable"])
+    ours, ref = runs["ours"]["losses"], runs["reference"]["losses"]
+    assert len(ours) == 6 and ours[-1] < ours[0]
+    assert ours == pytest.approx(ref, abs=2e-3), (ours, ref)
