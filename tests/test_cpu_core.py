@@ -446,3 +446,33 @@ def test_sharded_optimizer_range_planning():
             owned.sort()
             assert all(lo % 8 == 0 for lo, _ in owned)
             assert [lo for lo, _ in owned] == [0] + [hi for _, hi in owned[:-1]] and owned[-1][1] == numel
+
+
+def test_iterator_resume_with_a_different_world_size():
+    """A position saved by a 2-rank run is rescaled when the job resumes on 1 rank (and back): the restored
+    iterator has the remaining fraction of the epoch left (reference ``iterators.py:331-336``)."""
+    ds = _ListDataset(64, length=1)
+    batches = ds.batch_by_size(ds.ordered_indices(), batch_size=4)  # 16 batches
+
+    def make(num_shards, shard):
+        return EpochBatchIterator(ds, ds.collater, batches, seed=3, num_shards=num_shards, shard_id=shard)
+
+    two = make(2, 0)
+    assert len(two) == 8
+    itr = two.next_epoch_itr(shuffle=True)
+    for _ in range(2):
+        next(itr)
+    state = two.state_dict()
+    assert state["iterations_in_epoch"] == 2 and state["len"] == 8
+    one = make(1, 0)
+    assert len(one) == 16
+    one.load_state_dict(state)
+    rest = list(one.next_epoch_itr(shuffle=True))
+    assert len(rest) == 16 - 4  # a quarter of the epoch was consumed
+    back = make(2, 1)
+    one_state = {"epoch": 1, "iterations_in_epoch": 8, "shuffle": True, "len": 16}
+    back.load_state_dict(one_state)
+    assert len(list(back.next_epoch_itr(shuffle=True))) == 4
+    fresh = make(2, 0)
+    fresh.load_state_dict({"epoch": 3, "iterations_in_epoch": 0, "shuffle": True, "len": 8})
+    assert fresh.next_epoch_idx == 3 and len(list(fresh.next_epoch_itr(shuffle=True))) == 8

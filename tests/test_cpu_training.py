@@ -266,3 +266,17 @@ def test_loss_trajectory_matches_the_reference_trainer(tmp_path):
     ours, ref = runs["ours"]["losses"], runs["reference"]["losses"]
     assert len(ours) == 6 and ours[-1] < ours[0]
     assert ours == pytest.approx(ref, abs=2e-3), (ours, ref)
+
+
+@pytest.mark.parametrize("backend", ["c10d", "no_c10d"])
+def test_uneven_shards_use_a_dummy_batch(tmp_path, backend):
+    """3 batches over 2 ranks: the short rank trains on a dummy batch with zero weight so that the collective
+    schedule matches (reference ``trainer.py:913-918``); both epochs complete and the checkpoint is valid."""
+    save = str(tmp_path / "ck")
+    log = run_cli(["--save-dir", save, "--tmp-save-dir", save, "--disable-validation", "--synthetic-num-samples", "24",
+                   "--max-epoch", "2", "--ddp-backend", backend], nproc=2)
+    vals = losses_of(log)
+    assert len(vals) == 4 and all(v == v and v < 20 for v in vals)  # 2 updates per epoch, finite
+    ck = torch.load(os.path.join(save, "checkpoint_last.pt"), map_location="cpu", weights_only=False)
+    assert ck["optimizer_history"][-1]["num_updates"] == 4
+    assert all(torch.isfinite(v).all() for v in ck["model"].values())
