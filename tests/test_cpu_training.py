@@ -280,3 +280,14 @@ def test_uneven_shards_use_a_dummy_batch(tmp_path, backend):
     ck = torch.load(os.path.join(save, "checkpoint_last.pt"), map_location="cpu", weights_only=False)
     assert ck["optimizer_history"][-1]["num_updates"] == 4
     assert all(torch.isfinite(v).all() for v in ck["model"].values())
+
+
+def test_fp16_overflow_is_skipped_consistently_on_two_ranks(tmp_path):
+    """The overflow decision comes from the all-reduced gradients, so both ranks skip the same steps, lower the
+    scale together and never fall out of step (no hang, equal update counts)."""
+    save = str(tmp_path / "ck")
+    log = run_cli(["--save-dir", save, "--tmp-save-dir", save, "--disable-validation", "--max-update", "3", "--fp16",
+                   "--fp16-init-scale", str(2 ** 40), "--fp16-scale-window", "1000"], nproc=2)
+    assert "overflow" in log.lower() and len(losses_of(log)) >= 3
+    ck = torch.load(os.path.join(save, "checkpoint_last.pt"), map_location="cpu", weights_only=False)
+    assert ck["optimizer_history"][-1]["num_updates"] == 3 and ck["last_optimizer_state"]["loss_scale"] < 2 ** 40
