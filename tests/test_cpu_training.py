@@ -291,3 +291,20 @@ def test_fp16_overflow_is_skipped_consistently_on_two_ranks(tmp_path):
     assert "overflow" in log.lower() and len(losses_of(log)) >= 3
     ck = torch.load(os.path.join(save, "checkpoint_last.pt"), map_location="cpu", weights_only=False)
     assert ck["optimizer_history"][-1]["num_updates"] == 3 and ck["last_optimizer_state"]["loss_scale"] < 2 ** 40
+
+
+def test_two_rank_checkpoint_broadcast_and_resume(tmp_path):
+    """Rank 0 writes the checkpoint; on resume it reads the file and broadcasts model, optimizer and EMA state to
+    the other rank (reference ``trainer.py:300-345``); validation statistics are reduced over both ranks."""
+    save = str(tmp_path / "ck")
+    base = ["--save-dir", save, "--tmp-save-dir", save, "--ema-decay", "0.99", "--validate-interval-updates", "2",
+            "--save-interval-updates", "2", "--synthetic-num-samples", "64", "--fp16", "--fp16-init-scale", "4"]
+    first = run_cli(base + ["--max-update", "2"], nproc=2)
+    assert len(losses_of(first)) == 2 and "valid" in first
+    assert os.path.isfile(os.path.join(save, "checkpoint_last.pt"))
+    second = run_cli(base + ["--max-update", "4"], nproc=2)
+    assert "Loaded checkpoint" in second and "@ 2 updates" in second
+    resumed = losses_of(second)
+    assert len(resumed) == 2 and all(v == v for v in resumed)
+    ck = torch.load(os.path.join(save, "checkpoint_last.pt"), map_location="cpu", weights_only=False)
+    assert ck["optimizer_history"][-1]["num_updates"] == 4 and "ema" in ck
