@@ -1,6 +1,7 @@
 """Table-driven registration of the plain ``torch.optim`` optimizers (``sgd``, ``adagrad``, ``adadelta``).
 
-The reference ships one hand-written wrapper class per optimizer (``unicore/optim/{sgd,adagrad,adadelta}.py``);
+The reference ships one hand-written wrapper class per optimizer (``unicore/optim/sgd.py:13``, ``adagrad.py:13``,
+``adadelta.py:13``);
 they only differ in the torch class, the flags they contribute and how flags map to constructor keywords.
 Here that is data: ``_SPECS`` lists, per registry name, the torch class, its flags (``(dest, flag names,
 argparse keywords)``), the constructor-keyword -> ``args`` attribute mapping and whether the update works on a

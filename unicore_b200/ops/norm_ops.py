@@ -1,6 +1,8 @@
 """LayerNorm / RMSNorm with hand-written sm_100a forward and single-pass backward kernels.
 
-Replaces reference extensions N4-N7 (``csrc/layernorm``, ``csrc/rmsnorm``): any hidden size
+Replaces reference extensions N4-N7 (``csrc/layernorm/layernorm.cu:25-148``, ``layernorm_backward.cu:130-247``,
+``csrc/rmsnorm/rmsnorm.cu:25-125``, ``rmsnorm_backward.cu:108-196``; Python callers ``unicore/modules/layer_norm.py:22-48``,
+``rms_norm.py:24-56``): any hidden size
 (the reference supports 16 sizes), 128-bit accesses, fp32 statistics, and ONE backward kernel that
 reads ``x`` and ``dy`` once and produces ``dx`` plus ``dgamma``/``dbeta`` partials reduced by the
 last CTA (the reference reads them twice: dx kernel + two gamma/beta kernels).
