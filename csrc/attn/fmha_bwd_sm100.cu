@@ -1,4 +1,5 @@
-// Fused multi-head attention backward for sm_100a (head_dim 64, fp16/bf16), flash-attention style:
+// Fused multi-head attention backward for sm_100a (head_dim 64, fp16/bf16), flash-attention style
+// (reference: autograd through unicore/modules/multihead_attention.py:47-113 + softmax_fast.h:513-666):
 // probabilities are recomputed from the saved log-sum-exp; the dropout keep bits come from the
 // forward pass (1 bit / element).
 //

@@ -1,5 +1,7 @@
 // Fused multi-head attention forward for sm_100a (head_dim 64, fp16/bf16):
 //   O = dropout(softmax(scale * Q K^T + bias + key_padding)) V        LSE = logsumexp of the logits
+// One kernel for what the reference runs as bmm -> masked_fill -> softmax_dropout -> bmm plus four transposes
+// (unicore/modules/multihead_attention.py:47-113, csrc/softmax_dropout/softmax_fast.h:207-434).
 //
 // Tensor-core path: tcgen05.mma (cta_group::1, M=128) with fp32 accumulators in tensor memory.
 //   S (128 x 128 fp32) lives in TMEM columns [0,128), O (128 x 64 fp32) in columns [128,192).

@@ -1,7 +1,8 @@
 // LayerNorm / RMSNorm forward + single-pass backward, and the fused
 // "bias + dropout + residual + LayerNorm" block epilogue, for sm_100a.
 //
-// Replaces reference csrc/layernorm/{layernorm.cu,layernorm_backward.cu} and csrc/rmsnorm/*:
+// Replaces reference csrc/layernorm/layernorm.cu:25-148, layernorm_backward.cu:130-247, csrc/rmsnorm/rmsnorm.cu:25-125,
+// rmsnorm_backward.cu:108-196:
 //   * any hidden size that is a multiple of the 16-byte vector width (reference: 16 fixed sizes);
 //   * a row is owned by a group of TPR threads (TPR = 1..256, power of two, picked from the hidden
 //     size) that keeps the whole row in registers: VPT 16-byte vectors per thread; groups of <= 32

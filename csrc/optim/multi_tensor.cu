@@ -1,9 +1,9 @@
 // Multi-tensor optimizer kernels for sm_100a: L2 norm, scale, Adam (+16-bit write-back,
 // stochastic rounding, EMA, grad zeroing), fp32->bf16 stochastic rounding, EMA.
 //
-// Replaces reference csrc/adam/adam_kernel.cu (scalar accesses, one launch per tensor),
-// csrc/multi_tensor/* (chunk table by value + separate cleanup kernel) and
-// csrc/rounding/fp32_to_bf16.cu (curand_init per element).
+// Replaces reference csrc/adam/adam_kernel.cu:16-152 (scalar accesses, one launch per tensor),
+// csrc/multi_tensor/multi_tensor_l2norm_kernel.cu:27-118 (chunk table by value + separate cleanup kernel) and
+// csrc/rounding/fp32_to_bf16.cu:23-59 (curand_init per element).
 //
 // Design: up to 24 tensors per launch are described by value in the kernel parameter block.
 // Work is cut into fixed chunks of kChunk elements; a persistent grid walks the chunk list
