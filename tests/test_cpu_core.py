@@ -476,3 +476,82 @@ def test_iterator_resume_with_a_different_world_size():
     fresh = make(2, 0)
     fresh.load_state_dict({"epoch": 3, "iterations_in_epoch": 0, "shuffle": True, "len": 8})
     assert fresh.next_epoch_idx == 3 and len(list(fresh.next_epoch_itr(shuffle=True))) == 8
+
+
+def test_sharded_step_plumbing_matches_the_fused_step_on_cpu():
+    """Python side of the (experimental) sharded optimizer step, with a stand-in stepper that applies the reference
+    Adam math range by range: hyper-parameters, step counting, gradient zeroing and ``consolidate_state`` must leave
+    exactly what the replicated fused step leaves."""
+    from unicore.optim.fp16_optimizer import FP16Optimizer
+    from unicore.optim.fused_adam import FusedAdam
+    from unicore_b200.ops import optim_ops
+
+    class FakeStepper:
+        """Owns two ranges of every group; the complementary 'rank' is simulated by a second instance."""
+
+        def __init__(self, which):
+            self.which, self.calls, self.gathers = which, 0, 0
+
+        def ranges(self, flat, numel):
+            cut = (numel // 2) // 8 * 8
+            return [(0, cut)] if self.which == 0 else [(cut, numel)]
+
+        def step(self, flat, master, exp_avg, exp_avg_sq, *, grad_scale, stochastic_rounding=False, **hyper):
+            self.calls += 1
+            inv = 1.0 / grad_scale if not torch.is_tensor(grad_scale) else grad_scale.reciprocal()
+            for lo, hi in self.ranges(flat, master.numel()):
+                optim_ops._adam_reference_math(
+                    dict(p=master[lo:hi], g=flat.grad[lo:hi], m=exp_avg[lo:hi], v=exp_avg_sq[lo:hi],
+                         p_half=flat.data[lo:hi], **hyper), inv, False, stochastic_rounding)
+
+        def gather_(self, t, flat):
+            self.gathers += 1
+
+    def build():
+        torch.manual_seed(0)
+        args = bert_args(["--bf16", "--weight-decay", "0.01", "--clip-norm", "0"])
+        import bert  # noqa: F401
+        from unicore import tasks
+
+        task = tasks.setup_task(args)
+        model = task.build_model(args).bfloat16()
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        opt = FP16Optimizer.build_optimizer(args, named)
+        # the CPU build is unfused (torch Adam inside); the fused step itself has a PyTorch fallback, so give it the
+        # inner optimizer it expects and switch it on
+        inner = opt.fp32_optimizer.optimizer
+        groups = [dict(params=g["params"], lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"])
+                  for g in inner.param_groups]
+        opt.fp32_optimizer.optimizer = FusedAdam(groups)
+        opt._fused = True
+        return model, opt
+
+    def fill_grads(opt, seed):
+        g = torch.Generator().manual_seed(seed)
+        for group in opt.fp16_params:
+            for flat in group["params"]:
+                flat.grad.copy_(torch.randn(flat.numel(), generator=g).mul_(1e-2).to(flat.dtype))
+
+    ref_model, ref = build()
+    _, lo_half = build()
+    _, hi_half = build()
+    assert lo_half.enable_sharded_step(FakeStepper(0)) and hi_half.enable_sharded_step(FakeStepper(1))
+    for step in range(3):
+        for opt in (ref, lo_half, hi_half):
+            fill_grads(opt, 10 + step)
+            opt._multiply_factor = 0.5
+            opt._fused_step()
+            assert all(float(f.grad.abs().sum()) == 0 for g in opt.fp16_params for f in g["params"])  # zeroed
+    assert lo_half._sharded.calls == 3 * len(lo_half.fp16_params)
+    for (rf, rm), (lf, lm), (hf, hm) in zip(ref._pairs(), lo_half._pairs(), hi_half._pairs()):
+        n = rm.numel()
+        cut = (n // 2) // 8 * 8
+        assert torch.equal(rm.data[:cut], lm.data[:cut]) and torch.equal(rm.data[cut:], hm.data[cut:])
+        assert torch.equal(rf[0].data[:cut], lf[0].data[:cut]) and torch.equal(rf[0].data[cut:], hf[0].data[cut:])
+        assert not torch.equal(rm.data[cut:], lm.data[cut:])  # the other shard is stale until consolidated
+        inner_r, inner_l = ref.fp32_optimizer.optimizer, lo_half.fp32_optimizer.optimizer
+        assert inner_r._state_for(rm)["step"] == inner_l._state_for(lm)["step"] == 3
+        assert torch.equal(inner_r._state_for(rm)["exp_avg"][:cut], inner_l._state_for(lm)["exp_avg"][:cut])
+    lo_half.consolidate_state()
+    assert lo_half._sharded.gathers == 3 * len(lo_half.fp16_params)  # master + two moments per group
+    ref.consolidate_state()  # no-op for the replicated optimizer
