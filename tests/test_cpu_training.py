@@ -127,6 +127,24 @@ def _object_collectives_worker(rank, world, port):
     g = model.module.weight.grad.clone()
     gathered = du.all_gather_list(g)
     assert torch.equal(gathered[0], gathered[1]) and torch.allclose(g, torch.full_like(g, 3.0))
+    # sharded optimizer state: every rank holds its ranges, gather_ rebuilds the full vector everywhere
+    from unicore_b200.parallel.symm_dp import ShardedAdamStepper
+
+    stepper = ShardedAdamStepper.__new__(ShardedAdamStepper)
+    stepper.rank, stepper.world, stepper.group, stepper.bucket_slices = rank, world, None, {}
+
+    class _Flat:
+        class grad:  # noqa: N801
+            @staticmethod
+            def data_ptr():
+                return 0
+
+    full = torch.arange(37, dtype=torch.float32)
+    mine = torch.full((37,), -1.0)
+    for lo, hi in stepper.ranges(_Flat, 37):
+        mine[lo:hi] = full[lo:hi]
+    stepper.gather_(mine, _Flat)
+    assert torch.equal(mine, full)
     dist.barrier()
     dist.destroy_process_group()
 
