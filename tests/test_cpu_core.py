@@ -555,3 +555,43 @@ def test_sharded_step_plumbing_matches_the_fused_step_on_cpu():
     lo_half.consolidate_state()
     assert lo_half._sharded.gathers == 3 * len(lo_half.fp16_params)  # master + two moments per group
     ref.consolidate_state()  # no-op for the replicated optimizer
+
+
+def test_engine_plans_bucket_slices_like_the_kernels():
+    """``SymmDataParallel._plan_bucket_slices`` (mode 2 of the experimental sharded step) must hand the stepper the
+    slices the reduce-scatter kernels leave on this rank: vectors [begin + r*per, begin + (r+1)*per), per = ceil(n/world)."""
+    import types
+
+    from unicore_b200.parallel.symm_dp import SymmDataParallel, _Bucket
+
+    arena = torch.zeros(1000 * 8 + 8 * 3, dtype=torch.bfloat16)
+    buf = types.SimpleNamespace(tensor=arena)
+    edges = [0, 4096, 8024]
+    for world in (2, 4, 8):
+        covered = []
+        for rank in range(world):
+            eng = SymmDataParallel.__new__(SymmDataParallel)
+            eng._stepper = types.SimpleNamespace(bucket_slices={})
+            eng._shard_mode, eng._covers_all_params, eng.world_size = 2, True, world
+            eng.reducer = types.SimpleNamespace(rank=rank, native=types.SimpleNamespace(SYMM_MAX_SHARD_RANGES=48))
+            eng._buckets = [_Bucket(buf, lo, hi) for lo, hi in zip(edges[:-1], edges[1:])]
+            eng._plan_bucket_slices()
+            assert eng._scatter_buckets
+            slices = eng._stepper.bucket_slices[arena.data_ptr()]
+            for (lo, hi), (blo, bhi) in zip(slices, zip(edges[:-1], edges[1:])):
+                nvec = (bhi - blo) // 8
+                per = -(-nvec // world)
+                assert lo == blo + min(nvec, per * rank) * 8 and hi == blo + min(nvec, per * (rank + 1)) * 8
+            covered += slices
+        covered.sort()
+        assert covered[0][0] == 0 and covered[-1][1] == edges[-1]
+        total = sum(hi - lo for lo, hi in covered)
+        assert total == edges[-1]
+    # too many buckets for the kernel's range table: stay on the full all-reduce
+    eng = SymmDataParallel.__new__(SymmDataParallel)
+    eng._stepper = types.SimpleNamespace(bucket_slices={})
+    eng._shard_mode, eng._covers_all_params, eng.world_size = 2, True, 2
+    eng.reducer = types.SimpleNamespace(rank=0, native=types.SimpleNamespace(SYMM_MAX_SHARD_RANGES=2))
+    eng._buckets = [_Bucket(buf, i * 8, (i + 1) * 8) for i in range(5)]
+    eng._plan_bucket_slices()
+    assert not eng._scatter_buckets and eng._stepper.bucket_slices == {}
