@@ -595,3 +595,68 @@ def test_engine_plans_bucket_slices_like_the_kernels():
     eng._buckets = [_Bucket(buf, i * 8, (i + 1) * 8) for i in range(5)]
     eng._plan_bucket_slices()
     assert not eng._scatter_buckets and eng._stepper.bucket_slices == {}
+
+
+def test_engine_bucket_countdown_launches_each_bucket_once():
+    """Overlap logic of ``--ddp-backend b200`` without a GPU: gradient-ready hooks count every bucket of the flat
+    arena down and launch it exactly once, only after all parameters that overlap it have their gradients;
+    ``no_sync`` micro-batches launch nothing."""
+    import types
+
+    from unicore_b200.parallel.symm_dp import SymmDataParallel
+
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                                torch.nn.Linear(16, 4))
+    bufs = []
+
+    def grad_alloc(numel, dtype, device):
+        buf = types.SimpleNamespace(tensor=torch.zeros(-(-numel // 8) * 8, dtype=dtype))
+        bufs.append(buf)
+        return buf.tensor[:numel]
+
+    flats = flatten_parameters(list(model.parameters()), grad_alloc=grad_alloc)
+    optimizer = types.SimpleNamespace(fp16_params=[{"params": flats}])
+    eng = SymmDataParallel.__new__(SymmDataParallel)
+    torch.nn.Module.__init__(eng)
+    eng.module, eng._buffers, eng.bucket_bytes = model, bufs, 100 * 4  # 100-element buckets -> 96 after rounding
+    eng._hooks, eng._buckets, eng._param_bucket = [], [], {}
+    eng.accumulate_grads, eng.world_size = False, 2
+    eng.shard_optimizer, eng._shard_mode, eng._param_buffers, eng._stepper = False, 0, [], None
+    eng._scatter_buckets, eng._covers_all_params, eng._sq_valid, eng._started = False, False, False, False
+    eng.reducer = types.SimpleNamespace(rank=0)
+    ready, launched = set(), []
+
+    def fake_launch(bucket):
+        # every parameter overlapping this bucket must already have produced its gradient
+        base = flats[0].grad.data_ptr()
+        for p in model.parameters():
+            off = (p.grad.data_ptr() - base) // p.grad.element_size()
+            if off < bucket.hi and off + p.grad.numel() > bucket.lo:
+                assert id(p) in ready, "bucket launched before one of its gradients was ready"
+        launched.append((bucket.lo, bucket.hi))
+        bucket.launched = True
+
+    eng._launch = fake_launch
+    eng.attach_optimizer(optimizer)
+    assert eng._covers_all_params and len(eng._buckets) == -(-bufs[0].tensor.numel() // 96)
+    # record readiness just before the engine's own hook logic runs
+    inner = eng._on_grad_ready
+
+    def on_ready(p):
+        ready.add(id(p))
+        inner(p)
+
+    for h in eng._hooks:
+        h.remove()
+    eng._hooks = [p.register_post_accumulate_grad_hook(on_ready) for p in model.parameters()]
+    x = torch.randn(5, 8)
+    with eng.no_sync():
+        model(x).sum().backward()
+    assert launched == []  # accumulation micro-batch: no communication
+    ready.clear()
+    eng._reset_counters()
+    model(x).sum().backward()
+    assert sorted(launched) == [(b.lo, b.hi) for b in eng._buckets] and len(set(launched)) == len(launched)
+    first_lo = launched[0][0]
+    assert first_lo > 0  # the last layer's gradients arrive first: the arena is not reduced front to back
