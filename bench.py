@@ -41,6 +41,10 @@ def parse():
     ap.add_argument("--ema-decay", type=float, default=-1.0)
     ap.add_argument("--ddp-backend", default=None)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-ext", action="store_true",
+                    help="reference arm only: make the reference's OWN CUDA extensions importable (rebuilt with an sm_100 "
+                         "gencode into baseline/_ref_ext by baseline/build_ref_ext.sh) = BASELINE.md B2; the default "
+                         "reference arm is its stock install without extensions (B1)")
     ap.add_argument("--sync-overflow-check", action="store_true",
                     help="ours: read the grad norm on the host every step (reference behaviour) instead of the "
                          "deferred, device-side overflow skip")
@@ -164,7 +168,7 @@ def train_flags(a, world):
     return flags
 
 
-def setup_paths(impl):
+def setup_paths(impl, ref_ext=False):
     if impl == "reference":
         ref = os.path.join(REPO, "baseline", "_ref")
         if not os.path.isdir(os.path.join(ref, "unicore")):
@@ -174,6 +178,11 @@ def setup_paths(impl):
         # reference first, then its examples (so `import bert` finds the reference model), then stubs
         for p in (os.path.join(REPO, "baseline", "stubs"), os.path.join(ref, "examples"), ref):
             sys.path.insert(0, p)
+        if ref_ext:
+            ext = os.path.join(REPO, "baseline", "_ref_ext")
+            if not any(f.startswith("unicore_fused_layernorm") for f in (os.listdir(ext) if os.path.isdir(ext) else [])):
+                return "baseline/_ref_ext has no rebuilt reference extensions (run baseline/build_ref_ext.sh)"
+            sys.path.insert(0, ext)
         # make sure OUR packages are not importable on this arm
         sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != REPO]
         for mod in list(sys.modules):
@@ -271,7 +280,7 @@ def main():
     if world != a.gpus and world > 1:
         a.gpus = world
 
-    why = setup_paths(a.impl)
+    why = setup_paths(a.impl, a.ref_ext)
     if why is not None:
         if rank == 0:
             print(json.dumps({"impl": a.impl, "unavailable": why}))
@@ -386,6 +395,7 @@ def main():
             "metric": "{} masked-LM training throughput (samples/s, whole job, device-timed, max over ranks)".format(
                 {"bert_base": "BERT-base", "bert_large": "BERT-large"}.get(a.arch, a.arch)),
             "impl": a.impl,
+            "reference_cuda_ext": bool(a.ref_ext) if a.impl == "reference" else None,
             "value": value,
             "unit": "samples/s",
             "n_gpus": world,

@@ -111,9 +111,10 @@ void multi_tensor_adam(const std::vector<Tensor>& p, const std::vector<Tensor>& 
                        const std::vector<double>& beta2, const std::vector<double>& eps,
                        const std::vector<int64_t>& step, const std::vector<bool>& bias_correction,
                        const std::vector<double>& weight_decay, double grad_scale, const OptTensor& scale_dev,
-                       bool zero_grad, bool stochastic_rounding) {
+                       bool zero_grad, bool stochastic_rounding, const std::vector<OptTensor>& ema, double ema_decay) {
   const size_t n = p.size();
   TORCH_CHECK(n > 0 && g.size() == n && m.size() == n && v.size() == n && p_half.size() == n);
+  TORCH_CHECK(ema.empty() || ema.size() == n, "ema: one (optional) fp32 buffer per tensor");
   const c10::cuda::CUDAGuard guard(p[0].device());
   ub::AdamLaunch cfg{};
   cfg.inv_scale = (float)(1.0 / grad_scale);
@@ -124,7 +125,7 @@ void multi_tensor_adam(const std::vector<Tensor>& p, const std::vector<Tensor>& 
   }
   cfg.zero_grad = zero_grad ? 1 : 0;
   cfg.stochastic_rounding = stochastic_rounding ? 1 : 0;
-  cfg.ema_decay = 0.f;
+  cfg.ema_decay = (float)ema_decay;
   cfg.seed = cfg.offset = 0;
   if (stochastic_rounding) {
     auto so = philox_reserve(4);
@@ -159,6 +160,12 @@ void multi_tensor_adam(const std::vector<Tensor>& p, const std::vector<Tensor>& 
         t.half_dtype[k] = dtype_tag(*p_half[i]);
       }
       t.ema[k] = nullptr;
+      if (!ema.empty() && ema[i].has_value() && ema[i]->defined()) {
+        // EMA of the updated fp32 weights in the same pass: ema -= (1 - decay) * (ema - p)
+        check_cuda_contig(*ema[i], "adam ema");
+        TORCH_CHECK(ema[i]->scalar_type() == at::kFloat && ema[i]->numel() == p[i].numel(), "ema must be fp32, same length");
+        t.ema[k] = ema[i]->data_ptr<float>();
+      }
       t.numel[k] = p[i].numel();
       double step_size = lr[i];
       if (bias_correction[i]) {
@@ -683,6 +690,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> gbf_bwd(const Tensor& dy, const Tenso
 // defined in attn/fmha_bind.cpp and comm/comm_bind.cpp
 void register_fmha(pybind11::module_& m);
 void register_comm(pybind11::module_& m);
+void register_symm_mem(pybind11::module_& m);
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "unicore_b200 sm_100a kernels";
@@ -715,4 +723,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gbf_bwd", &gbf_bwd);
   register_fmha(m);
   register_comm(m);
+  register_symm_mem(m);
 }

@@ -677,6 +677,357 @@ __global__ void __launch_bounds__(1024) colsum_finalize_kernel(const float* __re
   }
 }
 
+// ================================================================================================
+// v3 kernels: ONE WARP PER ROW (or 32/LPR short rows per warp), no block-level synchronisation in the row loop.
+//
+// The v2 kernels spend their time in barriers: six __syncthreads per 8-row tile (stage hand-over plus the cross-warp
+// row reductions of a 96-thread row group) at 35 % of the HBM copy rate (profiles/elementwise_bench_r1.jsonl).  Here a
+// row of up to 32 * VPL 16-byte vectors is held by one warp - lane l owns vectors l, l + 32, ... - so the row
+// reductions are five shuffles, every load is a fully coalesced 512-byte warp request and nothing in the loop waits
+// for another warp.  A warp works on R rows at a time and already has the NEXT R rows in flight (register double
+// buffer, kPF).  Rows stay PACKED (16-bit) in registers and are converted again by each pass over them - conversions
+// are cheap, registers are what limits the bytes in flight; gamma / beta / bias are held packed as well.  Rows shorter
+// than 32 vectors are packed 32 / LPR to a warp (LPR = lanes per row, a power of two).  The backward keeps its
+// dgamma / dbeta (/ dbias) column accumulators in registers for the whole persistent loop and combines the CTA's warps
+// once at the end, in a fixed order (no atomics).
+// ================================================================================================
+constexpr int kNormV3Threads = 256;
+constexpr int kNormV3Warps = kNormV3Threads / 32;
+constexpr int kNormV3BwdThreads = 384;  // backward: 12 warps, one CTA per SM (168 registers: the column accumulators)
+constexpr int kNormV3BwdWarps = kNormV3BwdThreads / 32;
+constexpr int kNormV3MaxVPL = 4;  // longer rows (> 1024 16-bit elements) stay on the v2 kernels: the row no longer fits a warp's registers
+
+struct NormGeom3 {
+  int rows, cols, nvec;
+};
+
+template <int LPR>
+UB_DEVICE float row_sum(float v) {
+#pragma unroll
+  for (int o = LPR >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Forward.  The current row lives in fp32 registers (every pass after the first is pure math), the NEXT row is already
+// in flight as packed 16-bit vectors (kPF), gamma / beta / bias are NOT held in registers: they are re-read at their
+// single use per row from L1 (a 1.5 KB working set that never leaves it), which is two issue slots per eight elements
+// and frees 24-36 registers for occupancy.  kFull: the row is exactly 32 * VPL vectors - no per-vector predicates.
+// ncu of the first v3 (profiles/ncu_norm_v3.txt): 18 instructions per element, 64 % issue-slot utilisation at 53 % of
+// the copy rate - instruction-bound (re-conversion passes, predicate selects, register-copy double buffer, spills).
+template <typename T, int VPL, int LPR, int R, bool kPF, bool kRMS, bool kFused, bool kFull>
+__global__ void __launch_bounds__(kNormV3Threads, (VPL <= 3 ? 3 : (VPL == 4 ? 2 : 1))) norm_fwd_v3_kernel(
+    const T* __restrict__ x, const T* __restrict__ gamma, const T* __restrict__ beta, T* __restrict__ y,
+    float* __restrict__ mean_out, float* __restrict__ rstd_out, NormGeom3 g, float eps,
+    const T* __restrict__ bias, const T* __restrict__ residual, T* __restrict__ summed, float p, float keep_scale,
+    unsigned long long seed, unsigned long long offset) {
+  constexpr int EPV = VecTraits<T>::kElems;
+  constexpr int RW = 32 / LPR;  // short rows per warp
+  static_assert(LPR == 32 || VPL == 1, "short rows use one vector per lane");
+  static_assert(R == 1 || !kFused, "the fused variant works on one row group at a time");
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, j = lane % LPR;
+  const long long gw = (long long)blockIdx.x * kNormV3Warps + (threadIdx.x >> 5);
+  const long long stride = (long long)gridDim.x * kNormV3Warps * (RW * R);
+  const float inv_cols = 1.f / (float)g.cols;
+  const uint32_t thresh = kFused ? dropout_thresh16(p) : 0u;
+  const bool has_bias = kFused && bias != nullptr;
+
+  bool ok[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) ok[k] = kFull || (j + k * LPR < g.nvec);
+  const T* gam_p = gamma + (size_t)j * EPV;
+  const T* bet_p = kRMS ? nullptr : beta + (size_t)j * EPV;
+  const T* bia_p = has_bias ? bias + (size_t)j * EPV : nullptr;
+
+  auto fetch = [&](long long base, Vec16 (&xd)[R][VPL], Vec16 (&rd)[kFused ? R : 1][VPL]) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long r = base + i * RW + sub;
+      if (r < g.rows) {
+        const T* xp = x + (size_t)r * g.cols + (size_t)j * EPV;
+        const T* rp = kFused ? residual + (size_t)r * g.cols + (size_t)j * EPV : nullptr;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          if (ok[k]) {
+            xd[i][k] = ld_global_nc_v4(xp + k * (LPR * EPV));
+            if (kFused) rd[kFused ? i : 0][k] = ld_global_nc_v4(rp + k * (LPR * EPV));
+          }
+        }
+      }
+    }
+  };
+  long long base = gw * (RW * R);
+  Vec16 xv[R][VPL], rv[kFused ? R : 1][VPL];
+  fetch(base, xv, rv);
+  for (; base < g.rows; base += stride) {
+    float xs[R][VPL][EPV];
+    float acc[R];
+    // pass 1: convert (fused: bias + dropout + residual, store the rounded sum), row sum
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long row = base + i * RW + sub;
+      acc[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        if (row < g.rows && ok[k]) {
+          unpack<T>(xv[i][k], xs[i][k]);
+          if (kFused) {
+            const size_t off = (size_t)row * g.cols + (size_t)(j + k * LPR) * EPV;
+            float res[EPV];
+            unpack<T>(rv[kFused ? i : 0][k], res);
+            if (has_bias) {
+              float bf[EPV];
+              unpack<T>(ldv(bia_p + k * (LPR * EPV)), bf);
+#pragma unroll
+              for (int e = 0; e < EPV; ++e) xs[i][k][e] += bf[e];
+            }
+            uint32_t keep = 0xffu;
+            if (p > 0.f) keep = dropout_keep8(seed, offset, off / 8, thresh);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+              xs[i][k][e] = fmaf(xs[i][k][e], ((keep >> e) & 1u) ? keep_scale : 0.f, res[e]);
+            // the sum is rounded to T first: backward and the pre-LN consumer see exactly this value
+            const Vec16 sv = pack<T>(xs[i][k]);
+            st_global_v4(summed + off, sv);
+            unpack<T>(sv, xs[i][k]);
+          }
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) acc[i] += kRMS ? xs[i][k][e] * xs[i][k][e] : xs[i][k][e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) xs[i][k][e] = 0.f;
+        }
+      }
+    }
+    // the packed registers are free now: the next rows start their trip through the memory system
+    if (kPF) fetch(base + stride, xv, rv);
+#pragma unroll
+    for (int i = 0; i < R; ++i) acc[i] = row_sum<LPR>(acc[i]);
+    float mu[R], rs[R];
+    if (kRMS) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        mu[i] = 0.f;
+        rs[i] = rsqrtf(acc[i] * inv_cols + eps);
+      }
+    } else {
+      float var[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        mu[i] = acc[i] * inv_cols;
+        var[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          if (kFull || ok[k]) {
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+              xs[i][k][e] -= mu[i];  // centred values are what the output needs
+              var[i] = fmaf(xs[i][k][e], xs[i][k][e], var[i]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < R; ++i) rs[i] = rsqrtf(row_sum<LPR>(var[i]) * inv_cols + eps);
+    }
+    // pass 3: y = x_hat * gamma (+ beta); gamma / beta come from L1
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (kFull || ok[k]) {
+        float gf[EPV], bf[EPV];
+        unpack<T>(ldv(gam_p + k * (LPR * EPV)), gf);
+        if (!kRMS) unpack<T>(ldv(bet_p + k * (LPR * EPV)), bf);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const long long row = base + i * RW + sub;
+          if (row < g.rows) {
+            float o[EPV];
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+              const float xh = xs[i][k][e] * rs[i];
+              o[e] = kRMS ? xh * gf[e] : fmaf(xh, gf[e], bf[e]);
+            }
+            st_global_v4(y + (size_t)row * g.cols + (size_t)(j + k * LPR) * EPV, pack<T>(o));
+          }
+        }
+      }
+    }
+    if (j == 0) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const long long row = base + i * RW + sub;
+        if (row < g.rows) {
+          if (!kRMS) mean_out[row] = mu[i];
+          rstd_out[row] = rs[i];
+        }
+      }
+    }
+    if (!kPF) fetch(base + stride, xv, rv);
+  }
+}
+
+// part = [3][gridDim.x][cols] fp32 partial column sums (dgamma, dbeta, dbias of the fused op) - the layout of the v2
+// kernel, finished by colsum_finalize_kernel.  Dynamic shared memory: kNormV3BwdWarps * cols floats.
+template <typename T, int VPL, int LPR, int R, bool kPF, bool kRMS, bool kFused, bool kFull>
+__global__ void __launch_bounds__(kNormV3BwdThreads, (VPL <= 1 ? 2 : 1)) norm_bwd_v3_kernel(
+    const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const T* __restrict__ gamma, T* __restrict__ dx, float* __restrict__ part,
+    NormGeom3 g, T* __restrict__ dx_drop, int want_dbias, float p, float keep_scale, unsigned long long seed,
+    unsigned long long offset) {
+  constexpr int EPV = VecTraits<T>::kElems;
+  constexpr int RW = 32 / LPR;
+  static_assert(LPR == 32 || VPL == 1, "short rows use one vector per lane");
+  extern __shared__ __align__(16) float sm_cols[];  // [kNormV3BwdWarps][cols]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPR, j = lane % LPR;
+  const long long gw = (long long)blockIdx.x * kNormV3BwdWarps + warp;
+  const long long stride = (long long)gridDim.x * kNormV3BwdWarps * (RW * R);
+  const float inv_cols = 1.f / (float)g.cols;
+  const uint32_t thresh = kFused ? dropout_thresh16(p) : 0u;
+
+  bool ok[VPL];
+  float dg[VPL][EPV], db[VPL][EPV], dbi[kFused ? VPL : 1][EPV];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    ok[k] = kFull || (j + k * LPR < g.nvec);
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) {
+      dg[k][e] = db[k][e] = 0.f;
+      if (kFused) dbi[kFused ? k : 0][e] = 0.f;
+    }
+  }
+  const T* gam_p = gamma + (size_t)j * EPV;  // re-read from L1 at its use (see the forward kernel)
+
+  auto fetch = [&](long long base, Vec16 (&xd)[R][VPL], Vec16 (&dd)[R][VPL], float (&mu)[R], float (&rs)[R]) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long r = base + i * RW + sub;
+      mu[i] = 0.f;
+      rs[i] = 0.f;
+      if (r < g.rows) {
+        if (!kRMS) mu[i] = __ldg(mean + r);
+        rs[i] = __ldg(rstd + r);
+        const T* dp = dy + (size_t)r * g.cols + (size_t)j * EPV;
+        const T* xp = x + (size_t)r * g.cols + (size_t)j * EPV;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          if (ok[k]) {
+            dd[i][k] = ld_global_nc_v4(dp + k * (LPR * EPV));
+            xd[i][k] = ld_global_nc_v4(xp + k * (LPR * EPV));
+          }
+        }
+      }
+    }
+  };
+  long long base = gw * (RW * R);
+  Vec16 xv[R][VPL], dv[R][VPL];
+  float mu[R], rs[R];
+  fetch(base, xv, dv, mu, rs);
+  for (; base < g.rows; base += stride) {
+    // pass 1: x_hat and dy * gamma in fp32 registers, row sums, column accumulators
+    float xh[R][VPL][EPV], gy[R][VPL][EPV];
+    float s0[R], s1[R], rs_c[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) s0[i] = s1[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      float gf[EPV];
+      if (kFull || ok[k]) unpack<T>(ldv(gam_p + k * (LPR * EPV)), gf);
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const long long row = base + i * RW + sub;
+        if (row < g.rows && ok[k]) {
+          float xf[EPV], df[EPV];
+          unpack<T>(xv[i][k], xf);
+          unpack<T>(dv[i][k], df);
+          const float nmr = -mu[i] * rs[i];
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) {
+            xh[i][k][e] = fmaf(xf[e], rs[i], nmr);
+            gy[i][k][e] = df[e] * gf[e];
+            s0[i] += gy[i][k][e];
+            s1[i] = fmaf(gy[i][k][e], xh[i][k][e], s1[i]);
+            dg[k][e] = fmaf(df[e], xh[i][k][e], dg[k][e]);
+            if (!kRMS) db[k][e] += df[e];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) xh[i][k][e] = gy[i][k][e] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) rs_c[i] = rs[i];
+    // the packed registers are free: the next rows start their trip through the memory system
+    if (kPF) fetch(base + stride, xv, dv, mu, rs);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      if (!kRMS) s0[i] = row_sum<LPR>(s0[i]);
+      s1[i] = row_sum<LPR>(s1[i]);
+    }
+    // pass 2: dx = rstd * (gy - mean(gy) - x_hat * mean(gy * x_hat))
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long row = base + i * RW + sub;
+      if (row < g.rows) {
+        const float b0 = kRMS ? 0.f : -s0[i] * inv_cols * rs_c[i], c0 = -s1[i] * inv_cols * rs_c[i];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          if (kFull || ok[k]) {
+            const size_t off = (size_t)row * g.cols + (size_t)(j + k * LPR) * EPV;
+            float o[EPV];
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) o[e] = fmaf(xh[i][k][e], c0, fmaf(gy[i][k][e], rs_c[i], b0));
+            st_global_v4(dx + off, pack<T>(o));
+            if (kFused) {
+              uint32_t keep = 0xffu;
+              if (p > 0.f) keep = dropout_keep8(seed, offset, off / 8, thresh);
+#pragma unroll
+              for (int e = 0; e < EPV; ++e) {
+                o[e] = ((keep >> e) & 1u) ? o[e] * keep_scale : 0.f;
+                dbi[kFused ? k : 0][e] += o[e];
+              }
+              if (dx_drop != dx) st_global_v4(dx_drop + off, pack<T>(o));
+            }
+          }
+        }
+      }
+    }
+    if (!kPF) fetch(base + stride, xv, dv, mu, rs);
+  }
+
+  // column sums: sub-rows of a warp by shuffles, the CTA's warps through one shared-memory row each, then a fixed
+  // order sum per column -> one fp32 partial row per CTA and array (deterministic: no atomics anywhere)
+  const int narr = kFused && want_dbias ? 3 : (kRMS ? 1 : 2);
+  for (int a = 0; a < narr; ++a) {
+    if (a == 1 && kRMS) continue;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      float v[EPV];
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) {
+        v[e] = a == 0 ? dg[k][e] : (a == 1 ? db[k][e] : dbi[kFused ? k : 0][e]);
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
+      }
+      if ((kFull || ok[k]) && sub == 0) {
+        float* dst = sm_cols + (size_t)warp * g.cols + (size_t)(j + k * LPR) * EPV;
+#pragma unroll
+        for (int e = 0; e < EPV; e += 4) *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+      }
+    }
+    __syncthreads();
+    float* out = part + ((size_t)a * gridDim.x + blockIdx.x) * g.cols;
+    for (int c = threadIdx.x; c < g.cols; c += kNormV3BwdThreads) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kNormV3BwdWarps; ++w) s += sm_cols[(size_t)w * g.cols + c];
+      out[c] = s;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -740,19 +1091,116 @@ static int v2_grid(const NormGeom2& g, int R) {
 
 static int dtype_epv(int dtype) { return dtype == kF32 ? 4 : 8; }
 
+// ---- v3 geometry -----------------------------------------------------------------------------------------------------
+static bool make_geom3(int rows, int cols, int epv, NormGeom3& g, int& vpl, int& lpr) {
+  g.rows = rows;
+  g.cols = cols;
+  g.nvec = cols / epv;
+  if (g.nvec < 1 || cols % epv != 0) return false;
+  if (g.nvec <= 32) {
+    lpr = pow2ceil(g.nvec);
+    vpl = 1;
+  } else {
+    lpr = 32;
+    vpl = (g.nvec + 31) / 32;
+  }
+  return vpl <= kNormV3MaxVPL;
+}
+
+static int v3_rows_per_iter(int vpl, int lpr) { return (lpr == 32 && vpl == 1) ? 2 : 1; }
+
+// persistent grid: `per_sm` CTAs of 8 warps per SM, fewer when the rows do not fill them
+static int v3_grid(int rows, int lpr, int r, int warps, int per_sm) {
+  const int rows_per_cta = warps * (32 / lpr) * r;
+  const long long need = ((long long)rows + rows_per_cta - 1) / rows_per_cta;
+  const long long cap = (long long)sm_count() * per_sm;
+  const long long n = need < cap ? need : cap;
+  return (int)(n < 1 ? 1 : n);
+}
+static int v3_fwd_per_sm(int vpl) { return vpl <= 3 ? 3 : (vpl == 4 ? 2 : 1); }  // bwd: as many CTAs as fit (1 or 2 per SM); each emits one fp32 partial row per array
+static int v3_bwd_per_sm(int vpl) { return vpl <= 1 ? 2 : 1; }
+
 bool norm_v2_supported(int cols, int dtype) {
   NormGeom2 g;
-  return make_geom2(1, cols, dtype_epv(dtype), g);
+  NormGeom3 g3;
+  int vpl, lpr;
+  return make_geom3(1, cols, dtype_epv(dtype), g3, vpl, lpr) || make_geom2(1, cols, dtype_epv(dtype), g);
 }
 
 int norm_bwd_parts(int rows, int cols, int dtype) {
-  // one fp32 partial row per CTA (x3 arrays); at most 2 CTAs per SM keeps the finalize pass short
+  // one fp32 partial row per CTA (x3 arrays); few CTAs per SM keep the finalize pass short
+  NormGeom3 g3;
+  int vpl, lpr;
+  if (make_geom3(rows, cols, dtype_epv(dtype), g3, vpl, lpr)) return v3_grid(rows, lpr, v3_rows_per_iter(vpl, lpr), kNormV3BwdWarps, v3_bwd_per_sm(vpl));
   NormGeom2 g;
   if (make_geom2(rows, cols, dtype_epv(dtype), g)) return v2_grid(g, kBwdR);
   const long long cap = (long long)sm_count() * 2;
   const long long need = ((long long)rows + 7) / 8;
   long long n = need < cap ? need : cap;
   return (int)(n < 1 ? 1 : n);
+}
+
+// (vectors per lane, lanes per row) -> rows per warp iteration R and whether the next R rows are prefetched: about four
+// to six 16-byte vectors per lane and tensor in flight; very long rows (VPL >= 5) run without the register double buffer
+#define UB_V3_CASE(V, L, RR, PF, ...)                                                                     \
+  if (vpl == V && lpr == L) {                                                                             \
+    constexpr int VPL = V; constexpr int LPR = L; constexpr int R = RR; constexpr bool kPF = PF;          \
+    __VA_ARGS__;                                                                                          \
+    return true;                                                                                          \
+  }
+#define UB_DISPATCH_V3(...)                                                                               \
+  UB_V3_CASE(1, 1, 1, true, __VA_ARGS__) UB_V3_CASE(1, 2, 1, true, __VA_ARGS__)                           \
+  UB_V3_CASE(1, 4, 1, true, __VA_ARGS__) UB_V3_CASE(1, 8, 1, true, __VA_ARGS__)                           \
+  UB_V3_CASE(1, 16, 1, true, __VA_ARGS__) UB_V3_CASE(1, 32, 2, true, __VA_ARGS__)                         \
+  UB_V3_CASE(2, 32, 1, true, __VA_ARGS__) UB_V3_CASE(3, 32, 1, true, __VA_ARGS__)                         \
+  UB_V3_CASE(4, 32, 1, true, __VA_ARGS__)
+
+template <typename T, bool kRMS, bool kFused>
+static bool run_fwd_v3(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows,
+                       int cols, float eps, const void* bias, const void* residual, void* summed, float p,
+                       float keep_scale, unsigned long long seed, unsigned long long offset, cudaStream_t stream) {
+  NormGeom3 g;
+  int vpl, lpr;
+  if (!make_geom3(rows, cols, VecTraits<T>::kElems, g, vpl, lpr)) return false;
+  const int grid = v3_grid(rows, lpr, kFused ? 1 : v3_rows_per_iter(vpl, lpr), kNormV3Warps, v3_fwd_per_sm(vpl));
+  const bool full = g.nvec == vpl * lpr;
+  UB_DISPATCH_V3({
+    constexpr int RF = kFused ? 1 : R;
+    if (full)
+      norm_fwd_v3_kernel<T, VPL, LPR, RF, kPF, kRMS, kFused, true><<<grid, kNormV3Threads, 0, stream>>>(
+          (const T*)x, (const T*)gamma, (const T*)beta, (T*)y, mean, rstd, g, eps, (const T*)bias, (const T*)residual,
+          (T*)summed, p, keep_scale, seed, offset);
+    else
+      norm_fwd_v3_kernel<T, VPL, LPR, RF, kPF, kRMS, kFused, false><<<grid, kNormV3Threads, 0, stream>>>(
+          (const T*)x, (const T*)gamma, (const T*)beta, (T*)y, mean, rstd, g, eps, (const T*)bias, (const T*)residual,
+          (T*)summed, p, keep_scale, seed, offset);
+  });
+  return false;
+}
+
+template <typename T, bool kRMS, bool kFused>
+static bool run_bwd_v3(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma, void* dx,
+                       void* dgamma, void* dbeta, void* dbias, float* part, int rows, int cols, void* dx_drop, float p,
+                       float keep_scale, unsigned long long seed, unsigned long long offset, cudaStream_t stream) {
+  NormGeom3 g;
+  int vpl, lpr;
+  if (!make_geom3(rows, cols, VecTraits<T>::kElems, g, vpl, lpr)) return false;
+  const int grid = v3_grid(rows, lpr, v3_rows_per_iter(vpl, lpr), kNormV3BwdWarps, v3_bwd_per_sm(vpl));
+  const size_t smem = (size_t)kNormV3BwdWarps * cols * sizeof(float);
+  auto finish = [&]() {
+    colsum_finalize_kernel<T><<<dim3((cols + 31) / 32, 3), 1024, 0, stream>>>(part, grid, cols, (T*)dgamma, (T*)dbeta,
+                                                                              (T*)dbias);
+  };
+  const bool full = g.nvec == vpl * lpr;
+  UB_DISPATCH_V3({
+    auto kern = full ? norm_bwd_v3_kernel<T, VPL, LPR, R, (kPF && VPL <= 3), kRMS, kFused, true>
+                     : norm_bwd_v3_kernel<T, VPL, LPR, R, (kPF && VPL <= 3), kRMS, kFused, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kNormV3BwdThreads, smem, stream>>>((const T*)dy, (const T*)x, mean, rstd, (const T*)gamma, (T*)dx, part, g,
+                                                 (T*)dx_drop, dbias != nullptr ? 1 : 0, p, keep_scale, seed, offset);
+    finish();
+  });
+  return false;
 }
 
 #define UB_DISPATCH_VPT(VPT_VALUE, ...)                                   \
@@ -777,6 +1225,9 @@ static void run_fwd(const void* x, const void* gamma, const void* beta, void* y,
                     int cols, float eps, const void* bias, const void* residual, void* summed, float p,
                     unsigned long long seed, unsigned long long offset, cudaStream_t stream) {
   const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (run_fwd_v3<T, kRMS, kFused>(x, gamma, beta, y, mean, rstd, rows, cols, eps, bias, residual, summed, p, keep_scale,
+                                  seed, offset, stream))
+    return;
   NormGeom2 g2;
   if (make_geom2(rows, cols, VecTraits<T>::kElems, g2)) {
     auto fkern = norm_fwd_v2_kernel<T, kFwdR, kRMS, kFused>;
@@ -800,6 +1251,9 @@ static void run_bwd(const void* dy, const void* x, const float* mean, const floa
                     void* dgamma, void* dbeta, void* dbias, float* part, int rows, int cols, void* dx_drop, float p,
                     unsigned long long seed, unsigned long long offset, cudaStream_t stream) {
   const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (run_bwd_v3<T, kRMS, kFused>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dbias, part, rows, cols, dx_drop, p,
+                                  keep_scale, seed, offset, stream))
+    return;
   NormGeom2 g2;
   if (make_geom2(rows, cols, VecTraits<T>::kElems, g2)) {
     const int grid = v2_grid(g2, kBwdR);

@@ -407,47 +407,6 @@ def test_torch_seed_is_scoped_and_reproducible():
     assert torch.equal(outside_a, outside_b) and torch.equal(inside_a, inside_b) and not torch.equal(inside_a, inside_c)
 
 
-def test_sharded_optimizer_range_planning():
-    """Pure-Python part of the (experimental) sharded optimizer step: every element of a flat group is owned by
-    exactly one rank, every range starts on a 16-byte boundary, for the contiguous shard and for bucket slices."""
-    from unicore_b200.parallel.symm_dp import ShardedAdamStepper
-
-    class _Flat:  # stands in for the flat parameter: only ``.grad.data_ptr()`` is consulted
-        class grad:  # noqa: N801
-            @staticmethod
-            def data_ptr():
-                return 4096
-
-    def stepper(rank, world):
-        s = ShardedAdamStepper.__new__(ShardedAdamStepper)
-        s.rank, s.world, s.bucket_slices = rank, world, {}
-        return s
-
-    for world in (2, 3, 8):
-        for numel in (8, 17, 1000003, 85056):
-            owned = []
-            for rank in range(world):
-                owned += stepper(rank, world).ranges(_Flat, numel)
-            owned.sort()
-            assert all(lo % 8 == 0 for lo, _ in owned)
-            assert [lo for lo, _ in owned] == [0] + [hi for _, hi in owned[:-1]] and owned[-1][1] == numel
-            # bucket slices (the kernels' formula: per = ceil(vectors / world) per bucket), clipped to the group
-            padded = -(-numel // 8) * 8
-            edges = list(range(0, padded, 4096)) + [padded]
-            owned = []
-            for rank in range(world):
-                s = stepper(rank, world)
-                s.bucket_slices[4096] = []
-                for lo, hi in zip(edges[:-1], edges[1:]):
-                    nvec = (hi - lo) // 8
-                    per = -(-nvec // world)
-                    s.bucket_slices[4096].append((lo + min(nvec, per * rank) * 8, lo + min(nvec, per * (rank + 1)) * 8))
-                owned += s.ranges(_Flat, numel)
-            owned.sort()
-            assert all(lo % 8 == 0 for lo, _ in owned)
-            assert [lo for lo, _ in owned] == [0] + [hi for _, hi in owned[:-1]] and owned[-1][1] == numel
-
-
 def test_iterator_resume_with_a_different_world_size():
     """A position saved by a 2-rank run is rescaled when the job resumes on 1 rank (and back): the restored
     iterator has the remaining fraction of the epoch left (reference ``iterators.py:331-336``)."""
@@ -476,187 +435,3 @@ def test_iterator_resume_with_a_different_world_size():
     fresh = make(2, 0)
     fresh.load_state_dict({"epoch": 3, "iterations_in_epoch": 0, "shuffle": True, "len": 8})
     assert fresh.next_epoch_idx == 3 and len(list(fresh.next_epoch_itr(shuffle=True))) == 8
-
-
-def test_sharded_step_plumbing_matches_the_fused_step_on_cpu():
-    """Python side of the (experimental) sharded optimizer step, with a stand-in stepper that applies the reference
-    Adam math range by range: hyper-parameters, step counting, gradient zeroing and ``consolidate_state`` must leave
-    exactly what the replicated fused step leaves."""
-    from unicore.optim.fp16_optimizer import FP16Optimizer
-    from unicore.optim.fused_adam import FusedAdam
-    from unicore_b200.ops import optim_ops
-
-    class FakeStepper:
-        """Owns two ranges of every group; the complementary 'rank' is simulated by a second instance."""
-
-        def __init__(self, which):
-            self.which, self.calls, self.gathers = which, 0, 0
-
-        def ranges(self, flat, numel):
-            cut = (numel // 2) // 8 * 8
-            return [(0, cut)] if self.which == 0 else [(cut, numel)]
-
-        def step(self, flat, master, exp_avg, exp_avg_sq, *, grad_scale, stochastic_rounding=False, **hyper):
-            self.calls += 1
-            inv = 1.0 / grad_scale if not torch.is_tensor(grad_scale) else grad_scale.reciprocal()
-            for lo, hi in self.ranges(flat, master.numel()):
-                optim_ops._adam_reference_math(
-                    dict(p=master[lo:hi], g=flat.grad[lo:hi], m=exp_avg[lo:hi], v=exp_avg_sq[lo:hi],
-                         p_half=flat.data[lo:hi], **hyper), inv, False, stochastic_rounding)
-
-        def gather_(self, t, flat):
-            self.gathers += 1
-
-    def build():
-        torch.manual_seed(0)
-        args = bert_args(["--bf16", "--weight-decay", "0.01", "--clip-norm", "0"])
-        import bert  # noqa: F401
-        from unicore import tasks
-
-        task = tasks.setup_task(args)
-        model = task.build_model(args).bfloat16()
-        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
-        opt = FP16Optimizer.build_optimizer(args, named)
-        # the CPU build is unfused (torch Adam inside); the fused step itself has a PyTorch fallback, so give it the
-        # inner optimizer it expects and switch it on
-        inner = opt.fp32_optimizer.optimizer
-        groups = [dict(params=g["params"], lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"])
-                  for g in inner.param_groups]
-        opt.fp32_optimizer.optimizer = FusedAdam(groups)
-        opt._fused = True
-        return model, opt
-
-    def fill_grads(opt, seed):
-        g = torch.Generator().manual_seed(seed)
-        for group in opt.fp16_params:
-            for flat in group["params"]:
-                flat.grad.copy_(torch.randn(flat.numel(), generator=g).mul_(1e-2).to(flat.dtype))
-
-    ref_model, ref = build()
-    _, lo_half = build()
-    _, hi_half = build()
-    assert lo_half.enable_sharded_step(FakeStepper(0)) and hi_half.enable_sharded_step(FakeStepper(1))
-    for step in range(3):
-        for opt in (ref, lo_half, hi_half):
-            fill_grads(opt, 10 + step)
-            opt._multiply_factor = 0.5
-            opt._fused_step()
-            assert all(float(f.grad.abs().sum()) == 0 for g in opt.fp16_params for f in g["params"])  # zeroed
-    assert lo_half._sharded.calls == 3 * len(lo_half.fp16_params)
-    for (rf, rm), (lf, lm), (hf, hm) in zip(ref._pairs(), lo_half._pairs(), hi_half._pairs()):
-        n = rm.numel()
-        cut = (n // 2) // 8 * 8
-        assert torch.equal(rm.data[:cut], lm.data[:cut]) and torch.equal(rm.data[cut:], hm.data[cut:])
-        assert torch.equal(rf[0].data[:cut], lf[0].data[:cut]) and torch.equal(rf[0].data[cut:], hf[0].data[cut:])
-        assert not torch.equal(rm.data[cut:], lm.data[cut:])  # the other shard is stale until consolidated
-        inner_r, inner_l = ref.fp32_optimizer.optimizer, lo_half.fp32_optimizer.optimizer
-        assert inner_r._state_for(rm)["step"] == inner_l._state_for(lm)["step"] == 3
-        assert torch.equal(inner_r._state_for(rm)["exp_avg"][:cut], inner_l._state_for(lm)["exp_avg"][:cut])
-    lo_half.consolidate_state()
-    assert lo_half._sharded.gathers == 3 * len(lo_half.fp16_params)  # master + two moments per group
-    ref.consolidate_state()  # no-op for the replicated optimizer
-
-
-def test_engine_plans_bucket_slices_like_the_kernels():
-    """``SymmDataParallel._plan_bucket_slices`` (mode 2 of the experimental sharded step) must hand the stepper the
-    slices the reduce-scatter kernels leave on this rank: vectors [begin + r*per, begin + (r+1)*per), per = ceil(n/world)."""
-    import types
-
-    from unicore_b200.parallel.symm_dp import SymmDataParallel, _Bucket
-
-    arena = torch.zeros(1000 * 8 + 8 * 3, dtype=torch.bfloat16)
-    buf = types.SimpleNamespace(tensor=arena)
-    edges = [0, 4096, 8024]
-    for world in (2, 4, 8):
-        covered = []
-        for rank in range(world):
-            eng = SymmDataParallel.__new__(SymmDataParallel)
-            eng._stepper = types.SimpleNamespace(bucket_slices={})
-            eng._shard_mode, eng._covers_all_params, eng.world_size = 2, True, world
-            eng.reducer = types.SimpleNamespace(rank=rank, native=types.SimpleNamespace(SYMM_MAX_SHARD_RANGES=48))
-            eng._buckets = [_Bucket(buf, lo, hi) for lo, hi in zip(edges[:-1], edges[1:])]
-            eng._plan_bucket_slices()
-            assert eng._scatter_buckets
-            slices = eng._stepper.bucket_slices[arena.data_ptr()]
-            for (lo, hi), (blo, bhi) in zip(slices, zip(edges[:-1], edges[1:])):
-                nvec = (bhi - blo) // 8
-                per = -(-nvec // world)
-                assert lo == blo + min(nvec, per * rank) * 8 and hi == blo + min(nvec, per * (rank + 1)) * 8
-            covered += slices
-        covered.sort()
-        assert covered[0][0] == 0 and covered[-1][1] == edges[-1]
-        total = sum(hi - lo for lo, hi in covered)
-        assert total == edges[-1]
-    # too many buckets for the kernel's range table: stay on the full all-reduce
-    eng = SymmDataParallel.__new__(SymmDataParallel)
-    eng._stepper = types.SimpleNamespace(bucket_slices={})
-    eng._shard_mode, eng._covers_all_params, eng.world_size = 2, True, 2
-    eng.reducer = types.SimpleNamespace(rank=0, native=types.SimpleNamespace(SYMM_MAX_SHARD_RANGES=2))
-    eng._buckets = [_Bucket(buf, i * 8, (i + 1) * 8) for i in range(5)]
-    eng._plan_bucket_slices()
-    assert not eng._scatter_buckets and eng._stepper.bucket_slices == {}
-
-
-def test_engine_bucket_countdown_launches_each_bucket_once():
-    """Overlap logic of ``--ddp-backend b200`` without a GPU: gradient-ready hooks count every bucket of the flat
-    arena down and launch it exactly once, only after all parameters that overlap it have their gradients;
-    ``no_sync`` micro-batches launch nothing."""
-    import types
-
-    from unicore_b200.parallel.symm_dp import SymmDataParallel
-
-    torch.manual_seed(0)
-    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
-                                torch.nn.Linear(16, 4))
-    bufs = []
-
-    def grad_alloc(numel, dtype, device):
-        buf = types.SimpleNamespace(tensor=torch.zeros(-(-numel // 8) * 8, dtype=dtype))
-        bufs.append(buf)
-        return buf.tensor[:numel]
-
-    flats = flatten_parameters(list(model.parameters()), grad_alloc=grad_alloc)
-    optimizer = types.SimpleNamespace(fp16_params=[{"params": flats}])
-    eng = SymmDataParallel.__new__(SymmDataParallel)
-    torch.nn.Module.__init__(eng)
-    eng.module, eng._buffers, eng.bucket_bytes = model, bufs, 100 * 4  # 100-element buckets -> 96 after rounding
-    eng._hooks, eng._buckets, eng._param_bucket = [], [], {}
-    eng.accumulate_grads, eng.world_size = False, 2
-    eng.shard_optimizer, eng._shard_mode, eng._param_buffers, eng._stepper = False, 0, [], None
-    eng._scatter_buckets, eng._covers_all_params, eng._sq_valid, eng._started = False, False, False, False
-    eng.reducer = types.SimpleNamespace(rank=0)
-    ready, launched = set(), []
-
-    def fake_launch(bucket):
-        # every parameter overlapping this bucket must already have produced its gradient
-        base = flats[0].grad.data_ptr()
-        for p in model.parameters():
-            off = (p.grad.data_ptr() - base) // p.grad.element_size()
-            if off < bucket.hi and off + p.grad.numel() > bucket.lo:
-                assert id(p) in ready, "bucket launched before one of its gradients was ready"
-        launched.append((bucket.lo, bucket.hi))
-        bucket.launched = True
-
-    eng._launch = fake_launch
-    eng.attach_optimizer(optimizer)
-    assert eng._covers_all_params and len(eng._buckets) == -(-bufs[0].tensor.numel() // 96)
-    # record readiness just before the engine's own hook logic runs
-    inner = eng._on_grad_ready
-
-    def on_ready(p):
-        ready.add(id(p))
-        inner(p)
-
-    for h in eng._hooks:
-        h.remove()
-    eng._hooks = [p.register_post_accumulate_grad_hook(on_ready) for p in model.parameters()]
-    x = torch.randn(5, 8)
-    with eng.no_sync():
-        model(x).sum().backward()
-    assert launched == []  # accumulation micro-batch: no communication
-    ready.clear()
-    eng._reset_counters()
-    model(x).sum().backward()
-    assert sorted(launched) == [(b.lo, b.hi) for b in eng._buckets] and len(set(launched)) == len(launched)
-    first_lo = launched[0][0]
-    assert first_lo > 0  # the last layer's gradients arrive first: the arena is not reduced front to back

@@ -127,24 +127,22 @@ def _object_collectives_worker(rank, world, port):
     g = model.module.weight.grad.clone()
     gathered = du.all_gather_list(g)
     assert torch.equal(gathered[0], gathered[1]) and torch.allclose(g, torch.full_like(g, 3.0))
-    # sharded optimizer state: every rank holds its ranges, gather_ rebuilds the full vector everywhere
-    from unicore_b200.parallel.symm_dp import ShardedAdamStepper
+    # sharded optimizer state: every rank holds its slices compactly, to_full rebuilds the full vector everywhere
+    from unicore_b200.parallel.fused_tail import FusedTail
+    from unicore_b200.parallel.reference_tail import PlainComm, _PlainBuffer
 
-    stepper = ShardedAdamStepper.__new__(ShardedAdamStepper)
-    stepper.rank, stepper.world, stepper.group, stepper.bucket_slices = rank, world, None, {}
-
-    class _Flat:
-        class grad:  # noqa: N801
-            @staticmethod
-            def data_ptr():
-                return 0
-
-    full = torch.arange(37, dtype=torch.float32)
-    mine = torch.full((37,), -1.0)
-    for lo, hi in stepper.ranges(_Flat, 37):
-        mine[lo:hi] = full[lo:hi]
-    stepper.gather_(mine, _Flat)
-    assert torch.equal(mine, full)
+    n = 4096 + 40
+    comm = PlainComm(None, "cpu")
+    make = lambda: [_PlainBuffer(torch.zeros(n, dtype=torch.bfloat16), rank, world)]  # noqa: E731
+    tail = FusedTail(comm, make(), make(), bucket_bytes=1024)
+    full = torch.arange(n - 5, dtype=torch.float32)
+    compact = tail.to_compact(full, 0)
+    assert 0 < compact.numel() < n and torch.equal(tail.to_full(compact, 0, n - 5), full)
+    ema = full.clone()
+    for lo, hi in tail.owned_ranges(0, rank=1 - rank):
+        ema[lo:min(hi, ema.numel())] = -1.0  # the other rank's slices are stale here
+    tail.scatter_owned_(ema, 0)
+    assert torch.equal(ema, full)
     dist.barrier()
     dist.destroy_process_group()
 

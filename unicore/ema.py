@@ -66,6 +66,12 @@ class ExponentialMovingAverageModel:
                 if name in self.name2param:
                     self.update_one_param(self.name2param[name], p)
 
+    @torch.no_grad()
+    def reset_from(self, model) -> None:
+        """Restart the average from ``model``'s current weights (a checkpoint without EMA state was loaded)."""
+        source = dict(model.state_dict())
+        self.model_ema.load_state_dict({k: v.float() if torch.is_floating_point(v) else v for k, v in source.items()})
+
     def load_state_dict(self, state_dict):
         self.model_ema.load_state_dict(state_dict["params"])
         self.decay = state_dict["decay"] if "decay" in state_dict else self.decay

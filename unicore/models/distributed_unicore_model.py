@@ -25,8 +25,13 @@ def DistributedUnicoreModel(args, model, process_group, device):
     backend = args.ddp_backend
     on_cuda = device.type == "cuda"
     if backend == "b200":
-        from unicore_b200.parallel import SymmDataParallel, symm_available
+        from unicore_b200.parallel import SymmDataParallel, reference_tail_requested, symm_available
 
+        if reference_tail_requested():
+            from unicore_b200.parallel.reference_tail import ReferenceTailEngine
+
+            bucket_mb = float(getattr(args, "bucket_cap_mb", 25))
+            return ModuleProxyWrapper(ReferenceTailEngine(model.to(device), process_group, bucket_cap_mb=bucket_mb))
         if on_cuda and symm_available():
             wrapped = SymmDataParallel(model.to(device), process_group, bucket_cap_mb=args.bucket_cap_mb)
             return ModuleProxyWrapper(wrapped)

@@ -23,6 +23,8 @@ logger = logging.getLogger(__name__)
 class UnicoreAdam(UnicoreOptimizer):
     def __init__(self, args, params):
         super().__init__(args)
+        from unicore_b200.parallel import reference_tail_requested
+
         fused_cls = get_fused_adam_class()
         use_fused = (
             not getattr(args, "use_old_adam", False)
@@ -30,6 +32,10 @@ class UnicoreAdam(UnicoreOptimizer):
             and torch.cuda.is_available()
             and not getattr(args, "cpu", False)
         )
+        if reference_tail_requested() and not getattr(args, "use_old_adam", False):
+            from unicore.optim.fused_adam import FusedAdam
+
+            fused_cls, use_fused = FusedAdam, True  # (its kernel call has a PyTorch fallback)
         if use_fused:
             logger.info("using FusedAdam (sm_100a multi-tensor kernel)")
             self._optimizer = fused_cls(params, **self.optimizer_config)

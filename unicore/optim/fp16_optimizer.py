@@ -136,7 +136,9 @@ def flatten_parameters_fp32(params, set_to_param=False, set_grad=True):
     """One flat fp32 copy of ``params`` (dtype-major, same padding). With ``set_to_param`` the
     params themselves become views of it (used by the EMA shadow model)."""
     by_dtype, order, total = flatten_orders(params)
-    flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+    # the storage is a whole number of 32-byte groups (8 floats): kernels that walk the arena in 8-element vectors may
+    # touch the slack behind the last parameter
+    flat = torch.zeros(pad_numel(total, 8), dtype=torch.float32, device=params[0].device)[:total]
     ordered = [p for dtype in order for p in by_dtype[dtype]]
     for p, off, n in _slots(ordered):
         flat[off:off + n].copy_(p.data.reshape(-1))
@@ -176,31 +178,153 @@ class _FP16OptimizerMixin(object):
         self.bf16_sr = getattr(args, "bf16_sr", False)
         self._grads_zeroed = False
 
-    # -- sharded step (experimental, --ddp-backend b200 with UNICORE_B200_SHARD_OPTIMIZER=1) -----------------
-    def enable_sharded_step(self, stepper) -> bool:
-        """``stepper`` (``unicore_b200.parallel.symm_dp.ShardedAdamStepper``) runs Adam on this rank's 1/N shard
-        of every flat group and all-gathers the new parameters inside the same kernel.  Only the shard of the fp32
-        master / moments is current on a rank afterwards; ``consolidate_state`` (a collective) refreshes the rest."""
+    # -- fused tail (--ddp-backend b200): reduce-scatter tail + norm/stat exchange + clip + Adam(+EMA) on the shard +
+    #    parameter all-gather in ONE kernel, see unicore_b200/parallel/fused_tail.py ------------------------------------
+    _tail = None
+    _tail_engine = None
+
+    def enable_fused_tail(self, engine, tail) -> bool:
+        """``tail`` (``FusedTail``) owns the shard geometry; ``engine.run_tail(**kw)`` launches the kernel behind the
+        step's bucket kernels.  From here on the fp32 master weights and the Adam moments of this rank are COMPACT
+        shards (1/world of the state); ``state_dict()`` re-assembles the reference layout with collectives."""
         if not self._fused or any(len(g["params"]) != 1 for g in self.fp16_params):
             return False
-        self._sharded = stepper
+        inner = self.fp32_optimizer.optimizer
+        if not hasattr(inner, "_state_for"):
+            return False
+        self._tail, self._tail_engine = tail, engine
+        self._tail_full_numel = []
+        for gi, (_flats16, master) in enumerate(self._pairs()):
+            self._tail_full_numel.append(master.numel())
+            state = inner.state.get(master, None)
+            moments = None
+            if state is not None and "exp_avg" in state:
+                moments = (tail.to_compact(state["exp_avg"], gi), tail.to_compact(state["exp_avg_sq"], gi))
+            master.data = tail.to_compact(master.data, gi)
+            master.grad = None
+            if moments is not None:
+                state["exp_avg"], state["exp_avg_sq"] = moments
+        self._tail_max_norm = 0.0
+        self._tail_stats = None
+        self._tail_stats_len = 0
+        self._tail_denom_index = -1
+        self._ema_flats, self._ema_decay = None, 0.0
         return True
 
-    def consolidate_state(self):
-        """All ranks: gather the shards of master / exp_avg / exp_avg_sq so that ``state_dict()`` is complete."""
-        stepper = getattr(self, "_sharded", None)
-        if stepper is None:
+    @property
+    def uses_fused_tail(self) -> bool:
+        return self._tail is not None
+
+    def attach_ema(self, ema_flats, decay: float) -> bool:
+        """Fused tail only: the EMA update (``ema -= (1-d)(ema - w)`` on the fp32 master) moves into the kernel.
+        ``ema_flats[g]``: the full-length fp32 EMA arena of group g; a rank keeps ITS slices current."""
+        if self._tail is None:
+            return False
+        self._ema_flats, self._ema_decay = list(ema_flats), float(decay)
+        return True
+
+    def set_step_stats(self, values, denom_index: int = -1) -> None:
+        """Fused tail only: ``values`` (<= 64 numbers / device scalars) are summed over the ranks INSIDE the tail kernel;
+        the gradients are divided by sum number ``denom_index`` (the sample size).  Read them with ``step_stats()``."""
+        self._tail_stats, self._tail_denom_index = values, int(denom_index)
+        self._tail_stats_len = int(values.numel()) if torch.is_tensor(values) else len(values)
+
+    def step_stats(self):
+        """fp64 device vector with the rank sums of the statistics handed to ``set_step_stats`` (valid after ``step``;
+        a copy - the kernel's output buffer is overwritten by the next update)."""
+        return self._tail.stats_dst[:self._tail_stats_len].clone()
+
+    def step_grad_norm(self):
+        """The gradient norm the last ``step`` computed on the device (a copy of the tail's state slot)."""
+        return self._tail.state[0].clone()
+
+    def attach_replicated_ema(self, ema_flats, decay: float) -> bool:
+        """Replicated fused Adam: the EMA update rides in the Adam kernel's pass over the master weights instead of
+        being a separate sweep (reference ``unicore/ema.py:44-60``)."""
+        if self._tail is not None or not self._fused or any(len(g["params"]) != 1 for g in self.fp16_params):
+            return False
+        flats = list(ema_flats)
+        if len(flats) != len(self.fp32_params) or any(
+                f.numel() != g["params"][0].numel() for f, g in zip(flats, self.fp32_params)):
+            return False
+        self._replicated_ema = (flats, float(decay))
+        return True
+
+    @torch.no_grad()
+    def gather_ema(self) -> None:
+        """COLLECTIVE (fused tail): merge the ranks' slices of the EMA arenas so that every rank holds all of it."""
+        if self._tail is None or self._ema_flats is None:
             return
+        for gi, flat in enumerate(self._ema_flats):
+            self._tail.scatter_owned_(flat.data, gi)
+
+    @torch.no_grad()
+    def sync_master_from_params(self) -> None:
+        """Rebuild the fp32 master weights from the 16-bit model weights (after a checkpoint load)."""
+        for gi, (flats16, master) in enumerate(self._pairs()):
+            if self._tail is not None:
+                master.data.copy_(self._tail.to_compact(flats16[0].data.float(), gi))
+            else:
+                offset = 0
+                for f in flats16:
+                    master.data[offset:offset + f.numel()].copy_(f.data)
+                    offset += f.numel()
+
+    @torch.no_grad()
+    def consolidate_state(self) -> None:
+        """COLLECTIVE - call on EVERY rank before the master rank takes ``state_dict()`` (``checkpoint_utils`` does):
+        with the fused tail the ranks' shards of the Adam moments are assembled into the reference's full-length layout
+        (kept until the next update) and the EMA slices are merged.  No-op for the replicated optimizers."""
+        if self._tail is None:
+            return
+        self.resolve_pending_overflow()
         inner = self.fp32_optimizer.optimizer
-        for flats16, master in self._pairs():
-            state = inner._state_for(master)
-            for t in (master.data, state["exp_avg"], state["exp_avg_sq"]):
-                stepper.gather_(t, flats16[0])
+        self._consolidated = {}
+        for gi, (_f, master) in enumerate(self._pairs()):
+            state = inner.state.get(master, None)
+            if not state or "exp_avg" not in state:
+                continue
+            n = self._tail_full_numel[gi]
+            self._consolidated[gi] = tuple(self._tail.to_full(state[name], gi, n) for name in ("exp_avg", "exp_avg_sq"))
+        self.gather_ema()
+
+    def _tail_full_state(self, state):
+        """The inner optimizer's state dict with the full-length (reference layout) moments of ``consolidate_state``."""
+        inner = self.fp32_optimizer.optimizer
+        index = {id(master): gi for gi, (_f, master) in enumerate(self._pairs())}
+        packed = state["state"]
+        # torch packs state by parameter index in group order: one master per group, in order
+        order = [p for g in inner.param_groups for p in g["params"]]
+        full = getattr(self, "_consolidated", None)
+        for key, p in enumerate(order):
+            if key in packed and id(p) in index and "exp_avg" in packed[key]:
+                gi = index[id(p)]
+                if full is None or gi not in full:
+                    raise RuntimeError("sharded optimizer state: call consolidate_state() on every rank before state_dict()")
+                entry = dict(packed[key])
+                entry["exp_avg"], entry["exp_avg_sq"] = full[gi]
+                packed[key] = entry
+        return state
+
+    def _tail_reshard_loaded_state(self):
+        inner = self.fp32_optimizer.optimizer
+        for gi, (_f, master) in enumerate(self._pairs()):
+            state = inner.state.get(master, None)
+            if not state:
+                continue
+            for name in ("exp_avg", "exp_avg_sq"):
+                t = state.get(name, None)
+                if torch.is_tensor(t) and t.numel() != master.numel():
+                    state[name] = self._tail.to_compact(t.to(device=master.device, dtype=torch.float32), gi)
 
     # -- state ----------------------------------------------------------------------------------
     def state_dict(self):
+        """Reference schema (``unicore/optim/fp16_optimizer.py:163-178``).  With the fused tail the moments come from the
+        preceding ``consolidate_state()`` (a collective that every rank runs; only the master goes on to save)."""
         self.resolve_pending_overflow()
         state = self.fp32_optimizer.state_dict()
+        if self._tail is not None:
+            state = self._tail_full_state(state)
         if self.scaler is not None:
             state["loss_scale"] = self.scaler.loss_scale
         return state
@@ -209,6 +333,8 @@ class _FP16OptimizerMixin(object):
         if "loss_scale" in state_dict and self.scaler is not None:
             self.scaler.loss_scale = state_dict["loss_scale"]
         self.fp32_optimizer.load_state_dict(state_dict, optimizer_overrides)
+        if self._tail is not None:
+            self._tail_reshard_loaded_state()
 
     # -- backward -------------------------------------------------------------------------------
     def backward(self, loss):
@@ -314,6 +440,11 @@ class _FP16OptimizerMixin(object):
 
     def clip_grad_norm(self, max_norm, aggregate_norm_fn=None):
         """Fold clipping into ``_multiply_factor``; returns the un-scaled, pre-clip grad norm."""
+        if self._tail is not None:
+            # norm, clip coefficient and overflow decision are taken inside the tail kernel; the returned device scalar
+            # is filled in by ``step()`` (a "future": consumers read it after the update was launched)
+            self._tail_max_norm = float(max_norm)
+            return self._tail.state[0]
         raw = self._raw_grad_norm()
         grad_norm = self._multiply_factor * raw
         if aggregate_norm_fn is not None:
@@ -324,7 +455,8 @@ class _FP16OptimizerMixin(object):
             self.resolve_pending_overflow()
             factor = self._multiply_factor
             if max_norm > 0.0:
-                factor = factor * (max_norm / (grad_norm + 1e-6)).clamp_(max=1.0)
+                # fp16 path of the reference: ``if grad_norm > max_norm: factor *= max_norm / grad_norm`` (no epsilon)
+                factor = factor * torch.where(grad_norm > max_norm, max_norm / grad_norm, torch.ones_like(grad_norm))
             factor = torch.as_tensor(factor, dtype=torch.float32, device=grad_norm.device)
             self._multiply_factor = factor
             self._device_grad_scale = torch.where(
@@ -362,24 +494,41 @@ class _FP16OptimizerMixin(object):
         self._late_overflow_handlers.append(fn)
 
     def resolve_pending_overflow(self) -> None:
+        """Settle the update that was launched last: tell the loss scaler (exactly ONE tick per update: ``update()`` for a
+        finite norm, ``check_overflow()`` otherwise) and take back the optimistic bookkeeping of a skipped update."""
         pending = getattr(self, "_pending_norm", None)
         if pending is None:
             return
         self._pending_norm = None
-        norm_host = float(pending.get())
+        value = pending.get()
+        if self._tail is not None:  # the tail's state vector {grad_norm, multiplier, overflow, sum of squares}
+            norm_host = float(value[0]) if float(value[2]) == 0.0 else float("inf")
+        else:
+            norm_host = float(value)
+        self._last_grad_norm = norm_host
+        if self.scaler is None:
+            if norm_host != norm_host or abs(norm_host) == float("inf"):
+                self._undo_skipped_update("gradients are Nan/Inf")
+                raise FloatingPointError("gradients are Nan/Inf")
+            return
         try:
             self.scaler.check_overflow(norm_host)
         except OverflowError as exc:
-            # the device skipped that update (non-finite divisor): undo the optimistic host bookkeeping
-            inner = self.fp32_optimizer.optimizer
-            for _, master in self._pairs():
-                state = inner.state.get(master, None)
-                if state is not None and state.get("step", 0) > 0:
-                    state["step"] -= 1
-            if getattr(self, "_grads_zeroed", False) and not self._has_accumulated:
-                self._multiply_factor = 1.0 / float(self.scaler.loss_scale)
-            for fn in getattr(self, "_late_overflow_handlers", []):
-                fn(str(exc))
+            self._undo_skipped_update(str(exc))
+            return
+        self.scaler.update()
+
+    def _undo_skipped_update(self, message: str) -> None:
+        # the device skipped that update (non-finite divisor): undo the optimistic host bookkeeping
+        inner = self.fp32_optimizer.optimizer
+        for _, master in self._pairs():
+            state = inner.state.get(master, None)
+            if state is not None and state.get("step", 0) > 0:
+                state["step"] -= 1
+        if getattr(self, "_grads_zeroed", False) and not self._has_accumulated and self.scaler is not None:
+            self._multiply_factor = 1.0 / float(self.scaler.loss_scale)
+        for fn in getattr(self, "_late_overflow_handlers", []):
+            fn(message)
 
     # -- update ---------------------------------------------------------------------------------
     def step(self, closure=None, groups=None):
@@ -395,17 +544,18 @@ class _FP16OptimizerMixin(object):
                 self._unscale_grads()
                 self.fp32_optimizer.step(closure, groups=groups)
             self._sync_fp32_params_to_fp16()
-        if self.scaler is not None:
-            self.scaler.update()
+        if self.scaler is not None and getattr(self, "_pending_norm", None) is None:
+            self.scaler.update()  # (deferred / tail mode: the scaler is ticked when the outcome is known)
         self._has_accumulated = False
 
     def _fused_step(self):
         """unscale+clip, Adam on fp32 master, 16-bit write-back (+SR) and grad zeroing: one launch."""
         from unicore import ops
 
-        if getattr(self, "_sharded", None) is not None:
-            return self._sharded_fused_step()
+        if self._tail is not None:
+            return self._tail_step()
         inner = self.fp32_optimizer.optimizer
+        ema = getattr(self, "_replicated_ema", None)  # [(flat per group)], decay: the EMA pass rides in the Adam kernel
         work = []
         for (flats16, master), group in zip(self._pairs(), inner.param_groups):
             state = inner._state_for(master)
@@ -421,6 +571,8 @@ class _FP16OptimizerMixin(object):
                     step=state["step"], bias_correction=bool(group.get("bias_correction", True)),
                     weight_decay=group["weight_decay"],
                 ))
+                if ema is not None:
+                    work[-1]["ema"] = ema[0][len(work) - 1].data
                 offset += n
         factor = self._multiply_factor
         grad_scale = getattr(self, "_device_grad_scale", None)
@@ -432,31 +584,54 @@ class _FP16OptimizerMixin(object):
             grad_scale=grad_scale,
             zero_grad=True,
             stochastic_rounding=self.bf16_sr,
+            ema_decay=(ema[1] if ema is not None else None),
         )
         self._grads_zeroed = True
         self._needs_sync = False
 
-    def _sharded_fused_step(self):
-        """Same contract as ``_fused_step``; the kernel touches only this rank's shard and broadcasts the result."""
+    def _tail_step(self):
+        """Same contract as ``_fused_step``, but the whole tail - including what is left of the gradient reduction, the
+        norm, the clip / overflow decision and the statistics - is the ONE kernel of ``fused_tail.py``."""
+        from unicore_b200.parallel.fused_tail import adam_hyper
+
         inner = self.fp32_optimizer.optimizer
-        factor = self._multiply_factor
-        grad_scale = getattr(self, "_device_grad_scale", None)
-        self._device_grad_scale = None
-        if grad_scale is None:
-            grad_scale = (1.0 / factor) if not torch.is_tensor(factor) else factor.reciprocal()
-        for (flats16, master), group in zip(self._pairs(), inner.param_groups):
-            flat = flats16[0]
+        self._consolidated = None  # (a checkpoint's full-length copy of the moments is stale from here on)
+        masters, avgs, sqs, hypers = [], [], [], []
+        for (_flats16, master), group in zip(self._pairs(), inner.param_groups):
             state = inner._state_for(master)
             state["step"] += 1
             beta1, beta2 = group["betas"]
-            self._sharded.step(
-                flat, master.data, state["exp_avg"], state["exp_avg_sq"], lr=group["lr"], beta1=beta1, beta2=beta2,
-                eps=group["eps"], step=state["step"], bias_correction=bool(group.get("bias_correction", True)),
-                weight_decay=group["weight_decay"], grad_scale=grad_scale, stochastic_rounding=self.bf16_sr,
-            )
-            flat.grad.zero_()
+            masters.append(master.data)
+            avgs.append(state["exp_avg"])
+            sqs.append(state["exp_avg_sq"])
+            hypers.append(adam_hyper(group["lr"], beta1, beta2, group["eps"], state["step"],
+                                     bool(group.get("bias_correction", True)), group["weight_decay"]))
+        factor = self._multiply_factor
+        if torch.is_tensor(factor):
+            raise RuntimeError("fused tail: device-side gradient factors go through set_step_stats(denom_index=...)")
+        stats = self._tail_stats
+        if stats is not None and not torch.is_tensor(stats):
+            stats = utils.stack_scalars(stats, device=masters[0].device)
+        state_vec = self._tail_engine.run_tail(
+            masters=masters, exp_avgs=avgs, exp_avg_sqs=sqs, hypers=hypers, factor=float(factor),
+            max_norm=self._tail_max_norm, clip_eps=0.0 if self.scaler is not None else 1e-6,
+            emas=self._ema_flats, ema_decay=self._ema_decay, stats_src=stats, denom_index=self._tail_denom_index,
+            stochastic_rounding=self.bf16_sr,
+        )
+        self._tail_stats, self._tail_denom_index = None, -1
         self._grads_zeroed = True
         self._needs_sync = False
+        self._pending_norm = utils.AsyncHostRead(state_vec)
+        if not getattr(self.args, "deferred_overflow_check", False):
+            # reference behaviour: the caller learns about an overflow from this very call
+            skipped = []
+            self._late_overflow_handlers, saved = [skipped.append], getattr(self, "_late_overflow_handlers", [])
+            try:
+                self.resolve_pending_overflow()
+            finally:
+                self._late_overflow_handlers = saved
+            if skipped:
+                raise OverflowError(skipped[0])
 
     def zero_grad(self):
         """Zero the flat grads and reset the deferred factor to ``1/loss_scale``."""
@@ -517,9 +692,12 @@ class FP16Optimizer(_FP16OptimizerMixin, UnicoreOptimizer):
         if getattr(args, "fp16_no_flatten_grads", False):
             raise ValueError("--fp16-no-flatten-grads is not supported: flat arenas are the design")
         params = list(params)
+        from unicore_b200.parallel import reference_tail_requested
+
         on_cuda = len(params) > 0 and params[0][1].is_cuda
         want_fused = (
-            on_cuda and ops.HAS_CUDA_EXT and getattr(args, "optimizer", "adam") == "adam"
+            ((on_cuda and ops.HAS_CUDA_EXT) or reference_tail_requested())
+            and getattr(args, "optimizer", "adam") == "adam"
             and not getattr(args, "use_old_adam", False)
             and not getattr(args, "allreduce_fp32_grad", False)
             and getattr(args, "per_sample_clip_norm", 0) <= 0

@@ -113,16 +113,19 @@ _host_reader = _HostReader()
 
 
 class AsyncHostRead:
-    """A device scalar on its way to the host: the copy is enqueued now, ``get()`` is called later
-    (normally long after the copy has completed, so it does not stall anything)."""
+    """Device value(s) on their way to the host: the copy is enqueued now, ``get()`` is called later (normally long
+    after the copy has completed, so it does not stall anything).  A one-element tensor yields a python number, a
+    longer one a list."""
 
     def __init__(self, t: torch.Tensor):
         self._value = None
+        self._scalar = t.numel() == 1
         if not t.is_cuda:
-            self._value = t.detach().reshape(-1)[0].item()
+            flat = t.detach().reshape(-1)
+            self._value = flat[0].item() if self._scalar else flat.tolist()
             return
-        self._buf = torch.empty(1, dtype=t.dtype, pin_memory=True)
-        self._buf.copy_(t.detach().reshape(-1)[:1], non_blocking=True)
+        self._buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+        self._buf.copy_(t.detach().reshape(-1), non_blocking=True)
         self._event = torch.cuda.Event()
         self._event.record(torch.cuda.current_stream(t.device))
 
@@ -133,8 +136,43 @@ class AsyncHostRead:
         if self._value is None:
             while not self._event.query():
                 pass
-            self._value = self._buf[0].item()
+            self._value = self._buf[0].item() if self._scalar else self._buf.tolist()
         return self._value
+
+
+def stack_scalars(values, device=None, dtype=torch.float64) -> torch.Tensor:
+    """A list of python numbers and 0-dim tensors as ONE 1-D tensor on ``device``, in order, with as few launches as
+    possible: host numbers travel together in one pinned buffer, device scalars are stacked per dtype."""
+    values = list(values)
+    n = len(values)
+    dev_idx = [i for i, v in enumerate(values) if torch.is_tensor(v) and v.is_cuda]
+    if device is None:
+        device = values[dev_idx[0]].device if dev_idx else torch.device("cpu")
+    device = torch.device(device)
+    host_idx = [i for i in range(n) if i not in set(dev_idx)]
+    host_vals = [float(values[i]) if not torch.is_tensor(values[i]) else float(values[i].item()) for i in host_idx]
+    if not dev_idx:
+        return torch.tensor(host_vals, dtype=dtype).to(device, non_blocking=True)
+    parts, order = [], []
+    by_dtype = {}
+    for i in dev_idx:
+        by_dtype.setdefault(values[i].dtype, []).append(i)
+    for dt, idx in by_dtype.items():
+        parts.append(torch.stack([values[i].detach().reshape(()) for i in idx]).to(dtype))
+        order += idx
+    if host_idx:
+        host = torch.tensor(host_vals, dtype=dtype)
+        if device.type == "cuda":
+            host = host.pin_memory()
+        parts.append(host.to(device, non_blocking=True))
+        order += host_idx
+    packed = torch.cat(parts) if len(parts) > 1 else parts[0]
+    if order == list(range(n)):
+        return packed
+    inverse = [0] * n
+    for pos, i in enumerate(order):
+        inverse[i] = pos
+    return packed[torch.tensor(inverse, device=device)]
 
 
 def item(t):
@@ -557,6 +595,9 @@ def validate_with_ema(trainer, ema=False):
     if not ema:
         yield
         return
+    sync = getattr(trainer, "sync_ema_shards", None)
+    if sync is not None:
+        sync()  # (collective: a sharded EMA is merged on every rank before it is evaluated)
     live_model = trainer._wrapped_model
     shadow = copy.deepcopy(trainer.ema.model_ema)
     if trainer.args.fp16:

@@ -58,7 +58,7 @@ def multi_tensor_scale_(tensors: Sequence[torch.Tensor], scale: Scalar) -> None:
 # ------------------------------------------------------------------------------------------------
 # Adam
 # ------------------------------------------------------------------------------------------------
-def _adam_reference_math(w: Dict, inv_scale, zero_grad: bool, stochastic_rounding: bool) -> None:
+def _adam_reference_math(w: Dict, inv_scale, zero_grad: bool, stochastic_rounding: bool, ema_decay=None) -> None:
     """FusedAdam semantics in plain PyTorch (fp32 math), used on CPU."""
     p, g, m, v = w["p"], w["g"], w["m"], w["v"]
     beta1, beta2, eps, lr, wd, step = w["beta1"], w["beta2"], w["eps"], w["lr"], w["weight_decay"], w["step"]
@@ -79,13 +79,15 @@ def _adam_reference_math(w: Dict, inv_scale, zero_grad: bool, stochastic_roundin
             fp32_to_bf16_sr(p32, half)
         else:
             half.copy_(p32)
+    if w.get("ema") is not None and ema_decay is not None:
+        w["ema"].sub_(w["ema"] - p32, alpha=1.0 - ema_decay)
     if zero_grad:
         g.zero_()
 
 
 @torch.no_grad()
 def fused_adam(work: List[Dict], grad_scale: Scalar = 1.0, zero_grad: bool = False,
-               stochastic_rounding: bool = False) -> None:
+               stochastic_rounding: bool = False, ema_decay=None) -> None:
     """Adam update for a list of tensors in ONE launch.
 
     Each ``work`` item: ``p`` (fp32 master, or half/bf16 param), ``g`` (grad, any float dtype),
@@ -94,7 +96,9 @@ def fused_adam(work: List[Dict], grad_scale: Scalar = 1.0, zero_grad: bool = Fal
     (python float or device scalar) inside the kernel; a device scalar that is non-finite or zero
     makes the whole update skip itself (overflowed gradients, see ``--deferred-overflow-check``).  ``zero_grad`` clears ``g`` in the same
     pass; ``stochastic_rounding`` applies to bf16 ``p_half`` outputs (Philox keyed by the CUDA
-    generator's seed/offset so all data-parallel ranks round identically).
+    generator's seed/offset so all data-parallel ranks round identically).  A work item may carry ``ema`` (fp32,
+    same length as ``p``): with ``ema_decay`` given, ``ema -= (1 - decay) * (ema - p_new)`` happens in the same pass
+    (reference: a separate three-kernel sweep, ``unicore/ema.py:44-60``).
     """
     if len(work) == 0:
         return
@@ -113,6 +117,7 @@ def fused_adam(work: List[Dict], grad_scale: Scalar = 1.0, zero_grad: bool = Fal
             [float(w["eps"]) for w in work], [int(w["step"]) for w in work],
             [bool(w["bias_correction"]) for w in work], [float(w["weight_decay"]) for w in work],
             scale_f, inv, bool(zero_grad), bool(stochastic_rounding),
+            [w.get("ema") for w in work] if ema_decay is not None else [], float(ema_decay or 0.0),
         )
         return
     if torch.is_tensor(grad_scale):
@@ -124,7 +129,7 @@ def fused_adam(work: List[Dict], grad_scale: Scalar = 1.0, zero_grad: bool = Fal
             return
     inv_scale = (1.0 / grad_scale) if not torch.is_tensor(grad_scale) else grad_scale.reciprocal()
     for w in work:
-        _adam_reference_math(w, inv_scale, zero_grad, stochastic_rounding)
+        _adam_reference_math(w, inv_scale, zero_grad, stochastic_rounding, ema_decay)
 
 
 # ------------------------------------------------------------------------------------------------
