@@ -45,6 +45,7 @@ def parse():
                     help="reference arm only: make the reference's OWN CUDA extensions importable (rebuilt with an sm_100 "
                          "gencode into baseline/_ref_ext by baseline/build_ref_ext.sh) = BASELINE.md B2; the default "
                          "reference arm is its stock install without extensions (B1)")
+    ap.add_argument("--report-losses", action="store_true", help="add the losses read back in the end-to-end region")
     ap.add_argument("--sync-overflow-check", action="store_true",
                     help="ours: read the grad norm on the host every step (reference behaviour) instead of the "
                          "deferred, device-side overflow skip")
@@ -334,6 +335,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    seen_losses = []
+
     def run_steps(batches, n, read_loss):
         last = None
         for i in range(n):
@@ -341,6 +344,7 @@ def main():
             if read_loss and out is not None:
                 v = out.get("loss", None)
                 last = float(v) if v is not None else None  # device -> host read of the step result
+                seen_losses.append(last)
         return last
 
     # ---- warm-up (builds optimizer, allocator high-water mark, cuBLAS heuristics, loss scale) ----
@@ -417,10 +421,14 @@ def main():
                 "vocab": a.vocab,
                 "parallelism": "dp{}".format(world),
                 "ddp_backend": getattr(args, "ddp_backend", None),
-                "optimizer": "adam(0.9,0.98) clip 1.0 polynomial_decay, {}{}".format(
-                    "fp16 dynamic loss scale" if a.precision == "fp16" else "bf16 (no loss scaling)",
-                    " (overflow skip decided on the device, scaler updated before the next backward)"
-                    if (a.impl != "reference" and a.precision == "fp16" and not a.sync_overflow_check) else ""),
+                "optimizer": "adam(0.9,0.98) clip 1.0 polynomial_decay, {}".format(
+                    "fp16 dynamic loss scale" if a.precision == "fp16" else "bf16 (no loss scaling)"),
+                "overflow_check": "host read every step (reference behaviour)"
+                if (a.impl == "reference" or a.precision != "fp16" or a.sync_overflow_check)
+                else "decided on the device; the loss scaler is told before the next backward",
+                "optimizer_tail": "fused (one kernel after backward)"
+                if getattr(getattr(trainer, "optimizer", None), "uses_fused_tail", False) else "replicated",
+                "ema_decay": a.ema_decay if a.ema_decay > 0 else None,
                 "l2": "no explicit flush: each step streams >1.7 GB of weights/optimizer state/activations, "
                       "far above the 126 MB L2, and 8 distinct input batches rotate",
             },
@@ -428,6 +436,8 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches,
         }
+        if a.report_losses:
+            result["losses"] = seen_losses[:16]
         print(json.dumps(result))
     if world > 1:
         dist.barrier()

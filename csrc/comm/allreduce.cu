@@ -44,7 +44,6 @@ template <typename T>
 __global__ void __launch_bounds__(kCommThreads) allreduce_oneshot_kernel(CommPeers peers, long long begin_vec,
                                                                           long long end_vec, float scale, float* sq_out) {
   constexpr int EPV = 16 / sizeof(T);
-  if (comm_failed(peers)) return;
   // (the handshake kernel ahead of us in the stream established that every rank's producers finished)
   const long long v = begin_vec + (long long)blockIdx.x * kCommThreads + threadIdx.x;
   const bool active = v < end_vec;
@@ -86,7 +85,6 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_twoshot_kernel(CommPee
                                                                           long long end_vec, float scale, float* sq_out) {
   constexpr int EPV = 16 / sizeof(T);
   constexpr int kU = 16 / W;
-  if (comm_failed(peers)) return;
   const long long n = end_vec - begin_vec;
   const long long per = (n + peers.world - 1) / peers.world;
   long long lo = begin_vec + per * peers.rank;
@@ -141,7 +139,6 @@ template <typename T, bool kScatterOnly = false>
 __global__ void __launch_bounds__(kCommThreads) allreduce_nvls_kernel(CommPeers peers, long long begin_vec,
                                                                         long long end_vec, float scale, float* sq_out) {
   constexpr int EPV = 16 / sizeof(T);
-  if (comm_failed(peers)) return;
   const long long n = end_vec - begin_vec;
   const long long per = (n + peers.world - 1) / peers.world;
   long long lo = begin_vec + per * peers.rank;

@@ -140,8 +140,11 @@ void symm_fused_tail(const std::vector<int64_t>& xchg_ptrs, const std::vector<in
     G.exp_avg_sq = exp_avg_sq[g].data_ptr<float>();
     G.ema = nullptr;
     if (ema[g].has_value() && ema[g]->defined()) {
+      // (the arena view may end a few elements before the padded length; its STORAGE must cover the padding)
+      const int64_t room = (int64_t)(ema[g]->storage().nbytes() / sizeof(float)) - ema[g]->storage_offset();
       TORCH_CHECK(ema[g]->is_cuda() && ema[g]->scalar_type() == at::kFloat && ema[g]->is_contiguous() &&
-                  ema[g]->numel() >= numel[g] && (reinterpret_cast<uintptr_t>(ema[g]->data_ptr()) & 15) == 0);
+                      room >= numel[g] && (reinterpret_cast<uintptr_t>(ema[g]->data_ptr()) & 15) == 0,
+                  "EMA arena: fp32, 16-byte aligned, storage of at least the padded arena length");
       G.ema = ema[g]->data_ptr<float>();
     }
     TORCH_CHECK(numel[g] % 8 == 0, "arena lengths must be multiples of 8 elements");

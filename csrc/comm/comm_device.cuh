@@ -37,19 +37,28 @@ UB_DEVICE void comm_fail(const CommPeers& peers, uint32_t code, uint32_t detail)
 // A flag carries the caller's TAG (bucket index / kernel kind, never zero) instead of a bare 1: two ranks that pair up
 // on different collectives - e.g. gradient buckets launched in a different order - see a foreign tag and fail loudly
 // instead of reducing unrelated data.
+// The error word lives in HOST memory (a read costs a PCIe round trip): it is looked at only by a thread that has been
+// spinning for a while, never on the fast path - a healthy barrier costs exactly one flag round trip over NVLink.
+constexpr int kSpinsPerHealthCheck = 2048;
+
 UB_DEVICE bool flag_put(const CommPeers& peers, uint32_t* addr, uint32_t tag) {
   const long long t0 = clock64();
+  int spins = 0;
   while (atomicCAS_system(addr, 0u, tag) != 0u) {
     __nanosleep(32);
-    if (clock64() - t0 > 20000000000LL) {
-      comm_fail(peers, kCommTimeout, tag);
-      return false;
+    if (++spins % kSpinsPerHealthCheck == 0) {
+      if (comm_failed(peers)) return false;  // somebody (this GPU, earlier) already gave up: do not wait again
+      if (clock64() - t0 > 20000000000LL) {
+        comm_fail(peers, kCommTimeout, tag);
+        return false;
+      }
     }
   }
   return true;
 }
 UB_DEVICE bool flag_take(const CommPeers& peers, uint32_t* addr, uint32_t tag) {
   const long long t0 = clock64();
+  int spins = 0;
   for (;;) {
     const uint32_t seen = atomicCAS_system(addr, tag, 0u);
     if (seen == tag) return true;
@@ -58,9 +67,12 @@ UB_DEVICE bool flag_take(const CommPeers& peers, uint32_t* addr, uint32_t tag) {
       return false;
     }
     __nanosleep(32);  // keep the polling traffic off the links the data kernels of other buckets use
-    if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died; do not hang the GPU forever
-      comm_fail(peers, kCommTimeout, tag);
-      return false;
+    if (++spins % kSpinsPerHealthCheck == 0) {
+      if (comm_failed(peers)) return false;
+      if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died; do not hang the GPU forever
+        comm_fail(peers, kCommTimeout, tag);
+        return false;
+      }
     }
   }
 }
@@ -82,7 +94,7 @@ UB_DEVICE bool slot_barrier(const CommPeers& peers, int slot, bool release_first
     uint32_t* remote = reinterpret_cast<uint32_t*>(peers.flags[t]) + slot * peers.world + peers.rank;
     uint32_t* mine = reinterpret_cast<uint32_t*>(peers.flags[peers.rank]) + slot * peers.world + t;
     const uint32_t tag = peers.tag == 0u ? 1u : peers.tag;
-    if (comm_failed(peers) || !flag_put(peers, remote, tag) || !flag_take(peers, mine, tag)) ok_s = 0;
+    if (!flag_put(peers, remote, tag) || !flag_take(peers, mine, tag)) ok_s = 0;
   }
   __syncthreads();
   __threadfence_system();

@@ -330,7 +330,6 @@ __global__ void __launch_bounds__(kCommThreads) fused_tail_kernel(TailArgs A) {
 // ---- stand-alone statistics reduction (validation steps, replicated-optimizer fallback) ------------------------------
 __global__ void __launch_bounds__(kMaxStats) stats_allreduce_kernel(CommPeers x, const double* __restrict__ src,
                                                                     double* __restrict__ dst, int k, int parity) {
-  if (comm_failed(x)) return;
   const int rank = x.rank, world = x.world;
   for (int idx = threadIdx.x; idx < world * k; idx += kMaxStats) {
     const int p = idx / k, j = idx - p * k;

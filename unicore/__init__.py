@@ -8,7 +8,7 @@ import sys
 
 from .version import __version__  # noqa: F401
 
-__all__ = ["pdb"]
+__all__ = []
 
 from unicore.distributed import utils as distributed_utils  # noqa: E402
 from unicore.logging import meters, metrics, progress_bar  # noqa: E402,F401

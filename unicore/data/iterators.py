@@ -29,51 +29,62 @@ _END = object()  # sentinel placed in the prefetch queue when the source is exha
 
 
 class CountingIterator(object):
-    """Iterator wrapper that knows how many items it has yielded (``n``) and its total length."""
+    """An iterator that keeps score: ``n`` items handed out so far out of ``total``.
+
+    ``start`` lets a resumed iterator begin its count where the interrupted one stopped; a source that produces more
+    than ``total`` items is a bug upstream (different sharding than the checkpoint) and is reported as such."""
+
+    _TOO_LONG = (
+        "Mismatch between actual and expected iterable length. This may be caused by resuming training from a "
+        "checkpoint using a different number of GPUs, in which case you can try the --reset-dataloader option. "
+        "Alternatively you may have a train or validation set that is smaller than the number of GPUs. If none of "
+        "these apply, please report this."
+    )
 
     def __init__(self, iterable, start=None, total=None):
         self.iterable = iterable
-        self._itr = iter(self)
-        self.n = start if start is not None else getattr(iterable, "n", 0)
-        self.total = total if total is not None else self.n + len(iterable)
+        self.n = getattr(iterable, "n", 0) if start is None else start
+        self.total = self.n + len(iterable) if total is None else total
+        self._stream = self._counted()
+
+    def _counted(self):
+        for item in self.iterable:
+            if self.n >= self.total:
+                raise RuntimeError(self._TOO_LONG)
+            self.n += 1
+            yield item
+
+    def __iter__(self):
+        return self._stream
+
+    def __next__(self):
+        return next(self._stream)
 
     def __len__(self):
         return self.total
 
-    def __iter__(self):
-        for item in self.iterable:
-            if self.n >= self.total:
-                raise RuntimeError(
-                    "Mismatch between actual and expected iterable length. This may be caused by resuming "
-                    "training from a checkpoint using a different number of GPUs, in which case you can try "
-                    "the --reset-dataloader option. Alternatively you may have a train or validation set that "
-                    "is smaller than the number of GPUs. If none of these apply, please report this."
-                )
-            self.n += 1
-            yield item
-
-    def __next__(self):
-        return next(self._itr)
-
     def has_next(self):
-        return self.n < len(self)
+        return self.n < self.total
 
     def skip(self, num_to_skip):
-        next(itertools.islice(self._itr, num_to_skip, num_to_skip), None)
+        for _ in itertools.islice(self._stream, num_to_skip):
+            pass
         return self
 
     def take(self, n):
-        """Truncate to at most ``n`` items in total."""
+        """Stop after ``n`` items in total (counting the ones already consumed)."""
         self.total = min(self.total, n)
-        propagated = max(n - self.n, 0)
+        remaining = max(n - self.n, 0)
         if hasattr(self.iterable, "take"):
-            self.iterable.take(propagated)
+            self.iterable.take(remaining)
         else:
-            self.iterable = itertools.islice(self.iterable, propagated)
+            self.iterable = itertools.islice(self.iterable, remaining)
         return self
 
 
 class EpochBatchIterating(object):
+    """Interface of multi-epoch batch iterators (what the trainer and the CLI rely on)."""
+
     def __len__(self) -> int:
         raise NotImplementedError
 
@@ -103,183 +114,153 @@ class EpochBatchIterating(object):
 
 
 class EpochBatchIterator(EpochBatchIterating):
-    """Multi-epoch iterator over a fixed ("frozen") list of batches.
+    """Epoch after epoch over one fixed list of batches (lists of dataset indices).
 
-    Each epoch: shuffle the batch list with ``seed + epoch``, give rank ``shard_id`` every
-    ``num_shards``-th batch (short shards are padded with empty batches), feed the index lists to
-    a ``torch.utils.data.DataLoader`` and wrap the result for prefetch + counting.  The position
-    is checkpointable and can be restored into a run with a different world size.
+    An epoch's order is a pure function of ``(seed, epoch)``: the batch list is shuffled with ``seed + epoch``, rank
+    ``shard_id`` takes every ``num_shards``-th entry (a short shard is completed with empty batches so that all ranks
+    step in lockstep), and the index lists drive a ``DataLoader``.  That makes the position checkpointable as two
+    numbers - epoch and batches consumed - and restorable into a run with a different world size (the position is
+    rescaled by the ratio of the shard lengths).
     """
 
-    def __init__(
-        self,
-        dataset,
-        collate_fn,
-        batch_sampler,
-        seed=1,
-        num_shards=1,
-        shard_id=0,
-        num_workers=0,
-        epoch=1,
-        buffer_size=0,
-        timeout=0,
-        disable_shuffling=False,
-        pin_memory=False,
-    ):
+    def __init__(self, dataset, collate_fn, batch_sampler, seed=1, num_shards=1, shard_id=0, num_workers=0, epoch=1,
+                 buffer_size=0, timeout=0, disable_shuffling=False, pin_memory=False):
         if not isinstance(dataset, torch.utils.data.Dataset):
             raise TypeError("dataset must be a torch Dataset")
-        self.dataset = dataset
-        self.collate_fn = collate_fn
-        self.batch_sampler = batch_sampler
-        self._frozen_batches = None if callable(batch_sampler) else tuple(batch_sampler)
-        self.seed = seed
-        self.num_shards = num_shards
-        self.shard_id = shard_id
-        self.num_workers = num_workers
+        self.dataset, self.collate_fn, self.batch_sampler = dataset, collate_fn, batch_sampler
+        self.seed, self.num_shards, self.shard_id = seed, num_shards, shard_id
+        self.num_workers, self.timeout, self.pin_memory = num_workers, timeout, pin_memory
         self.buffer_size = min(buffer_size, 32)  # politeness cap on shared hosts
-        self.timeout = timeout
         self.disable_shuffling = disable_shuffling
-        self.pin_memory = pin_memory
-        self.epoch = max(epoch, 1)  # epochs are 1-based
         self.shuffle = not disable_shuffling
-        self._cur_epoch_itr = None
-        self._next_epoch_itr = None
-        self._supports_prefetch = getattr(dataset, "supports_prefetch", False)
+        self.epoch = max(epoch, 1)  # epochs count from 1
+        # a callable sampler is asked again every epoch; a plain list is frozen once
+        self._batches = None if callable(batch_sampler) else tuple(batch_sampler)
+        self._running = None   # the iterator of the epoch in progress
+        self._restored = None  # an iterator prepared by load_state_dict, handed out by the next next_epoch_itr()
+        self._prefetching_dataset = getattr(dataset, "supports_prefetch", False)
 
-    # -- batches ------------------------------------------------------------------------------
+    # ---- the batch list ---------------------------------------------------------------------------------------
     @property
     def frozen_batches(self):
-        if self._frozen_batches is None:
-            self._frozen_batches = tuple(self.batch_sampler(self.dataset, self.epoch))
-        return self._frozen_batches
+        if self._batches is None:
+            self._batches = tuple(self.batch_sampler(self.dataset, self.epoch))
+        return self._batches
 
     @property
     def first_batch(self):
-        if len(self.frozen_batches) == 0:
+        batches = self.frozen_batches
+        if not batches:
             raise Exception(
                 "The dataset is empty. This could indicate that all elements in the dataset have been skipped. "
                 "Try increasing the max number of allowed tokens or using a larger dataset."
             )
-        if getattr(self.dataset, "supports_fetch_outside_dataloader", True):
-            return self.collate_fn([self.dataset[i] for i in self.frozen_batches[0]])
-        return "DUMMY"
+        if not getattr(self.dataset, "supports_fetch_outside_dataloader", True):
+            return "DUMMY"
+        return self.collate_fn([self.dataset[i] for i in batches[0]])
 
     def __len__(self):
-        return int(math.ceil(len(self.frozen_batches) / float(self.num_shards)))
+        return -(-len(self.frozen_batches) // self.num_shards)
 
+    # ---- position ---------------------------------------------------------------------------------------------------
     @property
-    def n(self):
-        return self.iterations_in_epoch
+    def iterations_in_epoch(self):
+        active = self._running if self._running is not None else self._restored
+        return 0 if active is None else active.n
 
-    # -- epoch control ------------------------------------------------------------------------
+    n = iterations_in_epoch
+
+    def end_of_epoch(self) -> bool:
+        return not self._running.has_next()
+
     @property
     def next_epoch_idx(self):
-        if self._next_epoch_itr is not None:
-            return self.epoch
-        if self._cur_epoch_itr is not None and self.end_of_epoch():
+        if self._restored is None and self._running is not None and self.end_of_epoch():
             return self.epoch + 1
         return self.epoch
 
     def next_epoch_itr(self, shuffle=True, fix_batches_to_gpus=False, set_dataset_epoch=True):
-        if self.disable_shuffling:
-            shuffle = False
+        shuffle = shuffle and not self.disable_shuffling
         self.epoch = self.next_epoch_idx
         if set_dataset_epoch and hasattr(self.dataset, "set_epoch"):
             self.dataset.set_epoch(self.epoch)
-        if self._next_epoch_itr is not None:  # prepared by load_state_dict
-            self._cur_epoch_itr, self._next_epoch_itr = self._next_epoch_itr, None
+        if self._restored is not None:
+            self._running, self._restored = self._restored, None
         else:
             if callable(self.batch_sampler):
-                self._frozen_batches = None  # re-sample for the new epoch
-            self._cur_epoch_itr = self._get_iterator_for_epoch(
-                self.epoch, shuffle, fix_batches_to_gpus=fix_batches_to_gpus
-            )
+                self._batches = None  # new epoch, new sample of batches
+            self._running = self._get_iterator_for_epoch(self.epoch, shuffle, fix_batches_to_gpus=fix_batches_to_gpus)
         self.shuffle = shuffle
-        return self._cur_epoch_itr
+        return self._running
 
-    def end_of_epoch(self) -> bool:
-        return not self._cur_epoch_itr.has_next()
-
-    @property
-    def iterations_in_epoch(self):
-        for itr in (self._cur_epoch_itr, self._next_epoch_itr):
-            if itr is not None:
-                return itr.n
-        return 0
-
-    # -- checkpointing ------------------------------------------------------------------------
+    # ---- checkpointing ------------------------------------------------------------------------------------------
     def state_dict(self):
-        finished = self.end_of_epoch()
+        done = self.end_of_epoch()
         return {
-            "epoch": self.epoch + 1 if finished else self.epoch,
-            "iterations_in_epoch": 0 if finished else self.iterations_in_epoch,
+            "epoch": self.epoch + (1 if done else 0),
+            "iterations_in_epoch": 0 if done else self.iterations_in_epoch,
             "shuffle": self.shuffle,
             "len": len(self),
         }
 
     def load_state_dict(self, state_dict):
         self.epoch = state_dict["epoch"]
-        pos = state_dict.get("iterations_in_epoch", 0)
-        if pos <= 0:
-            self._next_epoch_itr = None
+        self._restored = None
+        consumed = state_dict.get("iterations_in_epoch", 0)
+        if consumed <= 0:
             return
-        saved_len = state_dict.get("len", None)
-        if saved_len is not None and saved_len != len(self):
-            rescaled = int(pos * len(self) / saved_len)
+        then, now = state_dict.get("len", None), len(self)
+        if then is not None and then != now:
+            rescaled = int(consumed * now / then)
             logger.info(
                 "Iterator size changed ({} -> {}; different world size or update_freq?). "
-                "Position rescaled from {} to {}.".format(saved_len, len(self), pos, rescaled)
+                "Position rescaled from {} to {}.".format(then, now, consumed, rescaled)
             )
-            pos = rescaled
-        self._next_epoch_itr = self._get_iterator_for_epoch(
-            self.epoch, shuffle=state_dict.get("shuffle", True), offset=pos
-        )
-        if self._next_epoch_itr is None:
+            consumed = rescaled
+        self._restored = self._get_iterator_for_epoch(self.epoch, shuffle=state_dict.get("shuffle", True), offset=consumed)
+        if self._restored is None:
             raise RuntimeError(
                 "Cannot resume training due to dataloader mismatch. You can relaunch "
                 "training with `--reset-dataloader` and it should work."
             )
 
-    # -- construction of one epoch's iterator ----------------------------------------------------
-    @staticmethod
-    def _shuffled(batches, seed):
-        batches = list(batches)
-        with data_utils.numpy_seed(seed):
-            np.random.shuffle(batches)
-        return batches
+    # ---- one epoch ------------------------------------------------------------------------------------------------
+    def _epoch_order(self, epoch, shuffle, fix_batches_to_gpus):
+        """This rank's batches of ``epoch``, in order."""
 
-    def _shard(self, batches):
-        return list(ShardedIterator(batches, self.num_shards, self.shard_id, fill_value=[]))
+        def shuffled(seq, seed):
+            seq = list(seq)
+            with data_utils.numpy_seed(seed):
+                np.random.shuffle(seq)
+            return seq
+
+        def my_share(seq):
+            return list(ShardedIterator(seq, self.num_shards, self.shard_id, fill_value=[]))
+
+        batches = self.frozen_batches
+        if not self._prefetching_dataset:
+            return my_share(shuffled(batches, self.seed + epoch) if shuffle else batches)
+        # datasets that load ahead of time: decide the shard first, tell the dataset what it will be asked for, and only
+        # then (optionally) reorder within the shard so that a rank keeps "its" batches across epochs
+        if shuffle and not fix_batches_to_gpus:
+            batches = shuffled(batches, self.seed + epoch)
+        mine = my_share(batches)
+        self.dataset.prefetch([i for batch in mine for i in batch])
+        if shuffle and fix_batches_to_gpus:
+            mine = shuffled(mine, self.seed + epoch + self.shard_id)
+        return mine
 
     def _get_iterator_for_epoch(self, epoch, shuffle, fix_batches_to_gpus=False, offset=0):
-        batches = self.frozen_batches
-        if self._supports_prefetch:
-            if shuffle and not fix_batches_to_gpus:
-                batches = self._shuffled(batches, self.seed + epoch)
-            batches = self._shard(batches)
-            self.dataset.prefetch([i for b in batches for i in b])
-            if shuffle and fix_batches_to_gpus:
-                batches = self._shuffled(batches, self.seed + epoch + self.shard_id)
-        else:
-            if shuffle:
-                batches = self._shuffled(batches, self.seed + epoch)
-            batches = self._shard(batches)
-
-        if offset > 0 and offset >= len(batches):
+        order = self._epoch_order(epoch, shuffle, fix_batches_to_gpus)
+        if 0 < offset and len(order) <= offset:
             return None
         if self.num_workers > 0:
             os.environ["PYTHONWARNINGS"] = "ignore:semaphore_tracker:UserWarning"
-
-        itr = torch.utils.data.DataLoader(
-            self.dataset,
-            collate_fn=self.collate_fn,
-            batch_sampler=batches[offset:],
-            num_workers=self.num_workers,
-            timeout=self.timeout,
-        )
+        loader = torch.utils.data.DataLoader(self.dataset, collate_fn=self.collate_fn, batch_sampler=order[offset:],
+                                             num_workers=self.num_workers, timeout=self.timeout)
         if self.buffer_size > 0:
-            itr = BufferedIterator(self.buffer_size, itr, pin_memory=self.pin_memory)
-        return CountingIterator(itr, start=offset)
+            loader = BufferedIterator(self.buffer_size, loader, pin_memory=self.pin_memory)
+        return CountingIterator(loader, start=offset)
 
 
 class GroupedIterator(CountingIterator):

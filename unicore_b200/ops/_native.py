@@ -33,7 +33,9 @@ def _is_blackwell() -> bool:
         return False
 
 
-if torch.cuda.is_available() and _C is None and os.environ.get("UNICORE_ALLOW_FALLBACK", "0") != "1":
+if _is_blackwell() and _C is None and os.environ.get("UNICORE_ALLOW_FALLBACK", "0") != "1":
+    # fail loudly where the kernels are the product; on other GPUs (A100 / H100 development boxes, CI) the PyTorch
+    # fallbacks are what runs anyway
     raise ImportError(
         "unicore_b200._C (sm_100a kernels) failed to load on a CUDA machine: {!r}. Build it with "
         "`python setup.py build_ext --inplace` (or __graft_entry__.build()), or set "
@@ -42,12 +44,21 @@ if torch.cuda.is_available() and _C is None and os.environ.get("UNICORE_ALLOW_FA
 
 # kernels are compiled for sm_100a only; on other GPUs use the fallbacks
 USE_NATIVE = HAS_CUDA_EXT and _is_blackwell() and os.environ.get("UNICORE_DISABLE_NATIVE", "0") != "1"
+if torch.cuda.is_available() and not USE_NATIVE:
+    import logging
+
+    logging.getLogger(__name__).warning(
+        "unicore_b200: the sm_100a kernels are not in use on this machine (%s); PyTorch fallbacks run instead",
+        "extension not built: {!r}".format(_ERR) if _C is None else "not a Blackwell GPU or UNICORE_DISABLE_NATIVE=1")
 
 
 # kernels launched per binding call (used for the benchmark's ``gpu_launches`` figure)
 _LAUNCHES_PER_CALL = {
     "layernorm_bwd": 2, "rmsnorm_bwd": 2, "bias_dropout_add_ln_bwd": 2, "fmha_bwd": 4, "bias_gelu_bwd": 2, "symm_allreduce": 2,
-    "column_sum": 2, "symm_sharded_adam": 2,
+    "column_sum": 2, "symm_reduce_scatter": 2, "symm_fused_tail": 1, "symm_stats_allreduce": 1,
+    # not kernels: allocation / capability queries
+    "SymmAllocation": 0, "symm_error_channel": 0, "symm_mem_supported": 0, "symm_multicast_supported": 0,
+    "symm_tail_max_blocks": 0, "symm_pick_algo": 0, "norm_v2_supported": 0,
 }
 _launch_count = 0
 
