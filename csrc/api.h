@@ -84,7 +84,8 @@ void launch_rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const 
 void launch_softmax_dropout_fwd(void* x, void* out, const void* mask, const void* bias, long long rows, int K,
                                 long long mask_div, long long bias_rows, float p, unsigned long long seed,
                                 unsigned long long offset, int dtype, cudaStream_t stream, void* logits = nullptr,
-                                float* lse = nullptr);
+                                float* lse = nullptr, void* probs = nullptr);
+// (plain mode writes the probabilities backward needs into `probs`; nullptr = over x itself, the in-place contract)
 // dx may alias dy.  Logits mode (lse != nullptr): `probs` holds the logits forward wrote; `addend` (nullable) is
 // added to dx before the store.
 void launch_softmax_dropout_bwd(const void* dy, void* dx, const void* probs, long long rows, int K, float p,

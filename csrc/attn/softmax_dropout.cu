@@ -64,9 +64,11 @@ struct SmGeom {
 
 template <typename T, int VPT>
 __global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
-    T* __restrict__ x, T* __restrict__ out, const T* __restrict__ mask, const T* __restrict__ bias, SmGeom g, float p,
+    const T* x, T* probs, T* __restrict__ out, const T* __restrict__ mask, const T* __restrict__ bias, SmGeom g, float p,
     float keep_scale, unsigned long long seed, unsigned long long offset, T* __restrict__ logits,
     float* __restrict__ lse) {
+  // `probs` (what backward reads) may be x itself (the reference's in-place contract) or a separate buffer (non
+  // in-place callers: no clone pass in front of the kernel)
   constexpr int EPV = VecTraits<T>::kElems;
   __shared__ float scratch[8];
   const int tpr = g.tpr, rows_per_cta = kSmThreads / tpr;
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_fwd_kernel(
 #pragma unroll
           for (int e = 0; e < EPV; ++e) pr[e] = v[k][e] * inv;
           const Vec16 packed = pack<T>(pr);
-          if (!logits_mode) st_global_v4(x + off, packed);
+          if (!logits_mode) st_global_v4(probs + off, packed);
           else if (!drop) st_global_v4(out + off, packed);
           if (drop) {
             // out = keep ? p * keep_scale : 0, the scale applied in fp32 ahead of the single rounding
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_dropout_bwd_kernel(
 
 // ---- scalar fallback (row length not a multiple of the vector width): one warp per row ----------------
 template <typename T>
-__global__ void softmax_dropout_fwd_scalar(T* x, T* out, const T* mask, const T* bias, SmGeom g, float p,
+__global__ void softmax_dropout_fwd_scalar(const T* x, T* probs, T* out, const T* mask, const T* bias, SmGeom g, float p,
                                            float keep_scale, unsigned long long seed, unsigned long long offset,
                                            T* logits, float* lse) {
   const int lane = threadIdx.x & 31;
@@ -254,7 +256,8 @@ __global__ void softmax_dropout_fwd_scalar(T* x, T* out, const T* mask, const T*
   const uint32_t thresh = dropout_thresh14(p);
   const bool logits_mode = lse != nullptr;
   for (long long row = warp; row < g.rows; row += nwarps) {
-    T* xr = x + row * g.K;
+    const T* xr = x + row * g.K;
+    T* pr_row = probs + row * g.K;
     T* zr = logits_mode ? logits + row * g.K : nullptr;
     const T* mr = mask ? mask + (row / g.mask_div) * g.K : nullptr;
     const T* br = bias ? bias + (row % g.bias_rows) * g.K : nullptr;
@@ -278,7 +281,7 @@ __global__ void softmax_dropout_fwd_scalar(T* x, T* out, const T* mask, const T*
     for (int c = lane; c < g.K; c += 32) {
       const float v = logits_mode ? to_f32<T>(zr[c]) : biased(c);
       const T pr = from_f32<T>(expf(v - mx) * inv);
-      if (!logits_mode) xr[c] = pr;
+      if (!logits_mode) pr_row[c] = pr;
       else if (p <= 0.f) out[row * g.K + c] = pr;
       if (p > 0.f) {
         const unsigned long long idx = (unsigned long long)(row * g.K + c);
@@ -387,11 +390,12 @@ static float keep_scale_for(float p) {
 template <typename T>
 static void run_sm_fwd(void* x, void* out, const void* mask, const void* bias, long long rows, int K,
                        long long mask_div, long long bias_rows, float p, unsigned long long seed,
-                       unsigned long long offset, void* logits, float* lse, cudaStream_t stream) {
+                       unsigned long long offset, void* logits, float* lse, cudaStream_t stream, void* probs) {
   SmGeom g;
   int vpt = 0;
+  if (probs == nullptr) probs = x;
   const bool vec = make_sm_geom(g, rows, K, VecTraits<T>::kElems, vpt) &&
-                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(probs) |
                      reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(bias) |
                      reinterpret_cast<uintptr_t>(logits)) & 15) == 0;
   g.mask_div = mask_div > 0 ? mask_div : 1;
@@ -404,14 +408,14 @@ static void run_sm_fwd(void* x, void* out, const void* mask, const void* bias, l
       static const int resident = resident_blocks(softmax_dropout_fwd_kernel<T, VPT>);
       const int grid = (int)(need < resident ? need : resident);
       softmax_dropout_fwd_kernel<T, VPT><<<grid, kSmThreads, 0, stream>>>(
-          (T*)x, (T*)out, (const T*)mask, (const T*)bias, g, p, keep_scale, seed, offset, (T*)logits, lse);
+          (const T*)x, (T*)probs, (T*)out, (const T*)mask, (const T*)bias, g, p, keep_scale, seed, offset, (T*)logits, lse);
     });
   } else {
     long long need = (rows + 7) / 8;
     const long long cap = (long long)sm_count2() * 8;
     const int grid = (int)(need < cap ? need : cap);
-    softmax_dropout_fwd_scalar<T><<<grid, 256, 0, stream>>>((T*)x, (T*)out, (const T*)mask, (const T*)bias, g, p,
-                                                            keep_scale, seed, offset, (T*)logits, lse);
+    softmax_dropout_fwd_scalar<T><<<grid, 256, 0, stream>>>((const T*)x, (T*)probs, (T*)out, (const T*)mask, (const T*)bias,
+                                                            g, p, keep_scale, seed, offset, (T*)logits, lse);
   }
 }
 
@@ -446,14 +450,15 @@ static void run_sm_bwd(const void* dy, void* dx, const void* probs, long long ro
 
 void launch_softmax_dropout_fwd(void* x, void* out, const void* mask, const void* bias, long long rows, int K,
                                 long long mask_div, long long bias_rows, float p, unsigned long long seed,
-                                unsigned long long offset, int dtype, cudaStream_t stream, void* logits, float* lse) {
+                                unsigned long long offset, int dtype, cudaStream_t stream, void* logits, float* lse,
+                                void* probs) {
   if (rows <= 0 || K <= 0) return;
   if (dtype == kF32)
-    run_sm_fwd<float>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, logits, lse, stream);
+    run_sm_fwd<float>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, logits, lse, stream, probs);
   else if (dtype == kF16)
-    run_sm_fwd<__half>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, logits, lse, stream);
+    run_sm_fwd<__half>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, logits, lse, stream, probs);
   else
-    run_sm_fwd<__nv_bfloat16>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, logits, lse, stream);
+    run_sm_fwd<__nv_bfloat16>(x, out, mask, bias, rows, K, mask_div, bias_rows, p, seed, offset, logits, lse, stream, probs);
 }
 
 void launch_softmax_dropout_bwd(const void* dy, void* dx, const void* probs, long long rows, int K, float p,

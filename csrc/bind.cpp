@@ -302,13 +302,17 @@ static SmBroadcast softmax_broadcast_plan(const Tensor& x, const OptTensor& mask
   return b;
 }
 
-std::tuple<Tensor, int64_t, int64_t> softmax_dropout_fwd(Tensor x, const OptTensor& mask, const OptTensor& bias, double p,
-                                                         bool training) {
+// Returns (out, probs, seed, offset).  in_place: the probabilities overwrite x (the reference's contract, probs IS x);
+// otherwise x is left untouched and the probabilities go to a fresh tensor - no clone pass in front of the kernel.
+// Without dropout `out` and `probs` are the same tensor.
+std::tuple<Tensor, Tensor, int64_t, int64_t> softmax_dropout_fwd(Tensor x, const OptTensor& mask, const OptTensor& bias,
+                                                                 double p, bool training, bool in_place) {
   const SmBroadcast b = softmax_broadcast_plan(x, mask, bias);
   const c10::cuda::CUDAGuard guard(x.device());
   const float pf = training ? (float)p : 0.f;
   uint64_t seed = 0, offset = 0;
-  Tensor out = x;
+  Tensor probs = in_place ? x : torch::empty_like(x);
+  Tensor out = probs;
   if (pf > 0.f) {
     auto so = philox_reserve(4);
     seed = so.first;
@@ -316,9 +320,10 @@ std::tuple<Tensor, int64_t, int64_t> softmax_dropout_fwd(Tensor x, const OptTens
     out = torch::empty_like(x);
   }
   ub::launch_softmax_dropout_fwd(x.data_ptr(), out.data_ptr(), opt_ptr(mask), opt_ptr(bias), b.rows, b.K, b.mask_div,
-                                 b.bias_rows, pf, seed, offset, dtype_tag(x), cur_stream());
+                                 b.bias_rows, pf, seed, offset, dtype_tag(x), cur_stream(), nullptr, nullptr,
+                                 probs.data_ptr());
   check_launch("softmax_dropout_fwd");
-  return {out, (int64_t)seed, (int64_t)offset};
+  return {out, probs, (int64_t)seed, (int64_t)offset};
 }
 
 // Logits mode: x is read-only; returns (dropout(softmax(z)), z = x + mask + bias, row log-sum-exp, seed, offset).

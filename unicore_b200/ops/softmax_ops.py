@@ -62,12 +62,13 @@ def _bias_plan(bias: torch.Tensor, x: torch.Tensor) -> bool:
 
 class _SoftmaxDropoutFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x3, mask3, bias3, p, training):
-        out, seed, offset = native().softmax_dropout_fwd(x3, mask3, bias3, float(p), bool(training))
+    def forward(ctx, x3, mask3, bias3, p, training, in_place=True):
+        out, probs, seed, offset = native().softmax_dropout_fwd(x3, mask3, bias3, float(p), bool(training), bool(in_place))
         ctx.p = float(p) if training else 0.0
         ctx.rng = (seed, offset)
         ctx.bias_rows = bias3.shape[0] if (bias3 is not None and bias3.requires_grad) else 0
-        ctx.save_for_backward(x3)  # now holds softmax probabilities (overwritten by the kernel)
+        # the softmax probabilities: x3 itself when the kernel ran in place, else the kernel's own buffer
+        ctx.save_for_backward(probs)
         return out
 
     @staticmethod
@@ -77,7 +78,7 @@ class _SoftmaxDropoutFn(torch.autograd.Function):
         if dy.data_ptr() == probs.data_ptr():
             dy = dy.clone()
         dx = native().softmax_dropout_bwd(dy, probs, ctx.p, ctx.rng[0], ctx.rng[1])
-        return dx, None, _bias_grad(dx, ctx.bias_rows), None, None
+        return dx, None, _bias_grad(dx, ctx.bias_rows), None, None, None
 
 
 def _bias_grad(dx3, bias_rows):
@@ -143,15 +144,16 @@ def _kernel_eligible(input, mask, bias):
 def softmax_dropout(input, dropout_prob, is_training=True, mask=None, bias=None, inplace=True):
     """See module docstring. Returns a tensor shaped like ``input``."""
     input = input.contiguous()
-    if not inplace:
-        input = input.clone()
     if _kernel_eligible(input, mask, bias):
         shape = input.shape
-        x3, mask, bias = _kernel_operands(input, mask, bias, may_overwrite=True)
-        if x3.requires_grad and x3.is_leaf:
-            x3 = x3.clone()  # cannot overwrite a leaf that needs grad
-        out = _SoftmaxDropoutFn.apply(x3, mask, bias, dropout_prob, is_training)
+        x3, mask, bias = _kernel_operands(input, mask, bias, may_overwrite=inplace)
+        # not in place (or a leaf that needs grad, which must not be overwritten): the kernel reads x and writes the
+        # probabilities to its own buffer - no clone pass
+        overwrite = inplace and not (x3.requires_grad and x3.is_leaf)
+        out = _SoftmaxDropoutFn.apply(x3, mask, bias, dropout_prob, is_training, overwrite)
         return out.view(shape)
+    if not inplace:
+        input = input.clone()
     if mask is not None:
         input = input + mask
     if bias is not None:
