@@ -15,7 +15,7 @@ import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
-sys.path.insert(0, os.path.join(REPO, "examples"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 def main():
@@ -26,7 +26,23 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp16", "bf16"])
     ap.add_argument("--max-atoms", type=int, default=254)
     ap.add_argument("--ddp-backend", default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"],
+                    help="reference: the unmodified reference framework from baseline/_ref (BASELINE.md B6)")
+    ap.add_argument("--ref-ext", action="store_true", help="reference arm: with its own CUDA extensions (sm_100 rebuild)")
+    ap.add_argument("--portable", action="store_true",
+                    help="use examples/unimol_portable (public Uni-Core API only; the plug-in both frameworks can load) "
+                         "instead of this framework's optimised examples/unimol; implied by --impl reference")
     a = ap.parse_args()
+    a.portable = a.portable or a.impl == "reference"
+    from op_compare import Clocks
+    sys.path.insert(0, REPO)
+    import bench as B
+
+    why = B.setup_paths(a.impl, a.ref_ext)
+    if why is not None:
+        print(json.dumps({"impl": a.impl, "unavailable": why}))
+        return 0
+    sys.path.insert(0, os.path.join(REPO, "examples"))
 
     import torch
     import torch.distributed as dist
@@ -40,21 +56,25 @@ def main():
         dist.init_process_group(backend="nccl", init_method="env://", world_size=world, rank=rank)
         dist.all_reduce(torch.zeros(1, device="cuda"))
 
-    importlib.import_module("unimol")
+    importlib.import_module("unimol_portable" if a.portable else "unimol")
     from unicore import options, tasks, utils
     from unicore.trainer import Trainer
 
-    backend = a.ddp_backend or ("b200" if world > 1 else "c10d")
+    backend = a.ddp_backend or ("b200" if (world > 1 and a.impl == "ours") else "c10d")
+    names = ("synthetic_unimol_portable", "unimol_portable", "unimol_portable_base") if a.portable else \
+        ("synthetic_unimol", "unimol", "unimol_base")
     flags = [
-        "--task", "synthetic_unimol", "--loss", "unimol", "--arch", "unimol_base",
+        "--task", names[0], "--loss", names[1], "--arch", names[2],
         "--synthetic-num-samples", str(a.batch_size * 8), "--synthetic-max-atoms", str(a.max_atoms),
         "--optimizer", "adam", "--adam-betas", "(0.9, 0.99)", "--adam-eps", "1e-6", "--clip-norm", "1.0",
         "--lr", "1e-4", "--lr-scheduler", "polynomial_decay", "--warmup-updates", "100",
         "--total-num-update", "100000", "--max-update", "100000", "--batch-size", str(a.batch_size),
         "--update-freq", "1", "--seed", "1", "--no-save", "--disable-validation", "--log-format", "none",
         "--distributed-world-size", str(world), "--ddp-backend", backend, "--device-id", str(local_rank),
-        "--distributed-rank", str(rank), "--" + a.precision, "--deferred-overflow-check",
+        "--distributed-rank", str(rank), "--" + a.precision,
     ]
+    if a.impl == "ours":
+        flags.append("--deferred-overflow-check")
     parser = options.get_training_parser()
     args = options.parse_args_and_arch(parser, input_args=flags)
     args.distributed_rank, args.device_id = rank, local_rank
@@ -75,6 +95,8 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    clocks = Clocks() if rank == 0 else None
+    mark = clocks.mark() if clocks is not None else 0
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for i in range(a.steps):
@@ -91,9 +113,17 @@ def main():
             "metric": "Uni-Mol pre-training throughput (molecules/s, whole job, device-timed, max over ranks)",
             "value": a.batch_size * world / t * 1e3, "unit": "molecules/s", "n_gpus": world, "ms_per_step": t,
             "steps": a.steps, "warmup": a.warmup, "dtype": a.precision, "data": "synthetic molecules",
+            "impl": a.impl, "plugin": "examples/unimol_portable" if a.portable else "examples/unimol",
+            "reference_cuda_ext": bool(a.ref_ext) if a.impl == "reference" else None,
             "config": {"model": "unimol_base", "params": nparams, "per_gpu_batch": a.batch_size,
                        "padded_atoms_per_batch": atoms, "ddp_backend": backend},
+            "clocks": clocks.since(mark) if clocks is not None else None,
         }))
+    if clocks is not None:
+        clocks.stop()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

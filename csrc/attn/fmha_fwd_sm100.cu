@@ -230,9 +230,21 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
       mbar_expect_tx(bar_b, kBiasBytes);
       tma_load_5d(smem_base + kSmemBias, &p.tm_bias, 0, 0, (jt_next * kBlockN) / 8, q0 / 8, bias_nb, bar_b);
     }
-    const float m_new = fmaxf(m_run, m_tile);
+    // Lazy rescaling: the running reference m_run only follows the true row maximum when that has grown by more than
+    // kRescaleSlack (natural-log units; exp(8) = 2981 keeps P, the row sum and the fp32 accumulator far from overflow:
+    // P <= 2981 < 65504).  exp(x - m_run) with a slightly stale m_run is exact arithmetic - the final division by the
+    // row sum and LSE = m_run + log(l) absorb it - and the TMEM round trip that rescales O (tcgen05.ld, 32 multiplies,
+    // tcgen05.st, two waits: the longest dependent chain of a tile) disappears from almost every tile.
+    constexpr float kRescaleSlack = 8.f;
+    const float m_true = fmaxf(m_run, m_tile);
+    const bool first = m_run == -CUDART_INF_F;
+    const bool jump = first || (m_true - m_run > kRescaleSlack);
+    const float m_new = jump ? m_true : m_run;
     const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-    const float alpha = exp2f((m_run - m_use) * kLog2e);  // m_run = -inf -> 0
+    const float alpha = jump ? exp2f((m_run - m_use) * kLog2e) : 1.f;  // m_run = -inf -> 0
+    // both threads of a row (different warps) take the same decision; a warp skips the O round trip when none of its
+    // rows moved its reference
+    const bool warp_rescales = __any_sync(0xffffffffu, jump && j > 0);
     l_run *= alpha;
     m_run = m_new;
 
@@ -274,7 +286,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
     UB_TRACE(9);
 
     // ---- rescale the running output accumulator (32 of the 64 columns per thread) ------------------------
-    if (j > 0) {
+    if (warp_rescales) {
       uint32_t acc[32];
       tmem_ld32(lane_base + kTmemColO + half * 32, acc);
       tmem_wait_ld();

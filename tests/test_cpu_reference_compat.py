@@ -87,3 +87,22 @@ def test_checkpoints_travel_between_the_reference_and_this_framework(tmp_path):
         assert got["loaded_updates"] == 3 and got["loaded_epoch"] == 1
         assert got["losses_after"] == pytest.approx(sides[writer]["losses_after"], abs=3e-3), (loader, writer)
         assert got["ema_checksum"] == pytest.approx(sides[writer]["ema_checksum"], rel=1e-5)
+
+
+def test_portable_unimol_plugin_gives_the_same_losses_under_both_frameworks(tmp_path):
+    """``examples/unimol_portable`` only uses the public Uni-Core API: the identical plug-in code trains under the
+    reference and under this framework, from the same weights, to the same losses."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "unicore")):
+        pytest.skip("reference not installed under baseline/_ref")
+    tool = os.path.join(ROOT, "tools", "unimol_portable_check.py")
+    init = str(tmp_path / "u.pt")
+    runs = {}
+    for impl in ("ours", "reference"):
+        out = subprocess.run([PY, tool, "--impl", impl, "--init", init, "--steps", "3"], env=dict(os.environ, OMP_NUM_THREADS="1"),
+                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-3000:]
+        runs[impl] = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+        if "unavailable" in runs[impl]:
+            pytest.skip(runs[impl]["unavailable"])
+    assert len(runs["ours"]["losses"]) == 3 and runs["ours"]["losses"][-1] < runs["ours"]["losses"][0]
+    assert runs["ours"]["losses"] == pytest.approx(runs["reference"]["losses"], abs=2e-3)

@@ -42,7 +42,10 @@ class StatLedger:
         them (one pinned transfer) - the same order on every rank because the keys and their kinds are."""
         on_device = [i for i, v in enumerate(self._values) if torch.is_tensor(v) and v.is_cuda]
         on_host = [i for i in range(len(self._values)) if i not in set(on_device)]
-        order = on_device + on_host
+        by_dtype = {}
+        for i in on_device:  # (the packing stacks device scalars per dtype: keep that grouping so no reorder is needed)
+            by_dtype.setdefault(self._values[i].dtype, []).append(i)
+        order = [i for group in by_dtype.values() for i in group] + on_host
         self._pos = {self._keys[i]: pos for pos, i in enumerate(order)}
         return utils.stack_scalars([self._values[i] for i in order], device=device)
 

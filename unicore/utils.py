@@ -140,39 +140,87 @@ class AsyncHostRead:
         return self._value
 
 
+class _PinnedRing:
+    """A few page-locked staging vectors per device, reused round-robin: host numbers reach the device with ONE
+    asynchronous copy and without allocating pinned memory on the step path.  A slot is reused only after the copy
+    that read it has completed (an event per slot; the ring is deep enough that this never waits in practice)."""
+
+    def __init__(self, device, capacity=128, depth=16):
+        self.device = device
+        self.slots = [torch.empty(capacity, dtype=torch.float64, pin_memory=True) for _ in range(depth)]
+        self.events = [None] * depth
+        self.cursor = 0
+
+    def send(self, numbers):
+        n = len(numbers)
+        i = self.cursor
+        self.cursor = (i + 1) % len(self.slots)
+        if n > self.slots[i].numel():
+            return torch.tensor(numbers, dtype=torch.float64).to(self.device)
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        buf = self.slots[i]
+        for k, v in enumerate(numbers):
+            buf[k] = v
+        out = buf[:n].to(self.device, non_blocking=True)
+        if self.events[i] is None:
+            self.events[i] = torch.cuda.Event()
+        self.events[i].record(torch.cuda.current_stream(self.device))
+        return out
+
+
+_pinned_rings = {}
+
+
 def stack_scalars(values, device=None, dtype=torch.float64) -> torch.Tensor:
-    """A list of python numbers and 0-dim tensors as ONE 1-D tensor on ``device``, in order, with as few launches as
-    possible: host numbers travel together in one pinned buffer, device scalars are stacked per dtype."""
+    """A list of python numbers and 0-dim tensors as ONE 1-D tensor on ``device``, in order, without synchronising
+    the host: host numbers travel together through a page-locked ring slot, device scalars are stacked per dtype; if
+    device scalars are not already in front (grouped by dtype) the result is assembled by slice copies."""
     values = list(values)
     n = len(values)
     dev_idx = [i for i, v in enumerate(values) if torch.is_tensor(v) and v.is_cuda]
     if device is None:
         device = values[dev_idx[0]].device if dev_idx else torch.device("cpu")
     device = torch.device(device)
-    host_idx = [i for i in range(n) if i not in set(dev_idx)]
+    on_dev = set(dev_idx)
+    host_idx = [i for i in range(n) if i not in on_dev]
     host_vals = [float(values[i]) if not torch.is_tensor(values[i]) else float(values[i].item()) for i in host_idx]
-    if not dev_idx:
-        return torch.tensor(host_vals, dtype=dtype).to(device, non_blocking=True)
+    if device.type != "cuda":
+        out = torch.empty(n, dtype=dtype)
+        for i, v in zip(host_idx, host_vals):
+            out[i] = v
+        for i in dev_idx:
+            out[i] = values[i].detach().to("cpu", dtype)
+        return out.to(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     parts, order = [], []
     by_dtype = {}
     for i in dev_idx:
         by_dtype.setdefault(values[i].dtype, []).append(i)
-    for dt, idx in by_dtype.items():
+    for _dt, idx in by_dtype.items():
         parts.append(torch.stack([values[i].detach().reshape(()) for i in idx]).to(dtype))
         order += idx
     if host_idx:
-        host = torch.tensor(host_vals, dtype=dtype)
-        if device.type == "cuda":
-            host = host.pin_memory()
-        parts.append(host.to(device, non_blocking=True))
+        ring = _pinned_rings.get(device)
+        if ring is None:
+            ring = _pinned_rings[device] = _PinnedRing(device)
+        staged = ring.send(host_vals)
+        parts.append(staged if dtype == torch.float64 else staged.to(dtype))
         order += host_idx
     packed = torch.cat(parts) if len(parts) > 1 else parts[0]
     if order == list(range(n)):
         return packed
-    inverse = [0] * n
-    for pos, i in enumerate(order):
-        inverse[i] = pos
-    return packed[torch.tensor(inverse, device=device)]
+    out = torch.empty(n, dtype=dtype, device=device)
+    # (rare: callers that care order their entries device-first; runs of consecutive targets become one copy each)
+    pos = 0
+    while pos < n:
+        end = pos + 1
+        while end < n and order[end] == order[end - 1] + 1:
+            end += 1
+        out[order[pos]:order[pos] + (end - pos)].copy_(packed[pos:end])
+        pos = end
+    return out
 
 
 def item(t):
