@@ -70,13 +70,14 @@ void launch_layernorm_fwd(const void* x, const void* gamma, const void* beta, vo
 // part: float[3 * norm_bwd_parts(...) * cols] scratch (per-CTA partial column sums); dgamma/dbeta in `dtype`
 int norm_bwd_parts(int rows, int cols, int dtype);
 bool norm_v2_supported(int cols, int dtype);  // geometries for which the fused op can also emit dbias
+// accumulate (bit 0: dgamma, bit 1: dbeta, bit 2: dbias): add to what the output already holds (gradient arena)
 void launch_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
                           void* dx, void* dgamma, void* dbeta, float* part, int rows, int cols, int dtype,
-                          cudaStream_t stream);
+                          cudaStream_t stream, int accumulate = 0);
 void launch_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int rows, int cols, float eps,
                         int dtype, cudaStream_t stream);
 void launch_rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* gamma, void* dx, void* dgamma,
-                        float* part, int rows, int cols, int dtype, cudaStream_t stream);
+                        float* part, int rows, int cols, int dtype, cudaStream_t stream, int accumulate = 0);
 
 // ---- softmax + dropout ---------------------------------------------------------------------------------------
 // x: [rows, K] overwritten with softmax probabilities; out: dropout result (may alias x when p == 0)
@@ -98,9 +99,10 @@ void launch_bias_gelu_fwd(const void* x, const void* bias, void* y, long long ro
 // dbias (nullable) = column sums of dx; part = float[bias_gelu_parts(rows, cols) * cols] scratch
 int bias_gelu_parts(long long rows, int cols);
 // out[cols] (16-bit) = column sums of x[rows, cols] (cols % 8 == 0), fp32 accumulation; same scratch size
-void launch_column_sum(const void* x, void* out, float* part, long long rows, int cols, int dtype, cudaStream_t stream);
+void launch_column_sum(const void* x, void* out, float* part, long long rows, int cols, int dtype, cudaStream_t stream,
+                       int accumulate = 0);
 void launch_bias_gelu_bwd(const void* dy, const void* x, const void* bias, void* dx, void* dbias, float* part,
-                          long long rows, int cols, int dtype, cudaStream_t stream);
+                          long long rows, int cols, int dtype, cudaStream_t stream, int accumulate = 0);
 // y = LN(residual + dropout(x + bias)); summed = residual + dropout(x + bias) (saved for backward)
 void launch_bias_dropout_add_ln_fwd(const void* x, const void* bias, const void* residual, const void* gamma,
                                     const void* beta, void* y, void* summed, float* mean, float* rstd, int rows,
@@ -110,7 +112,7 @@ void launch_bias_dropout_add_ln_fwd(const void* x, const void* bias, const void*
 void launch_bias_dropout_add_ln_bwd(const void* dy, const void* summed, const float* mean, const float* rstd,
                                     const void* gamma, void* dsum, void* dx, void* dgamma, void* dbeta,
                                     void* dbias, float* part, int rows, int cols, float p, unsigned long long seed,
-                                    unsigned long long offset, int dtype, cudaStream_t stream);
+                                    unsigned long long offset, int dtype, cudaStream_t stream, int accumulate = 0);
 // ---- Gaussian radial basis of (mul[edge] * d + bias[edge]) (Uni-Mol pair features), csrc/fused/gaussian.cu ----------
 // y: [n, K] in `dtype` (fp16 / bf16), K a multiple of 8 with K / 8 a power of two <= 32
 // token-major [B, L, T, H, D] <-> T head-major [B, H, L, D] tensors (null head pointer = zeros when gathering);

@@ -226,19 +226,34 @@ std::tuple<Tensor, Tensor, Tensor> layernorm_fwd(const Tensor& x, const Tensor& 
   return {y, mean, rstd};
 }
 
+// A parameter-gradient "sink": the parameter's view of the optimizer's flat gradient arena.  When given, the kernel
+// ADDS its result to the sink (and the sink is returned) - no temporary, no separate AccumulateGrad add kernel.
+static Tensor grad_out(const OptTensor& sink, const Tensor& like, int bit, int& acc_mask) {
+  if (sink.has_value() && sink->defined()) {
+    TORCH_CHECK(sink->is_cuda() && sink->is_contiguous() && sink->scalar_type() == like.scalar_type() &&
+                    sink->numel() == like.numel(),
+                "gradient sink must match the parameter (dtype, length, contiguous)");
+    acc_mask |= 1 << bit;
+    return *sink;
+  }
+  return torch::empty_like(like);
+}
+
 std::tuple<Tensor, Tensor, Tensor> layernorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& mean,
-                                                 const Tensor& rstd, const Tensor& gamma) {
+                                                 const Tensor& rstd, const Tensor& gamma, const OptTensor& dgamma_sink,
+                                                 const OptTensor& dbeta_sink) {
   check_cuda_contig(dy, "dy");
   check_cuda_contig(x, "x");
   const c10::cuda::CUDAGuard guard(x.device());
   const int rows = (int)x.size(0), cols = (int)x.size(1);
   Tensor dx = torch::empty_like(x);
-  Tensor dgamma = torch::empty_like(gamma), dbeta = torch::empty_like(gamma);
+  int acc = 0;
+  Tensor dgamma = grad_out(dgamma_sink, gamma, 0, acc), dbeta = grad_out(dbeta_sink, gamma, 1, acc);
   const int parts = ub::norm_bwd_parts(rows, cols, dtype_tag(x));
   Tensor part = torch::empty({3, parts, cols}, x.options().dtype(at::kFloat));
   ub::launch_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
                            gamma.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                           part.data_ptr<float>(), rows, cols, dtype_tag(x), cur_stream());
+                           part.data_ptr<float>(), rows, cols, dtype_tag(x), cur_stream(), acc);
   check_launch("layernorm_bwd");
   return {dx, dgamma, dbeta};
 }
@@ -257,17 +272,19 @@ std::tuple<Tensor, Tensor> rmsnorm_fwd(const Tensor& x, const Tensor& gamma, dou
   return {y, rstd};
 }
 
-std::tuple<Tensor, Tensor> rmsnorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& rstd, const Tensor& gamma) {
+std::tuple<Tensor, Tensor> rmsnorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& rstd, const Tensor& gamma,
+                                       const OptTensor& dgamma_sink) {
   check_cuda_contig(dy, "dy");
   check_cuda_contig(x, "x");
   const c10::cuda::CUDAGuard guard(x.device());
   const int rows = (int)x.size(0), cols = (int)x.size(1);
   Tensor dx = torch::empty_like(x);
-  Tensor dgamma = torch::empty_like(gamma);
+  int acc = 0;
+  Tensor dgamma = grad_out(dgamma_sink, gamma, 0, acc);
   const int parts = ub::norm_bwd_parts(rows, cols, dtype_tag(x));
   Tensor part = torch::empty({3, parts, cols}, x.options().dtype(at::kFloat));
   ub::launch_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), rstd.data_ptr<float>(), gamma.data_ptr(), dx.data_ptr(),
-                         dgamma.data_ptr(), part.data_ptr<float>(), rows, cols, dtype_tag(x), cur_stream());
+                         dgamma.data_ptr(), part.data_ptr<float>(), rows, cols, dtype_tag(x), cur_stream(), acc);
   check_launch("rmsnorm_bwd");
   return {dx, dgamma};
 }
@@ -398,7 +415,8 @@ Tensor bias_gelu_fwd(const Tensor& x, const OptTensor& bias) {
 }
 
 // returns (dx, dbias); dbias (column sums of dx, produced by the same pass) only when a bias was given
-std::tuple<Tensor, OptTensor> bias_gelu_bwd(const Tensor& dy, const Tensor& x, const OptTensor& bias) {
+std::tuple<Tensor, OptTensor> bias_gelu_bwd(const Tensor& dy, const Tensor& x, const OptTensor& bias,
+                                            const OptTensor& dbias_sink) {
   check_cuda_contig(dy, "dy");
   check_cuda_contig(x, "x");
   const c10::cuda::CUDAGuard guard(x.device());
@@ -408,19 +426,20 @@ std::tuple<Tensor, OptTensor> bias_gelu_bwd(const Tensor& dy, const Tensor& x, c
   OptTensor dbias;
   Tensor part;
   const bool has_bias = bias.has_value() && bias->defined();
+  int acc = 0;
   if (has_bias) {
-    dbias = torch::empty_like(*bias);
+    dbias = grad_out(dbias_sink, *bias, 0, acc);
     part = torch::empty({ub::bias_gelu_parts(rows, cols), cols}, x.options().dtype(at::kFloat));
   }
   ub::launch_bias_gelu_bwd(dy.data_ptr(), x.data_ptr(), opt_ptr(bias), dx.data_ptr(),
                            has_bias ? dbias->data_ptr() : nullptr, has_bias ? part.data_ptr<float>() : nullptr, rows,
-                           cols, dtype_tag(x), cur_stream());
+                           cols, dtype_tag(x), cur_stream(), acc);
   check_launch("bias_gelu_bwd");
   return {dx, dbias};
 }
 
 // column sums over all leading dims: x [..., cols] -> [cols] (bias gradient of a Linear layer)
-Tensor column_sum(const Tensor& x) {
+Tensor column_sum(const Tensor& x, const OptTensor& sink) {
   check_cuda_contig(x, "x");
   TORCH_CHECK(x.scalar_type() == at::kHalf || x.scalar_type() == at::kBFloat16, "column_sum supports fp16 / bf16");
   const int cols = (int)x.size(-1);
@@ -428,9 +447,11 @@ Tensor column_sum(const Tensor& x) {
   const long long rows = x.numel() / cols;
   TORCH_CHECK(rows < (1ll << 31), "too many rows");
   const c10::cuda::CUDAGuard guard(x.device());
-  Tensor out = torch::empty({cols}, x.options());
+  int acc = 0;
+  Tensor out = grad_out(sink, torch::empty({cols}, x.options()), 0, acc);
   Tensor part = torch::empty({ub::bias_gelu_parts(rows, cols), cols}, x.options().dtype(at::kFloat));
-  ub::launch_column_sum(x.data_ptr(), out.data_ptr(), part.data_ptr<float>(), rows, cols, dtype_tag(x), cur_stream());
+  ub::launch_column_sum(x.data_ptr(), out.data_ptr(), part.data_ptr<float>(), rows, cols, dtype_tag(x), cur_stream(),
+                        acc);
   check_launch("column_sum");
   return out;
 }
@@ -467,23 +488,27 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, OptTensor> bias_dropout_add_ln_bwd(co
                                                                               const Tensor& mean, const Tensor& rstd,
                                                                               const Tensor& gamma, double p,
                                                                               int64_t seed, int64_t offset,
-                                                                              bool need_dbias) {
+                                                                              bool need_dbias,
+                                                                              const OptTensor& dgamma_sink,
+                                                                              const OptTensor& dbeta_sink,
+                                                                              const OptTensor& dbias_sink) {
   check_cuda_contig(dy, "dy");
   check_cuda_contig(summed, "summed");
   const c10::cuda::CUDAGuard guard(dy.device());
   const int rows = (int)summed.size(0), cols = (int)summed.size(1);
   Tensor dsum = torch::empty_like(summed);
   Tensor dx = p > 0.0 ? torch::empty_like(summed) : dsum;
-  Tensor dgamma = torch::empty_like(gamma), dbeta = torch::empty_like(gamma);
+  int acc = 0;
+  Tensor dgamma = grad_out(dgamma_sink, gamma, 0, acc), dbeta = grad_out(dbeta_sink, gamma, 1, acc);
   const int parts = ub::norm_bwd_parts(rows, cols, dtype_tag(summed));
   Tensor part = torch::empty({3, parts, cols}, summed.options().dtype(at::kFloat));
   OptTensor dbias;
-  if (need_dbias && ub::norm_v2_supported(cols, dtype_tag(summed))) dbias = torch::empty_like(gamma);
+  if (need_dbias && ub::norm_v2_supported(cols, dtype_tag(summed))) dbias = grad_out(dbias_sink, gamma, 2, acc);
   ub::launch_bias_dropout_add_ln_bwd(dy.data_ptr(), summed.data_ptr(), mean.data_ptr<float>(),
                                      rstd.data_ptr<float>(), gamma.data_ptr(), dsum.data_ptr(), dx.data_ptr(),
                                      dgamma.data_ptr(), dbeta.data_ptr(), dbias.has_value() ? dbias->data_ptr() : nullptr,
                                      part.data_ptr<float>(), rows, cols, (float)p, (uint64_t)seed, (uint64_t)offset,
-                                     dtype_tag(summed), cur_stream());
+                                     dtype_tag(summed), cur_stream(), acc);
   check_launch("bias_dropout_add_ln_bwd");
   return {dsum, dx, dgamma, dbeta, dbias};
 }
@@ -705,18 +730,24 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("fp32_to_bf16_sr", &fp32_to_bf16_sr);
   m.def("ema_update", &ema_update);
   m.def("layernorm_fwd", &layernorm_fwd);
-  m.def("layernorm_bwd", &layernorm_bwd);
+  m.def("layernorm_bwd", &layernorm_bwd, pybind11::arg("dy"), pybind11::arg("x"), pybind11::arg("mean"), pybind11::arg("rstd"),
+        pybind11::arg("gamma"), pybind11::arg("dgamma_sink") = pybind11::none(), pybind11::arg("dbeta_sink") = pybind11::none());
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
-  m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("rmsnorm_bwd", &rmsnorm_bwd, pybind11::arg("dy"), pybind11::arg("x"), pybind11::arg("rstd"), pybind11::arg("gamma"),
+        pybind11::arg("dgamma_sink") = pybind11::none());
   m.def("softmax_dropout_fwd", &softmax_dropout_fwd);
   m.def("softmax_dropout_bwd", &softmax_dropout_bwd);
   m.def("softmax_dropout_logits_fwd", &softmax_dropout_logits_fwd);
   m.def("softmax_dropout_logits_bwd", &softmax_dropout_logits_bwd);
   m.def("bias_gelu_fwd", &bias_gelu_fwd);
-  m.def("bias_gelu_bwd", &bias_gelu_bwd);
-  m.def("column_sum", &column_sum);
+  m.def("bias_gelu_bwd", &bias_gelu_bwd, pybind11::arg("dy"), pybind11::arg("x"), pybind11::arg("bias"),
+        pybind11::arg("dbias_sink") = pybind11::none());
+  m.def("column_sum", &column_sum, pybind11::arg("x"), pybind11::arg("sink") = pybind11::none());
   m.def("bias_dropout_add_ln_fwd", &bias_dropout_add_ln_fwd);
-  m.def("bias_dropout_add_ln_bwd", &bias_dropout_add_ln_bwd);
+  m.def("bias_dropout_add_ln_bwd", &bias_dropout_add_ln_bwd, pybind11::arg("dy"), pybind11::arg("summed"), pybind11::arg("mean"),
+        pybind11::arg("rstd"), pybind11::arg("gamma"), pybind11::arg("p"), pybind11::arg("seed"), pybind11::arg("offset"),
+        pybind11::arg("need_dbias"), pybind11::arg("dgamma_sink") = pybind11::none(),
+        pybind11::arg("dbeta_sink") = pybind11::none(), pybind11::arg("dbias_sink") = pybind11::none());
   m.def("softmax_xent_fwd", &softmax_xent_fwd);
   m.def("softmax_xent_bwd", &softmax_xent_bwd);
   m.def("split_heads", &split_heads);

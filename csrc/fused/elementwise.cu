@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) bias_gelu_kernel(const T* __restrict__ dy
 // partial rows [parts][cols] fp32 -> column sums in T.  block = 32 columns x 32 row slices.
 template <typename T>
 __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ part, int parts, int cols,
-                                                        T* __restrict__ out) {
+                                                        T* __restrict__ out, int accumulate) {
   __shared__ float red[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
     float s = 0.f;
 #pragma unroll
     for (int r = 0; r < 32; ++r) s += red[r][cx];
+    if (accumulate) s += to_f32<T>(out[col]);  // straight into the optimizer's gradient arena
     out[col] = from_f32<T>(s);
   }
 }
@@ -227,28 +228,29 @@ int bias_gelu_parts(long long rows, int cols) {
 
 template <typename T, bool kBwd>
 static void run_bias_gelu_t(const void* dy, const void* x, const void* bias, void* out, void* dbias, float* part,
-                            long long rows, int cols, cudaStream_t stream) {
+                            long long rows, int cols, cudaStream_t stream, int accumulate = 0) {
   const int nvec = cols / 8;
   const int slices = bias_gelu_parts(rows, cols);
   dim3 grid((nvec + kGeluColsPerCta - 1) / kGeluColsPerCta, slices);
   const bool want = kBwd && dbias != nullptr && part != nullptr;
   bias_gelu_kernel<T, kBwd><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, (const T*)bias, (T*)out,
                                                       want ? part : nullptr, (int)rows, nvec);
-  if (want) colsum_kernel<T><<<(cols + 31) / 32, 1024, 0, stream>>>(part, slices, cols, (T*)dbias);
+  if (want) colsum_kernel<T><<<(cols + 31) / 32, 1024, 0, stream>>>(part, slices, cols, (T*)dbias, accumulate);
 }
 
 // out[cols] = column sums of x[rows, cols]; part = float[bias_gelu_parts(rows, cols) * cols] scratch
-void launch_column_sum(const void* x, void* out, float* part, long long rows, int cols, int dtype, cudaStream_t stream) {
+void launch_column_sum(const void* x, void* out, float* part, long long rows, int cols, int dtype, cudaStream_t stream,
+                       int accumulate) {
   if (rows <= 0 || cols <= 0) return;
   const int nvec = cols / 8;
   const int slices = bias_gelu_parts(rows, cols);
   dim3 grid((nvec + kGeluColsPerCta - 1) / kGeluColsPerCta, slices);
   if (dtype == kF16) {
     column_sum_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)x, part, (int)rows, nvec);
-    colsum_kernel<__half><<<(cols + 31) / 32, 1024, 0, stream>>>(part, slices, cols, (__half*)out);
+    colsum_kernel<__half><<<(cols + 31) / 32, 1024, 0, stream>>>(part, slices, cols, (__half*)out, accumulate);
   } else {
     column_sum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, part, (int)rows, nvec);
-    colsum_kernel<__nv_bfloat16><<<(cols + 31) / 32, 1024, 0, stream>>>(part, slices, cols, (__nv_bfloat16*)out);
+    colsum_kernel<__nv_bfloat16><<<(cols + 31) / 32, 1024, 0, stream>>>(part, slices, cols, (__nv_bfloat16*)out, accumulate);
   }
 }
 
@@ -262,12 +264,12 @@ void launch_bias_gelu_fwd(const void* x, const void* bias, void* y, long long ro
 }
 // dbias (nullable): column sums of dx; part: float[bias_gelu_parts(rows, cols) * cols] scratch
 void launch_bias_gelu_bwd(const void* dy, const void* x, const void* bias, void* dx, void* dbias, float* part,
-                          long long rows, int cols, int dtype, cudaStream_t stream) {
+                          long long rows, int cols, int dtype, cudaStream_t stream, int accumulate) {
   if (rows <= 0 || cols <= 0) return;
   if (dtype == kF16)
-    run_bias_gelu_t<__half, true>(dy, x, bias, dx, dbias, part, rows, cols, stream);
+    run_bias_gelu_t<__half, true>(dy, x, bias, dx, dbias, part, rows, cols, stream, accumulate);
   else
-    run_bias_gelu_t<__nv_bfloat16, true>(dy, x, bias, dx, dbias, part, rows, cols, stream);
+    run_bias_gelu_t<__nv_bfloat16, true>(dy, x, bias, dx, dbias, part, rows, cols, stream, accumulate);
 }
 
 // ================================================================================================

@@ -271,7 +271,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) norm_param_grad_kernel(const float* __restrict__ dg_part,
                                                                 const float* __restrict__ db_part, int parts,
                                                                 int cols, T* __restrict__ dgamma,
-                                                                T* __restrict__ dbeta) {
+                                                                T* __restrict__ dbeta, int acc_mask) {
   __shared__ float red[2][8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
@@ -292,8 +292,12 @@ __global__ void __launch_bounds__(256) norm_param_grad_kernel(const float* __res
       sa += red[0][r][cx];
       sb += red[1][r][cx];
     }
+    if (acc_mask & 1) sa += to_f32<T>(dgamma[col]);
     dgamma[col] = from_f32<T>(sa);
-    if (db_part != nullptr) dbeta[col] = from_f32<T>(sb);
+    if (db_part != nullptr) {
+      if (acc_mask & 2) sb += to_f32<T>(dbeta[col]);
+      dbeta[col] = from_f32<T>(sb);
+    }
   }
 }
 
@@ -652,10 +656,12 @@ __global__ void __launch_bounds__(kNormV2Threads, 2) norm_bwd_v2_kernel(
 }
 
 // partial rows -> 16-bit column sums.  block = (32 columns) x (32 row slices); grid.y picks the array.
+// acc_mask bit a: array a is ADDED to what `out` already holds (parameter gradients written straight into the
+// optimizer's flat gradient arena instead of into a temporary that autograd then adds with one more kernel)
 template <typename T>
 __global__ void __launch_bounds__(1024) colsum_finalize_kernel(const float* __restrict__ part, int parts, int cols,
                                                                  T* __restrict__ out0, T* __restrict__ out1,
-                                                                 T* __restrict__ out2) {
+                                                                 T* __restrict__ out2, int acc_mask) {
   __shared__ float red[32][33];
   T* out = blockIdx.y == 0 ? out0 : (blockIdx.y == 1 ? out1 : out2);
   if (out == nullptr) return;
@@ -673,6 +679,7 @@ __global__ void __launch_bounds__(1024) colsum_finalize_kernel(const float* __re
     float s = 0.f;
 #pragma unroll
     for (int r = 0; r < 32; ++r) s += red[r][cx];
+    if ((acc_mask >> blockIdx.y) & 1) s += to_f32<T>(out[col]);
     out[col] = from_f32<T>(s);
   }
 }
@@ -1031,6 +1038,9 @@ __global__ void __launch_bounds__(kNormV3BwdThreads, (VPL <= 1 ? 2 : 1)) norm_bw
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// set by the launch_* entry points for the duration of one call (the host side of a stream is single-threaded)
+static thread_local int g_acc_mask = 0;
+
 static int sm_count() {
   static int sms = 0;
   if (sms == 0) {
@@ -1189,7 +1199,7 @@ static bool run_bwd_v3(const void* dy, const void* x, const float* mean, const f
   const size_t smem = (size_t)kNormV3BwdWarps * cols * sizeof(float);
   auto finish = [&]() {
     colsum_finalize_kernel<T><<<dim3((cols + 31) / 32, 3), 1024, 0, stream>>>(part, grid, cols, (T*)dgamma, (T*)dbeta,
-                                                                              (T*)dbias);
+                                                                              (T*)dbias, g_acc_mask);
   };
   const bool full = g.nvec == vpl * lpr;
   UB_DISPATCH_V3({
@@ -1265,7 +1275,7 @@ static void run_bwd(const void* dy, const void* x, const float* mean, const floa
                                                        part, g2, (T*)dx_drop, dbias != nullptr ? 1 : 0, p, keep_scale,
                                                        seed, offset);
     colsum_finalize_kernel<T><<<dim3((cols + 31) / 32, 3), 1024, 0, stream>>>(part, grid, cols, (T*)dgamma, (T*)dbeta,
-                                                                              (T*)dbias);
+                                                                              (T*)dbias, g_acc_mask);
     return;
   }
   int vpt;
@@ -1281,7 +1291,7 @@ static void run_bwd(const void* dy, const void* x, const float* mean, const floa
                                                 dg_part, db_part, g, (T*)dx_drop, p, keep_scale, seed, offset);
   });
   norm_param_grad_kernel<T><<<(cols + 31) / 32, 256, 0, stream>>>(dg_part, kRMS ? nullptr : db_part, parts, cols,
-                                                                  (T*)dgamma, (T*)dbeta);
+                                                                  (T*)dgamma, (T*)dbeta, g_acc_mask);
 }
 
 void launch_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
@@ -1292,9 +1302,11 @@ void launch_layernorm_fwd(const void* x, const void* gamma, const void* beta, vo
 
 void launch_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
                           void* dx, void* dgamma, void* dbeta, float* part, int rows, int cols, int dtype,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int accumulate) {
+  g_acc_mask = accumulate;
   UB_DISPATCH_DTYPE(dtype, (run_bwd<T, false, false>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, nullptr, part, rows,
                                                      cols, nullptr, 0.f, 0, 0, stream)));
+  g_acc_mask = 0;
 }
 
 void launch_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int rows, int cols, float eps,
@@ -1304,9 +1316,11 @@ void launch_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, 
 }
 
 void launch_rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* gamma, void* dx, void* dgamma,
-                        float* part, int rows, int cols, int dtype, cudaStream_t stream) {
+                        float* part, int rows, int cols, int dtype, cudaStream_t stream, int accumulate) {
+  g_acc_mask = accumulate;
   UB_DISPATCH_DTYPE(dtype, (run_bwd<T, true, false>(dy, x, nullptr, rstd, gamma, dx, dgamma, nullptr, nullptr, part,
                                                     rows, cols, nullptr, 0.f, 0, 0, stream)));
+  g_acc_mask = 0;
 }
 
 void launch_bias_dropout_add_ln_fwd(const void* x, const void* bias, const void* residual, const void* gamma,
@@ -1325,8 +1339,9 @@ void launch_bias_dropout_add_ln_fwd(const void* x, const void* bias, const void*
 void launch_bias_dropout_add_ln_bwd(const void* dy, const void* summed, const float* mean, const float* rstd,
                                     const void* gamma, void* dsum, void* dx, void* dgamma, void* dbeta,
                                     void* dbias, float* part, int rows, int cols, float p, unsigned long long seed,
-                                    unsigned long long offset, int dtype, cudaStream_t stream) {
+                                    unsigned long long offset, int dtype, cudaStream_t stream, int accumulate) {
   // dbias (optional, v2 geometries only): column sums of dx, produced by the same pass
+  g_acc_mask = accumulate;
   if (dtype == kF16) {
     run_bwd<__half, false, true>(dy, summed, mean, rstd, gamma, dsum, dgamma, dbeta, dbias, part, rows, cols, dx, p,
                                  seed, offset, stream);
@@ -1334,6 +1349,7 @@ void launch_bias_dropout_add_ln_bwd(const void* dy, const void* summed, const fl
     run_bwd<__nv_bfloat16, false, true>(dy, summed, mean, rstd, gamma, dsum, dgamma, dbeta, dbias, part, rows, cols,
                                         dx, p, seed, offset, stream);
   }
+  g_acc_mask = 0;
 }
 
 }  // namespace ub

@@ -89,3 +89,55 @@ def test_deferred_overflow_skips_on_device_and_rescales():
     inner = trainer.optimizer.fp32_optimizer.optimizer
     steps = {int(st["step"]) for st in inner.state.values() if "step" in st}
     assert steps == {trainer.get_num_updates()}
+
+
+def _gradients_after_backward(extra, micro_batches):
+    """Flat gradient arena(s) after forward + backward of ``micro_batches`` (no optimizer step), dropout off."""
+    torch.manual_seed(0)
+    trainer, batches = _trainer(["--fp16-init-scale", "4", "--dropout", "0.0", "--attention-dropout", "0.0",
+                                 "--emb-dropout", "0.0", "--activation-dropout", "0.0"] + extra)
+    trainer.zero_grad()
+    trainer.model.train()
+    for i in range(micro_batches):
+        from unicore import utils
+
+        sample = utils.move_to_cuda(batches[i])
+        trainer.task.train_step(sample, trainer.model, trainer.loss, trainer.optimizer, 0)
+    torch.cuda.synchronize()
+    flats = [f.grad.detach().float().clone() for g in trainer.optimizer.fp16_params for f in g["params"]]
+    sinks = sum(1 for p in trainer.get_model().parameters() if getattr(p, "_ub_direct_grad", False))
+    return flats, sinks
+
+
+@pytest.mark.parametrize("micro_batches", [1, 3])
+def test_gradient_sinks_leave_the_same_gradients_as_autograd_accumulation(micro_batches):
+    """Backward kernels that add weight / bias / LayerNorm gradients straight into the flat arena
+    (``ops/grad_sink.py``) against plain autograd accumulation: same arena contents, also across gradient
+    accumulation micro-batches (the sink adds in fp32 before the single rounding, autograd rounds twice)."""
+    direct, n_direct = _gradients_after_backward([], micro_batches)
+    plain, n_plain = _gradients_after_backward(["--no-grad-sinks"], micro_batches)
+    assert n_direct > 0 and n_plain == 0
+    for a, b in zip(direct, plain):
+        assert a.shape == b.shape and torch.isfinite(a).all()
+        scale = b.abs().max().item() + 1e-12
+        assert (a - b).abs().max().item() / scale < 4e-3
+        assert b.abs().sum().item() > 0
+
+
+def test_gradient_sinks_remove_the_accumulate_kernels():
+    """The point of the sinks: far fewer ``add`` kernel launches per step (one AccumulateGrad add per parameter
+    before; only the parameters outside our layer kernels - embeddings, tied LM head - afterwards)."""
+    from torch.profiler import ProfilerActivity, profile
+
+    counts = {}
+    for name, extra in (("direct", []), ("plain", ["--no-grad-sinks"])):
+        torch.manual_seed(0)
+        trainer, batches = _trainer(["--fp16-init-scale", "4", "--deferred-overflow-check"] + extra)
+        for i in range(3):
+            trainer.train_step([batches[i % 4]])
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            trainer.train_step([batches[3]])
+            torch.cuda.synchronize()
+        counts[name] = sum(e.count for e in prof.key_averages() if "CUDAFunctor_add" in e.key)
+    assert counts["direct"] < counts["plain"] - 10, counts

@@ -87,7 +87,7 @@ def bulid_future_mask(seq_len):  # (sic) name kept for API compatibility
 # ------------------------------------------------------------------------------------------------
 def _linear_no_bias(layer: nn.Linear, x):
     """GEMM only; the bias is applied by the fused epilogue kernel that follows."""
-    return F.linear(x, layer.weight)
+    return ops.linear(x, layer.weight, None)
 
 
 class _BlockMixin:
@@ -111,7 +111,7 @@ class _BlockMixin:
         if self.post_ln and self._fused_ok(o):
             # out_proj bias + dropout + residual + LayerNorm in one pass over the GEMM output
             out = ops.bias_dropout_add_layer_norm(
-                F.linear(o, proj.weight), proj.bias, residual, norm.weight, norm.bias,
+                ops.linear(o, proj.weight, None), proj.bias, residual, norm.weight, norm.bias,
                 self.dropout, norm.eps, self.training,
             )
             return out, extra

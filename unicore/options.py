@@ -57,6 +57,9 @@ def _global_rows():
               help="fp16 + fused optimizer: do not read the gradient norm on the host before the update; the "
                    "fused Adam kernel skips itself when the norm is non-finite and the loss scaler learns about "
                    "the overflow before the next backward pass (removes the per-step pipeline drain)"),
+        _flag("--no-grad-sinks", action="store_true",
+              help="keep plain autograd accumulation of parameter gradients (default on CUDA with flat 16-bit arenas: the "
+                   "backward kernels add weight / bias / LayerNorm gradients straight into the gradient arena)"),
         _flag("--fp16-scale-tolerance", default=0.0, type=float,
               help="pct of updates that can overflow before decreasing the loss scale"),
         _flag("--min-loss-scale", default=1e-4, type=float, metavar="D",

@@ -181,6 +181,7 @@ class Trainer(object):
             )
             if hasattr(engine, "attach_optimizer"):
                 engine.attach_optimizer(self._optimizer, params=[p for _, p in named])
+            self._configure_grad_sinks([p for _, p in named])
         else:
             self._optimizer = optim.build_optimizer(args, named)
         if hasattr(self._optimizer, "add_late_overflow_handler"):
@@ -188,6 +189,22 @@ class Trainer(object):
         self._connect_ema()
         self._lr_scheduler = lr_scheduler.build_lr_scheduler(args, self._optimizer, self._total_train_steps)
         self._lr_scheduler.step_update(0)
+
+    def _configure_grad_sinks(self, params):
+        """Backward kernels may accumulate parameter gradients straight into the flat gradient arena
+        (``unicore_b200/ops/grad_sink.py``: no temporaries, no AccumulateGrad add per parameter).  That bypasses autograd's
+        gradient hooks, so it is enabled for a single process and for engines that take their "gradient ready" signal
+        from the sink (``--ddp-backend b200`` registers itself in ``attach_optimizer``); torch DDP and the legacy engine
+        keep plain autograd accumulation."""
+        try:
+            from unicore_b200.ops import grad_sink
+        except ImportError:
+            return
+        engine = self.dp_engine
+        if self.data_parallel_world_size == 1:
+            grad_sink.enable(params) if self.cuda and not getattr(self.args, "no_grad_sinks", False) else grad_sink.disable(params)
+        elif not hasattr(engine, "attach_optimizer") or getattr(self.args, "no_grad_sinks", False):
+            grad_sink.disable(params)
 
     def _connect_ema(self):
         """Let the optimizer kernel carry the EMA update when it can (fused tail: on the shard; replicated fused Adam:

@@ -18,6 +18,7 @@ from typing import Optional
 import torch
 import torch.nn.functional as F
 
+from . import grad_sink
 from ._native import aligned_param, native, use_native
 
 
@@ -28,12 +29,17 @@ class _BiasGeluFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bias):
         ctx.save_for_backward(x, bias)
+        ctx.bias_sink = grad_sink.claim(bias, ctx.needs_input_grad[1])
         return native().bias_gelu_fwd(x, bias)
 
     @staticmethod
     def backward(ctx, dy):
         x, bias = ctx.saved_tensors
-        dx, dbias = native().bias_gelu_bwd(dy.contiguous(), x, bias)
+        claimed = ctx.bias_sink
+        dx, dbias = native().bias_gelu_bwd(dy.contiguous(), x, bias, grad_sink.sink(claimed))
+        if claimed is not None:  # the bias gradient went straight into the arena
+            grad_sink.done(claimed)
+            dbias = None
         return dx, dbias
 
 
@@ -47,12 +53,17 @@ def bias_gelu(x: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
 # Linear with a fast bias gradient
 # ------------------------------------------------------------------------------------------------
 class _LinearFn(torch.autograd.Function):
-    """``x @ W^T + b`` - cuBLAS GEMMs both ways; the bias gradient is our column-sum kernel (fp32 accumulation,
-    one pass at copy bandwidth) instead of ATen's generic reduction."""
+    """``x @ W^T (+ b)`` - cuBLAS GEMMs both ways; the bias gradient is our column-sum kernel (fp32 accumulation, one
+    pass at copy bandwidth) instead of ATen's generic reduction; weight and bias gradients accumulate straight into
+    the optimizer's gradient arena when the parameters are claimed (``grad_sink``): the weight-gradient GEMM runs with
+    beta = 1 on the arena view."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
+        ctx.w_sink = grad_sink.claim(weight, ctx.needs_input_grad[1])
+        ctx.b_sink = grad_sink.claim(bias, ctx.needs_input_grad[2]) if bias is not None else None
+        ctx.has_bias = bias is not None
         return F.linear(x, weight, bias)
 
     @staticmethod
@@ -64,23 +75,39 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = dy.matmul(weight)
         if ctx.needs_input_grad[1]:
-            dw = dy2.t().mm(x.reshape(-1, x.shape[-1]))
-        if ctx.needs_input_grad[2]:
-            db = native().column_sum(dy2) if dy2.data_ptr() % 16 == 0 else dy2.sum(dim=0)
+            x2 = x.reshape(-1, x.shape[-1])
+            if ctx.w_sink is not None:
+                ctx.w_sink.grad.addmm_(dy2.t(), x2)
+                grad_sink.done(ctx.w_sink)
+            else:
+                dw = dy2.t().mm(x2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            claimed = ctx.b_sink
+            if dy2.data_ptr() % 16 == 0 and dy2.shape[-1] % 8 == 0 and dy2.dtype in (torch.float16, torch.bfloat16):
+                db = native().column_sum(dy2, grad_sink.sink(claimed))
+            else:
+                db = dy2.sum(dim=0)
+                if claimed is not None:
+                    claimed.grad.add_(db)
+            if claimed is not None:
+                grad_sink.done(claimed)
+                db = None
         return dx, dw, db
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``F.linear`` whose backward computes the bias gradient with ``column_sum`` (``csrc/fused/elementwise.cu``)."""
-    if (
-        bias is not None
-        and use_native(x, weight, bias)
-        and x.dtype in (torch.float16, torch.bfloat16)
-        and weight.dtype == x.dtype and bias.dtype == x.dtype
+    """``F.linear`` whose backward computes the bias gradient with ``column_sum`` (``csrc/fused/elementwise.cu``) and
+    writes parameter gradients in place into the gradient arena when they are claimed (``grad_sink``)."""
+    if not (use_native(x, weight, bias) and x.dtype in (torch.float16, torch.bfloat16) and weight.dtype == x.dtype
+            and torch.is_grad_enabled()):
+        return F.linear(x, weight, bias)
+    direct = grad_sink.wants(weight) or grad_sink.wants(bias)  # (grad mode was checked above)
+    fast_bias = (
+        bias is not None and bias.dtype == x.dtype
         and weight.shape[0] % 8 == 0 and weight.shape[0] >= 256  # narrow outputs leave the column kernel's CTAs idle
-        and torch.is_grad_enabled()
         and (x.requires_grad or weight.requires_grad or bias.requires_grad)
-    ):
+    )
+    if direct or fast_bias:
         return _LinearFn.apply(x, weight, bias)
     return F.linear(x, weight, bias)
 
@@ -100,6 +127,9 @@ class _BiasDropoutAddLNFn(torch.autograd.Function):
         ctx.p = p
         ctx.rng = (seed, offset)
         ctx.has_bias = bias is not None
+        need = ctx.needs_input_grad
+        ctx.sinks = (grad_sink.claim(bias, need[1]) if bias is not None else None, grad_sink.claim(ln_weight, need[3]),
+                     grad_sink.claim(ln_bias, need[4]))
         return y.view(shape)
 
     @staticmethod
@@ -107,11 +137,24 @@ class _BiasDropoutAddLNFn(torch.autograd.Function):
         summed, ln_weight, mean, rstd = ctx.saved_tensors
         dy2 = dy.contiguous().view(summed.shape)
         # dsum: gradient w.r.t. (residual + dropout(x+bias)); dx = dropout-masked dsum
+        b_sink, g_sink, be_sink = ctx.sinks
         dsum, dx, dgamma, dbeta, dbias = native().bias_dropout_add_ln_bwd(
-            dy2, summed, mean, rstd, ln_weight, ctx.p, ctx.rng[0], ctx.rng[1], ctx.has_bias
+            dy2, summed, mean, rstd, ln_weight, ctx.p, ctx.rng[0], ctx.rng[1], ctx.has_bias,
+            grad_sink.sink(g_sink), grad_sink.sink(be_sink), grad_sink.sink(b_sink),
         )
-        if ctx.has_bias and dbias is None:
+        if ctx.has_bias and dbias is None:  # geometries without the in-kernel bias sum
             dbias = dx.sum(dim=0)
+            if b_sink is not None:
+                b_sink.grad.add_(dbias)
+        if g_sink is not None:
+            grad_sink.done(g_sink)
+            dgamma = None
+        if be_sink is not None:
+            grad_sink.done(be_sink)
+            dbeta = None
+        if b_sink is not None:
+            grad_sink.done(b_sink)
+            dbias = None
         return dx.view(dy.shape), dbias, dsum.view(dy.shape), dgamma, dbeta, None, None, None
 
 

@@ -12,6 +12,7 @@ from typing import Optional
 import torch
 import torch.nn.functional as F
 
+from . import grad_sink
 from ._native import aligned_param, native, use_native
 
 
@@ -23,13 +24,22 @@ class _LayerNormFn(torch.autograd.Function):
         y, mean, rstd = native().layernorm_fwd(x2, weight, bias, eps)
         ctx.save_for_backward(x2, weight, mean, rstd)
         ctx.has_bias = bias is not None
+        need = ctx.needs_input_grad  # gradients go straight into the arena
+        ctx.sinks = (grad_sink.claim(weight, need[1]), grad_sink.claim(bias, need[2]))
         return y.view(shape)
 
     @staticmethod
     def backward(ctx, dy):
         x2, weight, mean, rstd = ctx.saved_tensors
         dy2 = dy.contiguous().view(x2.shape)
-        dx, dgamma, dbeta = native().layernorm_bwd(dy2, x2, mean, rstd, weight)
+        g_sink, b_sink = ctx.sinks
+        dx, dgamma, dbeta = native().layernorm_bwd(dy2, x2, mean, rstd, weight, grad_sink.sink(g_sink), grad_sink.sink(b_sink))
+        if g_sink is not None:
+            grad_sink.done(g_sink)
+            dgamma = None
+        if b_sink is not None:
+            grad_sink.done(b_sink)
+            dbeta = None
         return dx.view(dy.shape), dgamma, (dbeta if ctx.has_bias else None), None
 
 
@@ -40,13 +50,17 @@ class _RMSNormFn(torch.autograd.Function):
         x2 = x.contiguous().view(-1, shape[-1])
         y, rstd = native().rmsnorm_fwd(x2, weight, eps)
         ctx.save_for_backward(x2, weight, rstd)
+        ctx.g_sink = grad_sink.claim(weight, ctx.needs_input_grad[1])
         return y.view(shape)
 
     @staticmethod
     def backward(ctx, dy):
         x2, weight, rstd = ctx.saved_tensors
         dy2 = dy.contiguous().view(x2.shape)
-        dx, dgamma = native().rmsnorm_bwd(dy2, x2, rstd, weight)
+        dx, dgamma = native().rmsnorm_bwd(dy2, x2, rstd, weight, grad_sink.sink(ctx.g_sink))
+        if ctx.g_sink is not None:
+            grad_sink.done(ctx.g_sink)
+            dgamma = None
         return dx.view(dy.shape), dgamma, None
 
 

@@ -211,6 +211,12 @@ class SymmDataParallel(nn.Module):
                     b.total += 1
                 self._param_buckets[p] = touched
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
+        # kernels that write parameter gradients straight into the arena (ops/grad_sink.py) bypass AccumulateGrad and its
+        # hooks: they report through this callback instead
+        from unicore_b200.ops import grad_sink
+
+        self._sink_params = [p for p in params if p in self._param_buckets]
+        grad_sink.enable(self._sink_params, on_written=self._on_grad_ready)
         self._reset_counters()
         self._covers_all_params = all(p in self._param_buckets for p in params if p.requires_grad)
         if self.tail is None and self._covers_all_params and hasattr(optimizer, "set_external_grad_sq_norm"):
@@ -233,6 +239,8 @@ class SymmDataParallel(nn.Module):
         self._next = 0
         self._started = False
         self._seen = set()
+        for p in getattr(self, "_sink_params", ()):
+            p._ub_pending = 0
 
     def _on_grad_ready(self, param):
         if self.accumulate_grads or id(param) in self._seen:
