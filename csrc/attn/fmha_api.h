@@ -24,7 +24,11 @@ struct FmhaFwdParams {
   // TMA descriptors (csrc/attn/tma_map.h): 128 x 64 tiles of q / k / v, 128 x 128 tiles of the bias
   CUtensorMap tm_q, tm_k, tm_v, tm_bias;
 };
+// Dispatches to the warp-specialised kernel (fmha_fwd_ws_sm100.cu) when it supports the shape, else to the one-role
+// kernel (fmha_fwd_sm100.cu); UNICORE_B200_FMHA_FWD=v1 forces the latter.
 void launch_fmha_fwd(const FmhaFwdParams& p, cudaStream_t stream);
+bool fmha_fwd_ws_supported(const FmhaFwdParams& p);
+void launch_fmha_fwd_ws(const FmhaFwdParams& p, cudaStream_t stream);
 
 struct FmhaBwdParams {
   FmhaFwdParams f;   // same inputs as forward (out/lse hold the forward results)

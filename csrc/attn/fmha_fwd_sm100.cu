@@ -25,6 +25,7 @@
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "../common.cuh"
@@ -350,6 +351,14 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
 }  // namespace
 
 void launch_fmha_fwd(const FmhaFwdParams& p, cudaStream_t stream) {
+  static const bool force_v1 = [] {
+    const char* e = getenv("UNICORE_B200_FMHA_FWD");
+    return e != nullptr && e[0] == 'v' && e[1] == '1';
+  }();
+  if (!force_v1 && fmha_fwd_ws_supported(p)) {
+    launch_fmha_fwd_ws(p, stream);
+    return;
+  }
   dim3 grid((p.Lq + kBlockM - 1) / kBlockM, p.H, p.B);
   if (p.is_bf16) {
     auto kern = fmha_fwd_kernel<__nv_bfloat16>;

@@ -50,6 +50,14 @@ TC_DEVICE bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// one arrival (release.cta): pairs with mbar_wait on the other side
+TC_DEVICE void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// named barrier among `nthreads` threads of the CTA (id 1..15; 0 is __syncthreads)
+TC_DEVICE void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // Spin with a wall-clock bound: a lost arrive must abort the kernel (trap) instead of hanging the GPU.
 TC_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;

@@ -42,7 +42,7 @@ def _make(B, H, Lq, Lk, dtype, packed=True, seed=0):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("shape", [(2, 3, 128, 128), (2, 4, 512, 512), (1, 2, 256, 384), (2, 2, 200, 72), (1, 1, 8, 8)])
+@pytest.mark.parametrize("shape", [(2, 3, 128, 128), (2, 4, 512, 512), (1, 2, 256, 384), (2, 2, 200, 72), (1, 1, 8, 8), (1, 2, 640, 1000)])
 @pytest.mark.parametrize("with_bias,with_mask", [(False, False), (True, False), (True, True)])
 def test_fmha_forward(dtype, shape, with_bias, with_mask):
     ops = _ops()
