@@ -23,9 +23,11 @@ struct FmhaFwdParams {
   long long* trace;        // profiling only: per-phase clock64() stamps of CTA (0,0,0), thread 0; usually null
   // TMA descriptors (csrc/attn/tma_map.h): 128 x 64 tiles of q / k / v, 128 x 128 tiles of the bias
   CUtensorMap tm_q, tm_k, tm_v, tm_bias;
+  // 128-byte-swizzled maps of the same tensors (tma_map.h): one request per 128-byte row
+  CUtensorMap sw_q, sw_k, sw_v, sw_bias;
 };
-// Dispatches to the warp-specialised kernel (fmha_fwd_ws_sm100.cu) when it supports the shape, else to the one-role
-// kernel (fmha_fwd_sm100.cu); UNICORE_B200_FMHA_FWD=v1 forces the latter.
+// One-role kernel (fmha_fwd_sm100.cu, two CTAs per SM) by default; UNICORE_B200_FMHA_FWD=ws selects the warp-specialised
+// kernel (fmha_fwd_ws_sm100.cu: TMA warp + MMA warp + two softmax groups on two query tiles).
 void launch_fmha_fwd(const FmhaFwdParams& p, cudaStream_t stream);
 bool fmha_fwd_ws_supported(const FmhaFwdParams& p);
 void launch_fmha_fwd_ws(const FmhaFwdParams& p, cudaStream_t stream);
@@ -46,10 +48,10 @@ struct FmhaBwdParams {
   // kernel: 4096 red.v4 per tile.)  Both null when the bias needs no gradient.
   void* ds_buf;      // [B, H, Lq, Lk] 16-bit
   void* dbias;       // [bias_batch, H, Lq, Lk] 16-bit; == ds_buf when bias_batch == B
-  CUtensorMap tm_ds;
+  CUtensorMap sw_ds;   // 128-byte-swizzled map of ds_buf (two 64-column boxes per tile)
   int debug_flags;   // profiling only: 1 = skip dBias reductions, 2 = skip dQ reductions, 4 = skip exp/dS math
   long long* trace;  // profiling only: clock64() stamps of one CTA (see UB_BTRACE); usually null
-  CUtensorMap tm_do;  // 128 x 64 tiles of dO
+  CUtensorMap sw_do;  // 128 x 64 tiles of dO (128-byte swizzle)
 };
 void launch_fmha_bwd(const FmhaBwdParams& p, cudaStream_t stream);
 

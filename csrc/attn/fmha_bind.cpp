@@ -83,6 +83,10 @@ void fill_common(ub::FmhaFwdParams& p, const Tensor& q, const Tensor& k, const T
   ok = ok && ub::make_head_tile_map(&p.tm_k, p.k, bf16, p.B, p.Lk, p.H, p.k_sb, p.k_sl, 128);
   ok = ok && ub::make_head_tile_map(&p.tm_v, p.v, bf16, p.B, p.Lk, p.H, p.v_sb, p.v_sl, 128);
   if (p.bias != nullptr) ok = ok && ub::make_bias_tile_map(&p.tm_bias, p.bias, bf16, p.bias_batch * p.H, p.Lq, p.Lk);
+  ok = ok && ub::make_head_tile_map_sw128(&p.sw_q, p.q, bf16, p.B, p.Lq, p.H, p.q_sb, p.q_sl, p.q_sh, 128);
+  ok = ok && ub::make_head_tile_map_sw128(&p.sw_k, p.k, bf16, p.B, p.Lk, p.H, p.k_sb, p.k_sl, p.k_sh, 128);
+  ok = ok && ub::make_head_tile_map_sw128(&p.sw_v, p.v, bf16, p.B, p.Lk, p.H, p.v_sb, p.v_sl, p.v_sh, 128);
+  if (p.bias != nullptr) ok = ok && ub::make_bias_tile_map_sw128(&p.sw_bias, p.bias, bf16, p.bias_batch * p.H, p.Lq, p.Lk);
   TORCH_CHECK(ok, "cuTensorMapEncodeTiled failed for the attention operands");
 }
 
@@ -121,6 +125,8 @@ std::tuple<Tensor, Tensor, OptTensor> fmha_fwd(const Tensor& q, const Tensor& k,
       printf("fmha_fwd trace tile %d:", j);
       for (int sidx = 1; sidx < 12; ++sidx) printf(" %lld", (long long)(acc[j][sidx] - acc[j][sidx - 1]));
       if (j > 0) printf("  | since prev tile start %lld", (long long)(acc[j][0] - acc[j - 1][0]));
+      printf("\n   abs:");
+      for (int sidx = 0; sidx < 12; ++sidx) printf(" %lld", (long long)(acc[j][sidx] - acc[0][0]));
       printf("\n");
     }
   }
@@ -148,8 +154,8 @@ std::tuple<Tensor, Tensor, Tensor, OptTensor> fmha_bwd(const Tensor& dout, const
     p.f.drop_bits = reinterpret_cast<uint32_t*>(drop_bits->data_ptr());
   }
   p.dout = dout.data_ptr();
-  TORCH_CHECK(ub::make_head_tile_map(&p.tm_do, p.dout, p.f.is_bf16 != 0, p.f.B, p.f.Lq, p.f.H,
-                                     (long long)p.f.Lq * p.f.H * 64, (long long)p.f.H * 64, 128),
+  TORCH_CHECK(ub::make_head_tile_map_sw128(&p.sw_do, p.dout, p.f.is_bf16 != 0, p.f.B, p.f.Lq, p.f.H,
+                                           (long long)p.f.Lq * p.f.H * 64, (long long)p.f.H * 64, 64, 128),
               "cuTensorMapEncodeTiled failed for dO");
   {
     const char* dbg = std::getenv("UNICORE_FMHA_DEBUG");
@@ -181,7 +187,7 @@ std::tuple<Tensor, Tensor, Tensor, OptTensor> fmha_bwd(const Tensor& dout, const
     p.ds_buf = ds_buf.data_ptr();
     dbias = (p.f.bias_batch == p.f.B) ? ds_buf : torch::empty({p.f.bias_batch, p.f.H, p.f.Lq, p.f.Lk}, q.options());
     p.dbias = dbias->data_ptr();
-    TORCH_CHECK(ub::make_bias_tile_map(&p.tm_ds, p.ds_buf, p.f.is_bf16 != 0, p.f.B * p.f.H, p.f.Lq, p.f.Lk),
+    TORCH_CHECK(ub::make_bias_tile_map_sw128(&p.sw_ds, p.ds_buf, p.f.is_bf16 != 0, p.f.B * p.f.H, p.f.Lq, p.f.Lk),
                 "cuTensorMapEncodeTiled failed for the dS scratch tensor");
   }
   p.delta = delta.data_ptr<float>();

@@ -17,8 +17,8 @@
 //     which made the kernel atomics-bound.)
 //   Tensor-pipe order per tile: dQ_i (the math warps wait for it; its read-out and the next tile's loads then
 //   run under the rest), dV, dK, S / dP of tile i+1.  Q_{i+1}, dO_{i+1} and the bias tile of (i+1, j) arrive by
-//   TMA (5-D tensor maps, csrc/attn/tma_map.h) in the alternate buffers one tile ahead; the bias tile lands in the
-//   buffer that later receives dS (same core-matrix layout => in-place overwrite, chunk by chunk).
+//   TMA (128-byte-swizzled boxes, csrc/attn/tma_map.h) in the alternate buffers one tile ahead; the bias tile lands in
+//   the buffer that later receives dS (same swizzled layout => in-place overwrite, chunk by chunk).
 //   Every operand tile is written once and presented to the tensor core as K-major or MN-major by
 //   swapping descriptor strides (no transposes).
 // Pre-pass:  delta = rowsum(dO o O).   Post-pass: dq = sum of the per-key-tile partials (and dbias = batch sum of dS).
@@ -198,13 +198,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
     const int q0 = i * kBM;
     const uint32_t buf = (uint32_t)(i & 1);
     const uint32_t bar = bar_in0 + buf * 8;
-    if (has_bias) {  // first: the math warps wait for it
+    if (has_bias) {  // first: the math warps wait for it.  128 x 128 tile = two 64-column boxes
       mbar_expect_tx(bar_bias0 + buf * 8, kBiasBytes);
-      tma_load_5d(smem_base + kOffDS + buf * 32768, &p.tm_bias, 0, 0, key_tile0 / 8, q0 / 8, bias_nb, bar_bias0 + buf * 8);
+      tma_load_3d(smem_base + kOffDS + buf * 32768, &p.sw_bias, key_tile0, q0, bias_nb, bar_bias0 + buf * 8);
+      tma_load_3d(smem_base + kOffDS + buf * 32768 + 16384, &p.sw_bias, key_tile0 + 64, q0, bias_nb, bar_bias0 + buf * 8);
     }
     mbar_expect_tx(bar, 2 * kTileBytes);
-    tma_load_5d(smem_base + kOffQ + buf * 16384, &p.tm_q, 0, 0, h * 8, q0 / 8, b, bar);
-    tma_load_5d(smem_base + kOffDO + buf * 16384, &bp.tm_do, 0, 0, h * 8, q0 / 8, b, bar);
+    tma_load_4d(smem_base + kOffQ + buf * 16384, &p.sw_q, 0, h, q0, b, bar);
+    tma_load_4d(smem_base + kOffDO + buf * 16384, &bp.sw_do, 0, h, q0, b, bar);
   };
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t idesc_s = make_idesc_f16(kBM, kBN, kFmt, 0, 0);    // S, dP: both operands K-major
@@ -222,8 +223,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
   fence_after_thread_sync();
   if (tid == kIssuer) {  // barriers are initialised: K, V of this CTA and the first (Q, dO, bias) tile
     mbar_expect_tx(bar_kv, 2 * kTileBytes);
-    tma_load_5d(smem_base + kOffK, &p.tm_k, 0, 0, h * 8, key_tile0 / 8, b, bar_kv);
-    tma_load_5d(smem_base + kOffV, &p.tm_v, 0, 0, h * 8, key_tile0 / 8, b, bar_kv);
+    tma_load_4d(smem_base + kOffK, &p.sw_k, 0, h, key_tile0, b, bar_kv);
+    tma_load_4d(smem_base + kOffV, &p.sw_v, 0, h, key_tile0, b, bar_kv);
     issue_tile(0);
   }
   const uint32_t tmem_base = *tmem_slot;
@@ -235,14 +236,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
     const uint32_t sQ = smem_base + kOffQ + buf * 16384, sDO = smem_base + kOffDO + buf * 16384;
 #pragma unroll
     for (int kk = 0; kk < kD / 16; ++kk) {
-      const uint64_t dq_ = make_smem_desc(sQ + kk * 256, 128, 1024);
-      const uint64_t dk_ = make_smem_desc(smem_base + kOffK + kk * 256, 128, 1024);
+      const uint64_t dq_ = make_smem_desc_sw128(sQ + kk * 32);
+      const uint64_t dk_ = make_smem_desc_sw128(smem_base + kOffK + kk * 32);
       umma_f16_ss(tmem_base + kColS, dq_, dk_, idesc_s, kk > 0 ? 1u : 0u);
     }
 #pragma unroll
     for (int kk = 0; kk < kD / 16; ++kk) {
-      const uint64_t ddo = make_smem_desc(sDO + kk * 256, 128, 1024);
-      const uint64_t dv_ = make_smem_desc(smem_base + kOffV + kk * 256, 128, 1024);
+      const uint64_t ddo = make_smem_desc_sw128(sDO + kk * 32);
+      const uint64_t dv_ = make_smem_desc_sw128(smem_base + kOffV + kk * 32);
       umma_f16_ss(tmem_base + kColDP, ddo, dv_, idesc_s, kk > 0 ? 1u : 0u);
     }
     umma_commit(bar_a);
@@ -305,11 +306,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
       tmem_wait_ld();
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        const uint32_t off = tile128_off(r, (col0 >> 3) + v);
+        const uint32_t off = tile128_off(r, (col0 >> 3) + v);                              // P: core-matrix layout
+        const uint32_t off_ds = (uint32_t)(quarter >> 1) * 16384u + sw128_off(r, (quarter & 1) * 4 + v);  // bias / dS
         float bf[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) bf[e] = 0.f;
-        if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(smem + offDS + off), bf);
+        if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(smem + offDS + off_ds), bf);
         if (tile_masked) {
           const float4 ka = *reinterpret_cast<const float4*>(kadd + col0 + v * 8);
           const float4 kb = *reinterpret_cast<const float4*>(kadd + col0 + v * 8 + 4);
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
           od.w[e] = bwd_pack2<T>(ds[2 * e], ds[2 * e + 1]);
         }
         *reinterpret_cast<Vec16*>(smem + kOffP + off) = op;
-        *reinterpret_cast<Vec16*>(smem + offDS + off) = od;   // in place over the consumed bias chunk
+        *reinterpret_cast<Vec16*>(smem + offDS + off_ds) = od;   // in place over the consumed bias chunk
       }
     }
     UB_BTRACE(4);
@@ -364,28 +366,29 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
       fence_after_thread_sync();
       const uint32_t sDS = smem_base + offDS;
       if (bp.ds_buf != nullptr) {  // bias gradient: the dS tile leaves through one TMA store
-        tma_store_5d(&bp.tm_ds, 0, 0, key_tile0 / 8, q0 / 8, b * p.H + h, sDS);
+        tma_store_3d(&bp.sw_ds, key_tile0, q0, b * p.H + h, sDS);
+        tma_store_3d(&bp.sw_ds, key_tile0 + 64, q0, b * p.H + h, sDS + 16384);
         tma_store_commit();
       }
       // Issue order = execution order on the tensor pipe: dQ first (the threads are waiting for it: its read-out and
       // the next tile's statistics loads then run under dV / dK), then dV, dK, and S / dP of the next tile.
 #pragma unroll
       for (int kk = 0; kk < kBN / 16; ++kk) {  // dQ: reduction over the 128 keys
-        const uint64_t a_ds = make_smem_desc(sDS + kk * 256, 128, 2048);                  // dS   (K-major)
-        const uint64_t b_k = make_smem_desc(smem_base + kOffK + kk * 2048, 1024, 128);    // K    (MN-major)
+        const uint64_t a_ds = make_smem_desc_sw128(sDS + (kk >> 2) * 16384 + (kk & 3) * 32);   // dS (K-major, 2 x 64 keys)
+        const uint64_t b_k = make_smem_desc_sw128(smem_base + kOffK + kk * 2048);              // K  (MN-major)
         umma_f16_ss(tmem_base + kColDQ, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
       }
       umma_commit(bar_q);
 #pragma unroll
       for (int kk = 0; kk < kBM / 16; ++kk) {  // dV: reduction over the 128 query rows, 16 per step
         const uint64_t a_p = make_smem_desc(smem_base + kOffP + kk * 4096, 2048, 128);    // P^T  (MN-major)
-        const uint64_t b_do = make_smem_desc(sDO + kk * 2048, 1024, 128);                 // dO   (MN-major)
+        const uint64_t b_do = make_smem_desc_sw128(sDO + kk * 2048);                      // dO   (MN-major)
         umma_f16_ss(tmem_base + kColDV, a_p, b_do, idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
       }
 #pragma unroll
       for (int kk = 0; kk < kBM / 16; ++kk) {  // dK
-        const uint64_t a_ds = make_smem_desc(sDS + kk * 4096, 2048, 128);                 // dS^T (MN-major)
-        const uint64_t b_q = make_smem_desc(sQ + kk * 2048, 1024, 128);                   // Q    (MN-major)
+        const uint64_t a_ds = make_smem_desc_sw128(sDS + kk * 2048, 16384);               // dS^T (MN-major, M = 2 x 64 keys)
+        const uint64_t b_q = make_smem_desc_sw128(sQ + kk * 2048);                        // Q    (MN-major)
         umma_f16_ss(tmem_base + kColDK, a_ds, b_q, idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
       }
       umma_commit(bar_v);

@@ -58,7 +58,7 @@ constexpr uint32_t kSmBar = kSmFlag + 128;
 constexpr uint32_t kWsSmemBytes = kSmBar + 256;
 
 // mbarrier slots
-enum : int { kBarQ = 0, kBarKFull, kBarKEmpty, kBarVFull, kBarVEmpty, kBarGroup0 };
+enum : int { kBarQ = 0, kBarQB, kBarKFull, kBarKEmpty, kBarVFull, kBarVEmpty, kBarGroup0 };
 enum : int { kGSFull = 0, kGSFree, kGPFull, kGPvDone, kGBiasFull, kGBiasEmpty, kGCount };
 constexpr int kNumBars = kBarGroup0 + 2 * kGCount;
 static_assert(kNumBars * 8 + 8 <= 256, "barrier block");
@@ -82,6 +82,11 @@ UB_DEVICE void warp_arrive(uint32_t bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
+#define UB_WTRACE(cond, slot)                                                               \
+  do {                                                                                      \
+    if (trace != nullptr && (cond) && j < 64) trace[j * 12 + (slot)] = clock64();           \
+  } while (0)
+
 template <typename T>
 __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid_constant__ FmhaFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -95,6 +100,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
   float* kadd = reinterpret_cast<float*>(smem + kSmKAdd);
   int* tile_flag = reinterpret_cast<int*>(smem + kSmFlag);
 
+  // profiling only: clock64() stamps of CTA (0,1,1): slots 0-6 lane 0 of the first softmax warp, 7-11 the MMA issuer
+  long long* trace = (p.trace != nullptr && lane == 0 && blockIdx.x == 0 && blockIdx.y == 1 && blockIdx.z == 1) ? p.trace : nullptr;
   const bool has_bias = p.bias != nullptr;
   const int n_tiles = (p.Lk + kBlockN - 1) / kBlockN;
   const int nq = (q0 + kBlockM < p.Lq) ? 2 : 1;   // the second query tile may not exist
@@ -106,6 +113,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
   }
   if (tid == 32) {
     mbar_init(bar(kBarQ), 1);
+    mbar_init(bar(kBarQB), 1);
     mbar_init(bar(kBarKFull), 1);
     mbar_init(bar(kBarKEmpty), 1);
     mbar_init(bar(kBarVFull), 1);
@@ -139,25 +147,31 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      mbar_expect_tx(bar(kBarQ), nq * kTile);
-      for (int g = 0; g < nq; ++g)
-        tma_load_5d(smem_base + kSmQ + g * kTile, &p.tm_q, 0, 0, h * 8, (q0 + g * kBlockM) / 8, b, bar(kBarQ));
+      // first what the first MMA needs (Q_A, K_0), then Q_B: group A starts a third of the copy time earlier, and the
+      // two groups stay out of phase (their exp phases then do not compete for the SFU)
+      mbar_expect_tx(bar(kBarQ), kTile);
+      tma_load_4d(smem_base + kSmQ, &p.sw_q, 0, h, q0, b, bar(kBarQ));
       for (int j = 0; j < n_tiles; ++j) {
         const uint32_t free_parity = (uint32_t)((j & 1) ^ 1);   // passes on a fresh barrier, then follows the consumer
         mbar_wait(bar(kBarKEmpty), free_parity);
         mbar_expect_tx(bar(kBarKFull), kTile);
-        tma_load_5d(smem_base + kSmK, &p.tm_k, 0, 0, h * 8, (j * kBlockN) / 8, b, bar(kBarKFull));
+        tma_load_4d(smem_base + kSmK, &p.sw_k, 0, h, j * kBlockN, b, bar(kBarKFull));
+        if (j == 0 && nq > 1) {
+          mbar_expect_tx(bar(kBarQB), kTile);
+          tma_load_4d(smem_base + kSmQ + kTile, &p.sw_q, 0, h, q0 + kBlockM, b, bar(kBarQB));
+        }
         if (has_bias) {
           for (int g = 0; g < nq; ++g) {
             mbar_wait(gbar(g, kGBiasEmpty), free_parity);
             mbar_expect_tx(gbar(g, kGBiasFull), kTile2);
-            tma_load_5d(smem_base + kSmBias + g * kTile2, &p.tm_bias, 0, 0, (j * kBlockN) / 8,
-                        (q0 + g * kBlockM) / 8, bias_nb, gbar(g, kGBiasFull));
+            for (int hb = 0; hb < 2; ++hb)   // 128 x 128 tile = two 64-column boxes, one per thread half
+              tma_load_3d(smem_base + kSmBias + g * kTile2 + hb * kTile, &p.sw_bias, j * kBlockN + hb * 64,
+                          q0 + g * kBlockM, bias_nb, gbar(g, kGBiasFull));
           }
         }
         mbar_wait(bar(kBarVEmpty), free_parity);
         mbar_expect_tx(bar(kBarVFull), kTile);
-        tma_load_5d(smem_base + kSmV, &p.tm_v, 0, 0, h * 8, (j * kBlockN) / 8, b, bar(kBarVFull));
+        tma_load_4d(smem_base + kSmV, &p.sw_v, 0, h, j * kBlockN, b, bar(kBarVFull));
       }
     }
   } else if (warp == 1) {
@@ -168,8 +182,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
       auto issue_qk = [&](int g) {   // S_g = Q_g K^T: 4 x (K = 16)
 #pragma unroll
         for (int kk = 0; kk < kHeadDim / 16; ++kk) {
-          const uint64_t da = make_smem_desc(smem_base + kSmQ + g * kTile + kk * 256, 128, 1024);
-          const uint64_t db = make_smem_desc(smem_base + kSmK + kk * 256, 128, 1024);
+          const uint64_t da = make_smem_desc_sw128(smem_base + kSmQ + g * kTile + kk * 32);
+          const uint64_t db = make_smem_desc_sw128(smem_base + kSmK + kk * 32);
           umma_f16_ss(tmem_base + kTmemS + g * 128, da, db, idesc_qk, kk > 0 ? 1u : 0u);
         }
         umma_commit(gbar(g, kGSFull));
@@ -178,7 +192,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
 #pragma unroll
         for (int kk = 0; kk < kBlockN / 16; ++kk) {
           const uint64_t da = make_smem_desc(smem_base + kSmP + g * kTile2 + kk * 256, 128, 2048);
-          const uint64_t db = make_smem_desc(smem_base + kSmV + kk * 2048, 1024, 128);
+          const uint64_t db = make_smem_desc_sw128(smem_base + kSmV + kk * 2048);
           umma_f16_ss(tmem_base + kTmemO + g * 64, da, db, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(gbar(g, kGPvDone));
@@ -186,24 +200,32 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
       mbar_wait(bar(kBarQ), 0);
       mbar_wait(bar(kBarKFull), 0);
       fence_after_thread_sync();
-      for (int g = 0; g < nq; ++g) issue_qk(g);
+      issue_qk(0);
+      if (nq > 1) {
+        mbar_wait(bar(kBarQB), 0);
+        fence_after_thread_sync();
+        issue_qk(1);
+      }
       umma_commit(bar(kBarKEmpty));
       for (int j = 0; j < n_tiles; ++j) {
         const uint32_t par = (uint32_t)(j & 1);
         const bool more = j + 1 < n_tiles;
+        UB_WTRACE(true, 7);
         if (more) mbar_wait(bar(kBarKFull), par ^ 1);
         for (int g = 0; g < nq; ++g) {
           if (more) {   // group g has read S_g(j) out of tensor memory: the next logits may overwrite it
             mbar_wait(gbar(g, kGSFree), par);
             fence_after_thread_sync();
             issue_qk(g);
+            if (g == nq - 1) umma_commit(bar(kBarKEmpty));   // K_{j+1} has been read by every S MMA: K_{j+2} may land
           }
+          UB_WTRACE(true, 8 + 2 * g);
           mbar_wait(gbar(g, kGPFull), par);   // P_g(j) is in shared memory, O_g has been rescaled
           if (g == 0) mbar_wait(bar(kBarVFull), par);
           fence_after_thread_sync();
+          UB_WTRACE(true, 9 + 2 * g);
           issue_pv(g, j);
         }
-        if (more) umma_commit(bar(kBarKEmpty));
         umma_commit(bar(kBarVEmpty));
       }
     }
@@ -217,7 +239,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
       const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
       const uint32_t tS = lane_base + kTmemS + g * 128 + half * 64;
       const uint32_t tO = lane_base + kTmemO + g * 64 + half * 32;
-      const uint8_t* sBias = smem + kSmBias + g * kTile2;
+      const uint8_t* sBias = smem + kSmBias + g * kTile2 + half * kTile;   // my 64-column box
       uint8_t* sP = smem + kSmP + g * kTile2;
       float* xchg = reinterpret_cast<float*>(smem + kSmXchg) + g * 512;   // [parity][half][128]
       const int bar_id = 1 + g;
@@ -243,16 +265,19 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
         const uint32_t par = (uint32_t)(j & 1);
         const int key_tile0 = j * kBlockN;
         const bool tile_masked = tile_flag[j] != 0;
+        const bool tw = warp == 2;
+        UB_WTRACE(tw, 0);
         mbar_wait(gbar(g, kGSFull), par);
         fence_after_thread_sync();
         if (has_bias) mbar_wait(gbar(g, kGBiasFull), par);
+        UB_WTRACE(tw, 1);
 
         // logits of 8 keys: x = acc * scale + bias (+ key mask), packed fp32x2
         auto logits8 = [&](const uint32_t (&acc)[32], int col0, int v, F2 (&x)[4]) {
           float bf[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) bf[e] = 0.f;
-          if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(sBias + tile128_off(r, (col0 >> 3) + v)), bf);
+          if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(sBias + sw128_off(r, ((col0 >> 3) & 7) + v)), bf);
           if (tile_masked) {
             const float4 ka = *reinterpret_cast<const float4*>(kadd + key_tile0 + col0 + v * 8);
             const float4 kb = *reinterpret_cast<const float4*>(kadd + key_tile0 + col0 + v * 8 + 4);
@@ -281,8 +306,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
             for (int e = 0; e < 4; ++e) m_part = fmaxf(m_part, fmaxf(x[e].x, x[e].y));
           }
         }
+        UB_WTRACE(tw, 2);
         xchg[par * 256 + half * 128 + r] = m_part;
         named_bar_sync(bar_id, kGroupThreads);
+        UB_WTRACE(tw, 3);
         const float m_tile = fmaxf(m_part, xchg[par * 256 + (half ^ 1) * 128 + r]);
         const float m_true = fmaxf(m_run, m_tile);
         const bool first = m_run == -CUDART_INF_F;
@@ -309,6 +336,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
           tmem_wait_st();
         }
 
+        UB_WTRACE(tw, 4);
         // ---- pass 2: probabilities, dropout, P -> shared memory -------------------------------------------
         F2 psum2 = f2(0.f);
         const F2 log2e_2 = f2(kLog2e), nm_2 = f2(-m_use * kLog2e);
@@ -355,9 +383,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
         }
         if (has_bias) warp_arrive(gbar(g, kGBiasEmpty), lane);   // the next bias tile may land
         l_run += psum2.x + psum2.y;
+        UB_WTRACE(tw, 5);
         fence_proxy_async_smem();   // my P stores (generic proxy) before the tensor core (async proxy) reads them
         fence_before_thread_sync();
         warp_arrive(gbar(g, kGPFull), lane);
+        UB_WTRACE(tw, 6);
       }
 
       // ---- epilogue: O_g / row sum -> global, LSE ---------------------------------------------------------
@@ -392,7 +422,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
 
 }  // namespace
 
-bool fmha_fwd_ws_supported(const FmhaFwdParams& p) { return p.Lk <= kWsMaxKeys && p.trace == nullptr; }
+bool fmha_fwd_ws_supported(const FmhaFwdParams& p) { return p.Lk <= kWsMaxKeys; }
 
 void launch_fmha_fwd_ws(const FmhaFwdParams& p, cudaStream_t stream) {
   dim3 grid((p.Lq + 2 * kBlockM - 1) / (2 * kBlockM), p.H, p.B);

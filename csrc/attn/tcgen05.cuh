@@ -88,6 +88,23 @@ TC_DEVICE uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32
   return d;
 }
 
+// SWIZZLE_128B operand tile: rows of 128 bytes (64 16-bit elements), 16-byte chunk c of row r stored at chunk
+// c ^ (r & 7); tile base 1024-byte aligned.  Canonical layouts (cute/atom/mma_traits_sm100.hpp, in 16-byte units):
+//   K-major : Swizzle<3,4,3> o ((8,m),2):((8,SBO),1)         8-row groups SBO = 1024 B apart; a K = 16 step is +32 B
+//   MN-major: Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) 64 MN elements per row, 8-deep K groups SBO = 1024 B
+//             apart (a K = 16 step is +2048 B); LBO only matters when the MN extent exceeds 64
+TC_DEVICE uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes = 16) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // MN-major: bytes between 64-element groups along M/N
+  d |= (uint64_t)(1024u >> 4) << 32;      // stride byte offset
+  d |= (uint64_t)1 << 46;                 // descriptor version
+  d |= (uint64_t)2 << 61;                 // layout type SWIZZLE_128B
+  return d;
+}
+// byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a SWIZZLE_128B tile
+TC_DEVICE uint32_t sw128_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
 // 32-bit instruction descriptor for kind::f16: D fp32, A/B fp16 (fmt 0) or bf16 (fmt 1).
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int ab_fmt, int a_mn_major, int b_mn_major) {
   return (1u << 4) | ((uint32_t)ab_fmt << 7) | ((uint32_t)ab_fmt << 10) | ((uint32_t)a_mn_major << 15) |
@@ -167,6 +184,24 @@ TC_DEVICE void tma_load_5d(uint32_t dst_smem, const void* tensor_map, int c0, in
       : "memory");
 }
 
+TC_DEVICE void tma_load_4d(uint32_t dst_smem, const void* tensor_map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst_smem), "l"(tensor_map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+TC_DEVICE void tma_load_3d(uint32_t dst_smem, const void* tensor_map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst_smem), "l"(tensor_map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
+TC_DEVICE void tma_store_3d(const void* tensor_map, int c0, int c1, int c2, uint32_t src_smem) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tensor_map), "r"(c0),
+               "r"(c1), "r"(c2), "r"(src_smem)
+               : "memory");
+}
 // shared -> global tile store through a tensor map (bulk async-group completion); out-of-bounds parts clipped
 TC_DEVICE void tma_store_5d(const void* tensor_map, int c0, int c1, int c2, int c3, int c4, uint32_t src_smem) {
   asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(tensor_map),

@@ -20,4 +20,15 @@ bool make_head_tile_map(CUtensorMap* map, const void* base, bool bf16, int B, in
 // {0, 0, key0 / 8, q0 / 8, nb}.
 bool make_bias_tile_map(CUtensorMap* map, const void* base, bool bf16, int NB, int Lq, int Lk);
 
+// ---- 128-byte-swizzled variants (CU_TENSOR_MAP_SWIZZLE_128B) ------------------------------------------------------
+// The box rows are whole 128-byte lines (64 16-bit elements): one TMA request per row instead of one per 16-byte
+// chunk (measured: the 16-byte-row boxes above cost ~1.7 cycles per chunk, 3500 cycles for a K + V tile pair, which
+// bounded the attention kernels).  Shared-memory layout: row r at r * 128, its 16-byte chunk c at ((c ^ (r & 7)) * 16)
+// - the canonical UMMA SWIZZLE_128B layout (K-major operands, and MN-major operands whose MN extent is 64).
+// [B, L, H, 64] tensor, box = box_rows x 64 of one (batch, head); coordinates {0, head, row0, batch}.
+bool make_head_tile_map_sw128(CUtensorMap* map, const void* base, bool bf16, int B, int L, int H, long long sb,
+                              long long sl, long long sh, int box_rows);
+// bias [NB, Lq, Lk]: box = 128 rows x 64 columns (a 128 x 128 tile is two boxes); coordinates {key0, q0, nb}.
+bool make_bias_tile_map_sw128(CUtensorMap* map, const void* base, bool bf16, int NB, int Lq, int Lk);
+
 }  // namespace ub
