@@ -21,6 +21,9 @@ ap.add_argument("--top", type=int, default=45)
 ap.add_argument("--gaps", type=int, default=12)
 ap.add_argument("--cprofile", type=int, default=0, help="also run this many steps under cProfile (host-side cost)")
 ap.add_argument("--trace", default="", help="write a chrome trace (CPU + CUDA activities) of the profiled steps here")
+ap.add_argument("--host", action="store_true",
+                help="also record host activities and list the CUDA runtime calls the host spent time in (blocking "
+                     "synchronisations show up here) and the launch lead of the host over the device per step")
 a, rest = ap.parse_known_args()
 sys.argv = [sys.argv[0]] + rest
 args = B.parse()
@@ -62,7 +65,7 @@ if a.cprofile > 0:
         st.sort_stats("cumulative").print_stats(45)
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
-acts = [ProfilerActivity.CUDA] + ([ProfilerActivity.CPU] if a.trace else [])
+acts = [ProfilerActivity.CUDA] + ([ProfilerActivity.CPU] if (a.trace or a.host) else [])
 with profile(activities=acts, with_stack=bool(a.trace)) as prof:
     for i in range(a.prof_steps):
         trainer.train_step([dev[i % 4]])
@@ -113,3 +116,31 @@ if rank == 0:
         print("sum of gaps < 20 us: %.2f ms/step" % (small / 1e3 / a.prof_steps))
         for g, before, after in gaps[: a.gaps]:
             print("  gap %8.1f us  after %-60s before %s" % (g, before[:60], after[:60]))
+
+if rank == 0 and a.host:
+    # host side: which runtime calls block, and how far ahead of the device the launches are
+    runtime = {}
+    launches = []   # (host time of the launch call)
+    for e in prof.events():
+        tr = getattr(e, "time_range", None)
+        if tr is None or "cuda" in str(getattr(e, "device_type", "")).lower():
+            continue
+        name = e.name
+        if name.startswith("cuda") or name.startswith("cu"):
+            tot, cnt, mx = runtime.get(name, (0.0, 0, 0.0))
+            dur = tr.end - tr.start
+            runtime[name] = (tot + dur, cnt + 1, max(mx, dur))
+            if "Launch" in name or name in ("cudaMemcpyAsync", "cudaMemsetAsync"):
+                launches.append(tr.start)
+    print("host runtime calls (per step): total us, calls, longest us")
+    for name, (tot, cnt, mx) in sorted(runtime.items(), key=lambda kv: -kv[1][0])[:12]:
+        print("  %-34s %9.1f %7.1f %9.1f" % (name[:34], tot / a.prof_steps, cnt / a.prof_steps, mx))
+    kern = sorted((s, en) for s, en, _n in evs)
+    launches.sort()
+    if launches and kern:
+        # lead = device start of the k-th kernel minus host time of the k-th launch call (same order on one stream)
+        n = min(len(launches), len(kern))
+        lead = [kern[k][0] - launches[k] for k in range(n)]
+        per = max(1, n // (a.prof_steps * 10))
+        print("host lead over the device (us) at every %d-th launch of the profiled steps:" % per)
+        print("  " + " ".join("%.0f" % lead[k] for k in range(0, n, per)))

@@ -21,9 +21,7 @@ struct FmhaFwdParams {
   float scale, p_drop;
   unsigned long long seed, offset;
   long long* trace;        // profiling only: per-phase clock64() stamps of CTA (0,0,0), thread 0; usually null
-  // TMA descriptors (csrc/attn/tma_map.h): 128 x 64 tiles of q / k / v, 128 x 128 tiles of the bias
-  CUtensorMap tm_q, tm_k, tm_v, tm_bias;
-  // 128-byte-swizzled maps of the same tensors (tma_map.h): one request per 128-byte row
+  // TMA descriptors (csrc/attn/tma_map.h), 128-byte swizzle: 128 x 64 tiles of q / k / v, 128 x 64 half tiles of the bias
   CUtensorMap sw_q, sw_k, sw_v, sw_bias;
 };
 // One-role kernel (fmha_fwd_sm100.cu, two CTAs per SM) by default; UNICORE_B200_FMHA_FWD=ws selects the warp-specialised

@@ -79,11 +79,7 @@ void fill_common(ub::FmhaFwdParams& p, const Tensor& q, const Tensor& k, const T
   // TMA descriptors: heads must be contiguous (stride 64) so that (head, 16-byte chunk) is one dimension
   TORCH_CHECK(q.stride(2) == 64 && k.stride(2) == 64 && v.stride(2) == 64, "q/k/v head stride must be 64");
   const bool bf16 = p.is_bf16 != 0;
-  bool ok = ub::make_head_tile_map(&p.tm_q, p.q, bf16, p.B, p.Lq, p.H, p.q_sb, p.q_sl, 128);
-  ok = ok && ub::make_head_tile_map(&p.tm_k, p.k, bf16, p.B, p.Lk, p.H, p.k_sb, p.k_sl, 128);
-  ok = ok && ub::make_head_tile_map(&p.tm_v, p.v, bf16, p.B, p.Lk, p.H, p.v_sb, p.v_sl, 128);
-  if (p.bias != nullptr) ok = ok && ub::make_bias_tile_map(&p.tm_bias, p.bias, bf16, p.bias_batch * p.H, p.Lq, p.Lk);
-  ok = ok && ub::make_head_tile_map_sw128(&p.sw_q, p.q, bf16, p.B, p.Lq, p.H, p.q_sb, p.q_sl, p.q_sh, 128);
+  bool ok = ub::make_head_tile_map_sw128(&p.sw_q, p.q, bf16, p.B, p.Lq, p.H, p.q_sb, p.q_sl, p.q_sh, 128);
   ok = ok && ub::make_head_tile_map_sw128(&p.sw_k, p.k, bf16, p.B, p.Lk, p.H, p.k_sb, p.k_sl, p.k_sh, 128);
   ok = ok && ub::make_head_tile_map_sw128(&p.sw_v, p.v, bf16, p.B, p.Lk, p.H, p.v_sb, p.v_sl, p.v_sh, 128);
   if (p.bias != nullptr) ok = ok && ub::make_bias_tile_map_sw128(&p.sw_bias, p.bias, bf16, p.bias_batch * p.H, p.Lq, p.Lk);

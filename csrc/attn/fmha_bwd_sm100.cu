@@ -4,23 +4,26 @@
 // forward pass (1 bit / element).
 //
 //   grid = (key tiles, H, B); one CTA owns K_j, V_j (128 keys) and walks the query tiles i.  16 math warps
-//   (thread = (query row, 32-column quarter): no cross-thread reductions) + 1 warp that only issues TMA copies
-//   and tcgen05.mma, so the copy / MMA queues never sit behind softmax-grad arithmetic:
+//   (thread = (query row, 32-column quarter): no cross-thread reductions) + 1 warp whose elected lane issues every TMA
+//   copy and every tcgen05.mma.  The roles meet only through mbarriers (no CTA-wide barrier inside the loop):
 //     S   = Q_i K_j^T                      tcgen05.mma  -> TMEM [  0,128)
 //     dP  = dO_i V_j^T                     tcgen05.mma  -> TMEM [128,256)
 //     P   = exp2((S*scale + bias + kmask - LSE_i) * log2e) ;  dS = P o (drop(dP) - delta_i)   (packed fp32x2)
-//     dQ_i  = dS K_j                       tcgen05.mma  -> TMEM [384,448) -> 16-bit partial of this key tile
+//     dQ_i  = dS K_j                       tcgen05.mma  -> TMEM [384,448) / [448,512) alternating -> 16-bit partial
 //     dV_j += drop(P)^T dO_i               tcgen05.mma  -> TMEM [256,320)   (A and B MN-major views)
 //     dK_j += dS^T Q_i                     tcgen05.mma  -> TMEM [320,384)
-//     dS tile (16-bit, already in shared memory for the MMAs) -> ONE TMA store; a follow-up kernel sums it over
-//     the batch into dBias.  (The first versions used red.global.add.v4.f32 for dQ and dBias: 6144 per tile,
-//     which made the kernel atomics-bound.)
-//   Tensor-pipe order per tile: dQ_i (the math warps wait for it; its read-out and the next tile's loads then
-//   run under the rest), dV, dK, S / dP of tile i+1.  Q_{i+1}, dO_{i+1} and the bias tile of (i+1, j) arrive by
-//   TMA (128-byte-swizzled boxes, csrc/attn/tma_map.h) in the alternate buffers one tile ahead; the bias tile lands in
-//   the buffer that later receives dS (same swizzled layout => in-place overwrite, chunk by chunk).
-//   Every operand tile is written once and presented to the tensor core as K-major or MN-major by
-//   swapping descriptor strides (no transposes).
+//     dS tile (16-bit, already in shared memory for the MMAs) -> TMA store; a follow-up kernel sums it over the batch
+//     into dBias.  (The first versions used red.global.add.v4.f32 for dQ and dBias: 6144 per tile, atomics-bound.)
+//   Pipeline of one query tile (issuing warp | math warps):
+//     S_{i+1}, dP_{i+1} are issued as soon as the math warps hold S_i, dP_i in registers (kBarSFree), so they - and
+//     dQ_i / dV_i / dK_i, issued when P_i / dS_i are in shared memory (kBarPds) - run under the math of tiles i, i+1;
+//     dQ_{i-1} is read out of its own tensor-memory buffer after the math warps have handed over tile i, off the
+//     critical path.  Q / dO are fetched two tiles ahead (3 stages), the bias tile one ahead into the buffer that later
+//     receives dS (same swizzled layout => in-place overwrite, chunk by chunk).
+//   All TMA boxes are 128-byte-swizzled (csrc/attn/tma_map.h; the 16-byte-row boxes of the first version cost ~4000
+//   cycles per tile); every operand tile is written once and presented to the tensor core as K-major or MN-major by
+//   the descriptor (no transposes).  Measured (profiles/): the tile is now bound by the shared-memory port - ~400 KB
+//   of operand reads + tile writes per query tile - rather than by copies or by waiting.
 // Pre-pass:  delta = rowsum(dO o O).   Post-pass: dq = sum of the per-key-tile partials (and dbias = batch sum of dS).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -40,20 +43,24 @@ using namespace tc;
 constexpr int kBM = 128, kBN = 128, kD = 64;
 constexpr int kBwdMathThreads = 512;            // 16 warps: thread = (query row, 32-column quarter)
 constexpr int kBwdThreads = kBwdMathThreads + 32;  // + one warp that only issues TMA copies and tcgen05.mma
-constexpr int kIssuer = kBwdMathThreads;         // its elected thread
 constexpr uint32_t kBwdTmemCols = 512;
-constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;   // dQ: two 64-column buffers
 
 // shared memory map (bytes)
-constexpr uint32_t kOffQ = 0;          // 2 x 16 KB
-constexpr uint32_t kOffDO = 32768;     // 2 x 16 KB
-constexpr uint32_t kOffK = 65536;
-constexpr uint32_t kOffV = 81920;
-constexpr uint32_t kOffP = 98304;      // 32 KB
-constexpr uint32_t kOffDS = 131072;    // 2 x 32 KB: bias tile, then dS (in place)
-constexpr uint32_t kOffKAdd = 196608;  // float[128]
-constexpr uint32_t kOffBar = 196608 + 512;
-constexpr uint32_t kBwdSmemBytes = kOffBar + 96;
+constexpr int kQStages = 3;            // Q / dO are fetched two query tiles ahead
+constexpr uint32_t kOffQ = 0;          // 3 x 16 KB (128-byte-swizzled rows)
+constexpr uint32_t kOffDO = 49152;     // 3 x 16 KB
+constexpr uint32_t kOffK = 98304;
+constexpr uint32_t kOffV = 114688;
+constexpr uint32_t kOffP = 131072;     // 32 KB, core-matrix layout (written by the math warps)
+constexpr uint32_t kOffDS = 163840;    // 2 x 32 KB: bias tile, then dS (in place); two 64-column swizzled boxes each
+constexpr uint32_t kOffKAdd = 229376;  // float[128]
+constexpr uint32_t kOffBar = kOffKAdd + 512;
+// mbarriers
+enum : int { kBarKV = 0, kBarIn0, kBarBias0 = kBarIn0 + kQStages, kBarSdp = kBarBias0 + 2, kBarSFree, kBarPds, kBarDq, kBarDvk,
+             kNumBwdBars };
+constexpr uint32_t kBwdSmemBytes = kOffBar + 8 * kNumBwdBars + 16;
+static_assert(kBwdSmemBytes <= 232448, "shared memory budget");
 
 template <typename T>
 UB_DEVICE uint32_t bwd_pack2(float a, float b);
@@ -147,29 +154,27 @@ __global__ void __launch_bounds__(256) fmha_dq_sum_kernel(const T* __restrict__ 
 // ---- main kernel ----------------------------------------------------------------------------------------------
 #define UB_BTRACE(slot)                                                                     \
   do {                                                                                      \
-    if (trace != nullptr) trace[i * 12 + (slot)] = clock64();                               \
+    if (trace != nullptr && i < 64) trace[i * 12 + (slot)] = clock64();                     \
   } while (0)
+
+// whole warp: every lane has finished what the barrier protects -> one arrival
+UB_DEVICE void bwd_warp_arrive(uint32_t bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_constant__ FmhaBwdParams bp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const FmhaFwdParams& p = bp.f;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int r = tid & 127, quarter = tid >> 7;  // thread = (tile row, 32-column quarter)
-  const int col0 = quarter * 32;                // my columns inside the key tile
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = tid & 127, quarter = (tid >> 7) & 3;  // math thread = (tile row, 32-column quarter)
+  const int col0 = quarter * 32;                       // my columns inside the key tile
   const int key_tile0 = blockIdx.x * kBN, h = blockIdx.y, b = blockIdx.z;
   long long* trace = (bp.trace != nullptr && tid == 0 && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 1) ? bp.trace : nullptr;
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_a = smem_base + kOffBar, bar_b = smem_base + kOffBar + 8;
-  // TMA completion barriers: the K/V tiles of this CTA, and the two (Q, dO, bias) input buffers
-  const uint32_t bar_kv = smem_base + kOffBar + 24, bar_in0 = smem_base + kOffBar + 32;  // bar_in1 = bar_in0 + 8
-  // bar_q: dQ of the current tile is complete (read-out may start); bar_v: dV / dK of the current tile are
-  // complete (their operand buffers may be refilled).  bar_b is no longer used.
-  const uint32_t bar_q = smem_base + kOffBar + 48, bar_v = smem_base + kOffBar + 56;
-  // the bias tile has its own completion barrier (per buffer): the math warps need it first, Q / dO only matter
-  // to the issuing warp, much later
-  const uint32_t bar_bias0 = smem_base + kOffBar + 64;  // bar_bias1 = bar_bias0 + 8
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 16);
+  auto bar = [&](int k) { return smem_base + kOffBar + 8u * (uint32_t)k; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * kNumBwdBars);
   float* kadd = reinterpret_cast<float*>(smem + kOffKAdd);
 
   if (warp == 0) {
@@ -177,40 +182,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
     tmem_relinquish();
   }
   if (tid == 0) {
-    mbar_init(bar_a, 1);
-    mbar_init(bar_b, 1);
-    mbar_init(bar_kv, 1);
-    mbar_init(bar_in0, 1);
-    mbar_init(bar_in0 + 8, 1);
-    mbar_init(bar_q, 1);
-    mbar_init(bar_v, 1);
-    mbar_init(bar_bias0, 1);
-    mbar_init(bar_bias0 + 8, 1);
+    mbar_init(bar(kBarKV), 1);
+    for (int s = 0; s < kQStages; ++s) mbar_init(bar(kBarIn0 + s), 1);
+    mbar_init(bar(kBarBias0), 1);
+    mbar_init(bar(kBarBias0 + 1), 1);
+    mbar_init(bar(kBarSdp), 1);
+    mbar_init(bar(kBarSFree), kBwdMathThreads / 32);
+    mbar_init(bar(kBarPds), kBwdMathThreads / 32);
+    mbar_init(bar(kBarDq), 1);
+    mbar_init(bar(kBarDvk), 1);
     fence_mbarrier_init();
   }
   const int bb = p.bias_batch > 1 ? b : 0;
   const bool has_bias = p.bias != nullptr;
   const int n_qtiles = (p.Lq + kBM - 1) / kBM;
-
   constexpr uint32_t kTileBytes = kBM * kD * 2, kBiasBytes = kBM * kBN * 2;
   const int bias_nb = bb * p.H + h;
-  auto issue_tile = [&](int i) {  // ONE thread: three TMA boxes bring everything tile i needs
-    const int q0 = i * kBM;
-    const uint32_t buf = (uint32_t)(i & 1);
-    const uint32_t bar = bar_in0 + buf * 8;
-    if (has_bias) {  // first: the math warps wait for it.  128 x 128 tile = two 64-column boxes
-      mbar_expect_tx(bar_bias0 + buf * 8, kBiasBytes);
-      tma_load_3d(smem_base + kOffDS + buf * 32768, &p.sw_bias, key_tile0, q0, bias_nb, bar_bias0 + buf * 8);
-      tma_load_3d(smem_base + kOffDS + buf * 32768 + 16384, &p.sw_bias, key_tile0 + 64, q0, bias_nb, bar_bias0 + buf * 8);
-    }
-    mbar_expect_tx(bar, 2 * kTileBytes);
-    tma_load_4d(smem_base + kOffQ + buf * 16384, &p.sw_q, 0, h, q0, b, bar);
-    tma_load_4d(smem_base + kOffDO + buf * 16384, &bp.sw_do, 0, h, q0, b, bar);
-  };
-  constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
-  constexpr uint32_t idesc_s = make_idesc_f16(kBM, kBN, kFmt, 0, 0);    // S, dP: both operands K-major
-  constexpr uint32_t idesc_t = make_idesc_f16(kBN, kD, kFmt, 1, 1);     // dV, dK: both operands MN-major
-  constexpr uint32_t idesc_q = make_idesc_f16(kBM, kD, kFmt, 0, 1);     // dQ: A K-major, B MN-major
 
   bool key_masked = false;
   if (tid < kBN) {
@@ -221,192 +208,125 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
   fence_before_thread_sync();
   const bool tile_masked = __syncthreads_or(key_masked) != 0;  // usually no key of the tile is masked
   fence_after_thread_sync();
-  if (tid == kIssuer) {  // barriers are initialised: K, V of this CTA and the first (Q, dO, bias) tile
-    mbar_expect_tx(bar_kv, 2 * kTileBytes);
-    tma_load_4d(smem_base + kOffK, &p.sw_k, 0, h, key_tile0, b, bar_kv);
-    tma_load_4d(smem_base + kOffV, &p.sw_v, 0, h, key_tile0, b, bar_kv);
-    issue_tile(0);
-  }
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 
-  // S_i = Q_i K^T and dP_i = dO_i V^T (issued one tile ahead of the softmax that consumes them)
-  auto issue_s_dp = [&](int i) {
-    const uint32_t buf = (uint32_t)(i & 1);
-    const uint32_t sQ = smem_base + kOffQ + buf * 16384, sDO = smem_base + kOffDO + buf * 16384;
+  if (warp == kBwdMathThreads / 32) {
+    // ============================ issuing warp: every TMA copy and every tcgen05.mma ============================
+    if (lane == 0) {
+      constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+      constexpr uint32_t idesc_s = make_idesc_f16(kBM, kBN, kFmt, 0, 0);    // S, dP: both operands K-major
+      constexpr uint32_t idesc_t = make_idesc_f16(kBN, kD, kFmt, 1, 1);     // dV, dK: both operands MN-major
+      constexpr uint32_t idesc_q = make_idesc_f16(kBM, kD, kFmt, 0, 1);     // dQ: A K-major, B MN-major
+      auto load_q_do = [&](int i) {   // Q_i, dO_i -> stage i % 3
+        const uint32_t st = (uint32_t)(i % kQStages);
+        mbar_expect_tx(bar(kBarIn0 + st), 2 * kTileBytes);
+        tma_load_4d(smem_base + kOffQ + st * 16384, &p.sw_q, 0, h, i * kBM, b, bar(kBarIn0 + st));
+        tma_load_4d(smem_base + kOffDO + st * 16384, &bp.sw_do, 0, h, i * kBM, b, bar(kBarIn0 + st));
+      };
+      auto load_bias = [&](int i) {   // bias tile (i, j) -> the buffer that later receives dS_i; two 64-column boxes
+        const uint32_t buf = (uint32_t)(i & 1);
+        mbar_expect_tx(bar(kBarBias0 + buf), kBiasBytes);
+        tma_load_3d(smem_base + kOffDS + buf * 32768, &p.sw_bias, key_tile0, i * kBM, bias_nb, bar(kBarBias0 + buf));
+        tma_load_3d(smem_base + kOffDS + buf * 32768 + 16384, &p.sw_bias, key_tile0 + 64, i * kBM, bias_nb,
+                    bar(kBarBias0 + buf));
+      };
+      // S_i = Q_i K^T and dP_i = dO_i V^T
+      auto issue_s_dp = [&](int i) {
+        const uint32_t st = (uint32_t)(i % kQStages);
+        const uint32_t sQ = smem_base + kOffQ + st * 16384, sDO = smem_base + kOffDO + st * 16384;
 #pragma unroll
-    for (int kk = 0; kk < kD / 16; ++kk) {
-      const uint64_t dq_ = make_smem_desc_sw128(sQ + kk * 32);
-      const uint64_t dk_ = make_smem_desc_sw128(smem_base + kOffK + kk * 32);
-      umma_f16_ss(tmem_base + kColS, dq_, dk_, idesc_s, kk > 0 ? 1u : 0u);
-    }
+        for (int kk = 0; kk < kD / 16; ++kk)
+          umma_f16_ss(tmem_base + kColS, make_smem_desc_sw128(sQ + kk * 32), make_smem_desc_sw128(smem_base + kOffK + kk * 32),
+                      idesc_s, kk > 0 ? 1u : 0u);
 #pragma unroll
-    for (int kk = 0; kk < kD / 16; ++kk) {
-      const uint64_t ddo = make_smem_desc_sw128(sDO + kk * 32);
-      const uint64_t dv_ = make_smem_desc_sw128(smem_base + kOffV + kk * 32);
-      umma_f16_ss(tmem_base + kColDP, ddo, dv_, idesc_s, kk > 0 ? 1u : 0u);
-    }
-    umma_commit(bar_a);
-  };
-  if (tid == kIssuer) {
-    mbar_wait(bar_kv, 0);
-    mbar_wait(bar_in0, 0);
-    issue_s_dp(0);
-  }
-  const bool math_thread = tid < kBwdMathThreads;
-
-  const bool drop = p.p_drop > 0.f && p.drop_bits != nullptr;
-  // same 14-bit threshold arithmetic as the forward kernel (common.cuh)
-  const float keep_scale = p.p_drop > 0.f ? dropout_keep_scale14(dropout_thresh14(p.p_drop)) : 1.f;
-  constexpr float kLog2e = 1.4426950408889634f;
-  const F2 scale_2 = f2(p.scale), log2e_2 = f2(kLog2e);
-  const int words_per_row = (p.Lk + 31) / 32;
-  uint32_t phase_a = 0;
-  auto load_row_stats = [&](int i, float& lse, float& delta, uint32_t& keep) {
-    const int row = i * kBM + r;
-    const bool ok = row < p.Lq && math_thread;
-    const long long stat_idx = ((long long)b * p.H + h) * p.Lq + (ok ? row : 0);
-    lse = ok ? p.lse[stat_idx] : CUDART_INF_F;
-    delta = ok ? bp.delta[stat_idx] : 0.f;
-    keep = 0xffffffffu;
-    if (drop && ok && key_tile0 + col0 < p.Lk) keep = p.drop_bits[stat_idx * words_per_row + ((key_tile0 + col0) >> 5)];
-  };
-  float nx_lse, nx_delta;
-  uint32_t nx_keep;
-  load_row_stats(0, nx_lse, nx_delta, nx_keep);
-
-  for (int i = 0; i < n_qtiles; ++i) {
-    const int q0 = i * kBM;
-    const uint32_t buf = (uint32_t)(i & 1);
-    const uint32_t sQ = smem_base + kOffQ + buf * 16384, sDO = smem_base + kOffDO + buf * 16384;
-    const uint32_t offDS = kOffDS + buf * 32768;
-    const int row = q0 + r;
-    const bool row_valid = row < p.Lq;
-    if (math_thread) {
-    UB_BTRACE(0);
-    if (has_bias) mbar_wait(bar_bias0 + buf * 8, (uint32_t)((i >> 1) & 1));  // bias tile i is visible to ordinary loads
-    UB_BTRACE(1);
-
-    // per-row statistics and keep bits of this tile were requested during the previous tile's math
-    const float lse = nx_lse, delta = nx_delta;
-    const uint32_t keep_word = nx_keep;
-    if (i + 1 < n_qtiles) load_row_stats(i + 1, nx_lse, nx_delta, nx_keep);
-    // fully masked row (lse = -inf) or padding row -> p = 0
-    const float lse2 = (lse == -CUDART_INF_F || !row_valid) ? CUDART_INF_F : lse * kLog2e;
-    const F2 nlse_2 = f2(-lse2), ndelta_2 = f2(-delta);
-    UB_BTRACE(2);
-    mbar_wait(bar_a, phase_a);
-    phase_a ^= 1;
-    fence_after_thread_sync();
-    UB_BTRACE(3);
-    {
-      uint32_t acc[32], dpr[32];
-      tmem_ld32(lane_base + kColS + col0, acc);
-      tmem_ld32(lane_base + kColDP + col0, dpr);
-      tmem_wait_ld();
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        const uint32_t off = tile128_off(r, (col0 >> 3) + v);                              // P: core-matrix layout
-        const uint32_t off_ds = (uint32_t)(quarter >> 1) * 16384u + sw128_off(r, (quarter & 1) * 4 + v);  // bias / dS
-        float bf[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bf[e] = 0.f;
-        if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(smem + offDS + off_ds), bf);
-        if (tile_masked) {
-          const float4 ka = *reinterpret_cast<const float4*>(kadd + col0 + v * 8);
-          const float4 kb = *reinterpret_cast<const float4*>(kadd + col0 + v * 8 + 4);
-          bf[0] += ka.x; bf[1] += ka.y; bf[2] += ka.z; bf[3] += ka.w;
-          bf[4] += kb.x; bf[5] += kb.y; bf[6] += kb.z; bf[7] += kb.w;
+        for (int kk = 0; kk < kD / 16; ++kk)
+          umma_f16_ss(tmem_base + kColDP, make_smem_desc_sw128(sDO + kk * 32), make_smem_desc_sw128(smem_base + kOffV + kk * 32),
+                      idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(bar(kBarSdp));
+      };
+      mbar_expect_tx(bar(kBarKV), 2 * kTileBytes);
+      tma_load_4d(smem_base + kOffK, &p.sw_k, 0, h, key_tile0, b, bar(kBarKV));
+      tma_load_4d(smem_base + kOffV, &p.sw_v, 0, h, key_tile0, b, bar(kBarKV));
+      load_q_do(0);
+      if (has_bias) load_bias(0);
+      if (n_qtiles > 1) load_q_do(1);
+      mbar_wait(bar(kBarKV), 0);
+      mbar_wait(bar(kBarIn0), 0);
+      issue_s_dp(0);
+      for (int i = 0; i < n_qtiles; ++i) {
+        const uint32_t par = (uint32_t)(i & 1);
+        // (a) the math warps hold S_i / dP_i in registers: the next pair may overwrite tensor memory
+        if (i + 1 < n_qtiles) {
+          mbar_wait(bar(kBarIn0 + (i + 1) % kQStages), (uint32_t)(((i + 1) / kQStages) & 1));
+          mbar_wait(bar(kBarSFree), par);
+          fence_after_thread_sync();
+          issue_s_dp(i + 1);
         }
-        float pd[8], ds[8];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          // keep bits of the pair (keys 2i, 2i+1 of my 32): bit i and bit 16 + i (see fmha_fwd)
-          const int pi = v * 4 + e;
-          const bool k0 = (keep_word >> pi) & 1u, k1 = (keep_word >> (16 + pi)) & 1u;
-          const F2 a2 = F2{__uint_as_float(acc[v * 8 + 2 * e]), __uint_as_float(acc[v * 8 + 2 * e + 1])};
-          const F2 x2 = fma2(a2, scale_2, F2{bf[2 * e], bf[2 * e + 1]});
-          const F2 arg = fma2(x2, log2e_2, nlse_2);
-          F2 pr;
-          pr.x = ex2_approx(arg.x);
-          pr.y = ex2_approx(arg.y);
-          const F2 km = F2{k0 ? keep_scale : 0.f, k1 ? keep_scale : 0.f};
-          const F2 dp2 = F2{__uint_as_float(dpr[v * 8 + 2 * e]), __uint_as_float(dpr[v * 8 + 2 * e + 1])};
-          const F2 d2 = mul2(pr, fma2(dp2, km, ndelta_2));
-          pd[2 * e] = k0 ? pr.x : 0.f;       // keep_scale is applied to dV in the epilogue
-          pd[2 * e + 1] = k1 ? pr.y : 0.f;
-          ds[2 * e] = d2.x;                   // the softmax scale is applied to dQ / dK at read-out
-          ds[2 * e + 1] = d2.y;
+        // (b) dV / dK of tile i-1 are complete: its Q / dO stage and its dS buffer may be refilled
+        if (i >= 1) mbar_wait(bar(kBarDvk), par ^ 1);
+        tma_store_wait_read();
+        if (i + 1 < n_qtiles && has_bias) load_bias(i + 1);
+        if (i + 2 < n_qtiles) load_q_do(i + 2);
+        // (c) P_i and dS_i are in shared memory
+        mbar_wait(bar(kBarPds), par);
+        fence_after_thread_sync();
+        const uint32_t st = (uint32_t)(i % kQStages);
+        const uint32_t sQ = smem_base + kOffQ + st * 16384, sDO = smem_base + kOffDO + st * 16384;
+        const uint32_t sDS = smem_base + kOffDS + par * 32768;
+        if (bp.ds_buf != nullptr) {  // bias gradient: the dS tile leaves through two TMA stores (64 columns each)
+          tma_store_3d(&bp.sw_ds, key_tile0, i * kBM, b * p.H + h, sDS);
+          tma_store_3d(&bp.sw_ds, key_tile0 + 64, i * kBM, b * p.H + h, sDS + 16384);
+          tma_store_commit();
         }
-        Vec16 op, od;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          op.w[e] = bwd_pack2<T>(pd[2 * e], pd[2 * e + 1]);
-          od.w[e] = bwd_pack2<T>(ds[2 * e], ds[2 * e + 1]);
+        for (int kk = 0; kk < kBN / 16; ++kk) {  // dQ_i = dS K: reduction over the 128 keys
+          const uint64_t a_ds = make_smem_desc_sw128(sDS + (kk >> 2) * 16384 + (kk & 3) * 32);   // dS (K-major, 2 x 64 keys)
+          const uint64_t b_k = make_smem_desc_sw128(smem_base + kOffK + kk * 2048);              // K  (MN-major)
+          umma_f16_ss(tmem_base + kColDQ + par * 64, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);   // two dQ buffers
         }
-        *reinterpret_cast<Vec16*>(smem + kOffP + off) = op;
-        *reinterpret_cast<Vec16*>(smem + offDS + off_ds) = od;   // in place over the consumed bias chunk
+        umma_commit(bar(kBarDq));
+#pragma unroll
+        for (int kk = 0; kk < kBM / 16; ++kk) {  // dV += P^T dO: reduction over the 128 query rows
+          const uint64_t a_p = make_smem_desc(smem_base + kOffP + kk * 4096, 2048, 128);    // P^T  (MN-major, core matrices)
+          const uint64_t b_do = make_smem_desc_sw128(sDO + kk * 2048);                      // dO   (MN-major)
+          umma_f16_ss(tmem_base + kColDV, a_p, b_do, idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < kBM / 16; ++kk) {  // dK += dS^T Q
+          const uint64_t a_ds = make_smem_desc_sw128(sDS + kk * 2048, 16384);               // dS^T (MN-major, M = 2 x 64 keys)
+          const uint64_t b_q = make_smem_desc_sw128(sQ + kk * 2048);                        // Q    (MN-major)
+          umma_f16_ss(tmem_base + kColDK, a_ds, b_q, idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(bar(kBarDvk));
       }
+      tma_store_wait_read();  // shared memory must outlive the last dS store's reads
     }
-    UB_BTRACE(4);
-    UB_BTRACE(5);
-    fence_proxy_async_smem();   // my P / dS stores (generic proxy) before the tensor core (async proxy) reads them
-    fence_before_thread_sync();
-    } else if (tid == kIssuer && i + 1 < n_qtiles) {
-      // The issuing warp runs ahead of the math warps.  Tile i+1 lands in the buffers tile i-1 used: its dV / dK
-      // MMAs (bar_v) and its dS store must be done with them; the copy (64 KB in 16-byte rows, ~4000 cycles)
-      // then has the whole softmax-grad phase of tile i to land.
-      if (i >= 1) mbar_wait(bar_v, (uint32_t)((i - 1) & 1));
-      tma_store_wait_read();
-      issue_tile(i + 1);
-    }
-    __syncthreads();   // P and dS of tile i are in shared memory
-    UB_BTRACE(6);
-    if (tid == kIssuer) {
+  } else {
+    // ============================ math warps ==================================================================
+    const bool drop = p.p_drop > 0.f && p.drop_bits != nullptr;
+    // same 14-bit threshold arithmetic as the forward kernel (common.cuh)
+    const float keep_scale_m = p.p_drop > 0.f ? dropout_keep_scale14(dropout_thresh14(p.p_drop)) : 1.f;
+    constexpr float kLog2e = 1.4426950408889634f;
+    const F2 scale_2 = f2(p.scale), log2e_2 = f2(kLog2e);
+    const int words_per_row = (p.Lk + 31) / 32;
+    auto load_row_stats = [&](int i, float& lse, float& delta, uint32_t& keep) {
+      const int row = i * kBM + r;
+      const bool ok = row < p.Lq;
+      const long long stat_idx = ((long long)b * p.H + h) * p.Lq + (ok ? row : 0);
+      lse = ok ? p.lse[stat_idx] : CUDART_INF_F;
+      delta = ok ? bp.delta[stat_idx] : 0.f;
+      keep = 0xffffffffu;
+      if (drop && ok && key_tile0 + col0 < p.Lk) keep = p.drop_bits[stat_idx * words_per_row + ((key_tile0 + col0) >> 5)];
+    };
+    // dQ_i partial of this key tile -> 16-bit partial buffer (16 of the 64 columns per thread)
+    auto read_out_dq = [&](int i) {
+      mbar_wait(bar(kBarDq), (uint32_t)(i & 1));
       fence_after_thread_sync();
-      const uint32_t sDS = smem_base + offDS;
-      if (bp.ds_buf != nullptr) {  // bias gradient: the dS tile leaves through one TMA store
-        tma_store_3d(&bp.sw_ds, key_tile0, q0, b * p.H + h, sDS);
-        tma_store_3d(&bp.sw_ds, key_tile0 + 64, q0, b * p.H + h, sDS + 16384);
-        tma_store_commit();
-      }
-      // Issue order = execution order on the tensor pipe: dQ first (the threads are waiting for it: its read-out and
-      // the next tile's statistics loads then run under dV / dK), then dV, dK, and S / dP of the next tile.
-#pragma unroll
-      for (int kk = 0; kk < kBN / 16; ++kk) {  // dQ: reduction over the 128 keys
-        const uint64_t a_ds = make_smem_desc_sw128(sDS + (kk >> 2) * 16384 + (kk & 3) * 32);   // dS (K-major, 2 x 64 keys)
-        const uint64_t b_k = make_smem_desc_sw128(smem_base + kOffK + kk * 2048);              // K  (MN-major)
-        umma_f16_ss(tmem_base + kColDQ, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
-      }
-      umma_commit(bar_q);
-#pragma unroll
-      for (int kk = 0; kk < kBM / 16; ++kk) {  // dV: reduction over the 128 query rows, 16 per step
-        const uint64_t a_p = make_smem_desc(smem_base + kOffP + kk * 4096, 2048, 128);    // P^T  (MN-major)
-        const uint64_t b_do = make_smem_desc_sw128(sDO + kk * 2048);                      // dO   (MN-major)
-        umma_f16_ss(tmem_base + kColDV, a_p, b_do, idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
-      }
-#pragma unroll
-      for (int kk = 0; kk < kBM / 16; ++kk) {  // dK
-        const uint64_t a_ds = make_smem_desc_sw128(sDS + kk * 2048, 16384);               // dS^T (MN-major, M = 2 x 64 keys)
-        const uint64_t b_q = make_smem_desc_sw128(sQ + kk * 2048);                        // Q    (MN-major)
-        umma_f16_ss(tmem_base + kColDK, a_ds, b_q, idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
-      }
-      umma_commit(bar_v);
-      if (i + 1 < n_qtiles) {
-        mbar_wait(bar_in0 + (uint32_t)((i + 1) & 1) * 8, (uint32_t)(((i + 1) >> 1) & 1));  // Q, dO of tile i+1 landed
-        issue_s_dp(i + 1);   // commits bar_a: S / dP ready implies everything above is complete (P buffer is free)
-      }
-    }
-    UB_BTRACE(7);
-    if (math_thread) {
-    mbar_wait(bar_q, (uint32_t)(i & 1));
-    fence_after_thread_sync();
-    UB_BTRACE(8);
-    {  // dQ_i partial of this key tile -> 16-bit partial buffer (16 of the 64 columns per thread)
       uint32_t acc[16];
-      tmem_ld16(lane_base + kColDQ + quarter * 16, acc);
+      tmem_ld16(lane_base + kColDQ + (uint32_t)(i & 1) * 64 + quarter * 16, acc);
       tmem_wait_ld();
-      if (row_valid && !(bp.debug_flags & 2)) {
+      if (i * kBM + r < p.Lq && !(bp.debug_flags & 2)) {
         // partial layout [key tile][b][h][q tile][quarter][128 rows][16]: a warp (32 rows, one quarter) writes 1 KB
         // of consecutive bytes
         T* dst = reinterpret_cast<T*>(bp.dq_part) +
@@ -420,15 +340,103 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
         }
         st_global_v8(dst, o[0], o[1]);
       }
-    }
-    UB_BTRACE(9);
-    }
-  }
+    };
+    float nx_lse, nx_delta;
+    uint32_t nx_keep;
+    load_row_stats(0, nx_lse, nx_delta, nx_keep);
 
-  // ---- epilogue: dK_j, dV_j (16 of the 64 columns per thread) ---------------------------------------------------
-  mbar_wait(bar_v, (uint32_t)((n_qtiles - 1) & 1));   // the last dV / dK accumulation has completed
-  fence_after_thread_sync();
-  if (math_thread) {
+    for (int i = 0; i < n_qtiles; ++i) {
+      const uint32_t par = (uint32_t)(i & 1);
+      const uint32_t offDS = kOffDS + par * 32768;
+      const bool row_valid = i * kBM + r < p.Lq;
+      UB_BTRACE(0);
+      if (has_bias) mbar_wait(bar(kBarBias0 + par), (uint32_t)((i >> 1) & 1));  // bias tile i is visible to ordinary loads
+      UB_BTRACE(1);
+      // per-row statistics and keep bits of this tile were requested during the previous tile's math
+      const float lse = nx_lse, delta = nx_delta;
+      const uint32_t keep_word = nx_keep;
+      if (i + 1 < n_qtiles) load_row_stats(i + 1, nx_lse, nx_delta, nx_keep);
+      // fully masked row (lse = -inf) or padding row -> p = 0
+      const float lse2 = (lse == -CUDART_INF_F || !row_valid) ? CUDART_INF_F : lse * kLog2e;
+      const F2 nlse_2 = f2(-lse2), ndelta_2 = f2(-delta);
+      mbar_wait(bar(kBarSdp), par);
+      fence_after_thread_sync();
+      UB_BTRACE(2);
+      Vec16 op[4], od[4];
+      {
+        uint32_t acc[32], dpr[32];
+        tmem_ld32(lane_base + kColS + col0, acc);
+        tmem_ld32(lane_base + kColDP + col0, dpr);
+        tmem_wait_ld();
+        fence_before_thread_sync();
+        bwd_warp_arrive(bar(kBarSFree), lane);   // S_{i+1} / dP_{i+1} may be issued: they run under this tile's math
+        UB_BTRACE(3);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint32_t off_ds = (uint32_t)(quarter >> 1) * 16384u + sw128_off(r, (quarter & 1) * 4 + v);  // bias / dS
+          float bf[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) bf[e] = 0.f;
+          if (has_bias) unpack<T>(*reinterpret_cast<const Vec16*>(smem + offDS + off_ds), bf);
+          if (tile_masked) {
+            const float4 ka = *reinterpret_cast<const float4*>(kadd + col0 + v * 8);
+            const float4 kb = *reinterpret_cast<const float4*>(kadd + col0 + v * 8 + 4);
+            bf[0] += ka.x; bf[1] += ka.y; bf[2] += ka.z; bf[3] += ka.w;
+            bf[4] += kb.x; bf[5] += kb.y; bf[6] += kb.z; bf[7] += kb.w;
+          }
+          float pd[8], ds[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            // keep bits of the pair (keys 2i, 2i+1 of my 32): bit i and bit 16 + i (see fmha_fwd)
+            const int pi = v * 4 + e;
+            const bool k0 = (keep_word >> pi) & 1u, k1 = (keep_word >> (16 + pi)) & 1u;
+            const F2 a2 = F2{__uint_as_float(acc[v * 8 + 2 * e]), __uint_as_float(acc[v * 8 + 2 * e + 1])};
+            const F2 x2 = fma2(a2, scale_2, F2{bf[2 * e], bf[2 * e + 1]});
+            const F2 arg = fma2(x2, log2e_2, nlse_2);
+            F2 pr;
+            pr.x = ex2_approx(arg.x);
+            pr.y = ex2_approx(arg.y);
+            const F2 km = F2{k0 ? keep_scale_m : 0.f, k1 ? keep_scale_m : 0.f};
+            const F2 dp2 = F2{__uint_as_float(dpr[v * 8 + 2 * e]), __uint_as_float(dpr[v * 8 + 2 * e + 1])};
+            const F2 d2 = mul2(pr, fma2(dp2, km, ndelta_2));
+            pd[2 * e] = k0 ? pr.x : 0.f;       // keep_scale is applied to dV in the epilogue
+            pd[2 * e + 1] = k1 ? pr.y : 0.f;
+            ds[2 * e] = d2.x;                   // the softmax scale is applied to dQ / dK at read-out
+            ds[2 * e + 1] = d2.y;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            op[v].w[e] = bwd_pack2<T>(pd[2 * e], pd[2 * e + 1]);
+            od[v].w[e] = bwd_pack2<T>(ds[2 * e], ds[2 * e + 1]);
+          }
+        }
+      }
+      UB_BTRACE(4);
+      if (i > 0) {   // dV / dK of tile i-1 have consumed P (and the dS buffer of tile i-2 was released even earlier)
+        mbar_wait(bar(kBarDvk), par ^ 1);
+        fence_after_thread_sync();
+      }
+      UB_BTRACE(5);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        *reinterpret_cast<Vec16*>(smem + kOffP + tile128_off(r, (col0 >> 3) + v)) = op[v];   // P: core-matrix layout
+        const uint32_t off_ds = (uint32_t)(quarter >> 1) * 16384u + sw128_off(r, (quarter & 1) * 4 + v);
+        *reinterpret_cast<Vec16*>(smem + offDS + off_ds) = od[v];   // in place over the consumed bias chunk
+      }
+      fence_proxy_async_smem();   // my P / dS stores (generic proxy) before the tensor core (async proxy) reads them
+      fence_before_thread_sync();
+      bwd_warp_arrive(bar(kBarPds), lane);
+      UB_BTRACE(6);
+      // The previous tile's dQ (in the other tensor-memory buffer) has long been finished: its read-out runs here, while
+      // the tensor core works on this tile's dQ / dV / dK - off the critical path.
+      if (i > 0) read_out_dq(i - 1);
+      UB_BTRACE(7);
+    }
+    read_out_dq(n_qtiles - 1);
+
+    // ---- epilogue: dK_j, dV_j (16 of the 64 columns per thread) ------------------------------------------------
+    mbar_wait(bar(kBarDvk), (uint32_t)((n_qtiles - 1) & 1));   // the last dV / dK accumulation has completed
+    fence_after_thread_sync();
     const int key = key_tile0 + r;
     uint32_t accv[16], acck[16];
     tmem_ld16(lane_base + kColDV + quarter * 16, accv);
@@ -444,8 +452,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
       for (int v = 0; v < 2; ++v) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          ov[v].w[e] = bwd_pack2<T>(__uint_as_float(accv[v * 8 + 2 * e]) * keep_scale,
-                                    __uint_as_float(accv[v * 8 + 2 * e + 1]) * keep_scale);
+          ov[v].w[e] = bwd_pack2<T>(__uint_as_float(accv[v * 8 + 2 * e]) * keep_scale_m,
+                                    __uint_as_float(accv[v * 8 + 2 * e + 1]) * keep_scale_m);
           ok[v].w[e] = bwd_pack2<T>(__uint_as_float(acck[v * 8 + 2 * e]) * p.scale,
                                     __uint_as_float(acck[v * 8 + 2 * e + 1]) * p.scale);
         }
@@ -454,7 +462,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
       st_global_v8(dkg, ok[0], ok[1]);
     }
   }
-  if (tid == kIssuer) tma_store_wait_read();  // shared memory must outlive the last dS store's reads
   fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, kBwdTmemCols);

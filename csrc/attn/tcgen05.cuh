@@ -166,24 +166,14 @@ TC_DEVICE void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
 TC_DEVICE void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 TC_DEVICE void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// byte offset of the 16-byte chunk (row, chunk) inside a [rows x 64 halfs] tile: 8x8 core matrices,
-// [row/8][chunk][row%8] order => 1024 bytes per 8-row group.
-TC_DEVICE uint32_t tile64_off(int row, int chunk) { return (uint32_t)((row >> 3) * 1024 + chunk * 128 + (row & 7) * 16); }
-// same for a [rows x 128 halfs] tile (16 chunks per row) => 2048 bytes per 8-row group.
+// byte offset of the 16-byte chunk (row, chunk) inside a [rows x 128 halfs] tile of 8x8 core matrices (SWIZZLE_NONE),
+// [row/8][chunk][row%8] order => 2048 bytes per 8-row group: the layout of the thread-written P tiles.
 TC_DEVICE uint32_t tile128_off(int row, int chunk) { return (uint32_t)((row >> 3) * 2048 + chunk * 128 + (row & 7) * 16); }
 
-// ---- TMA: 5-D tiled tensor copy global -> shared, completion counted on an mbarrier ---------------------
+// ---- TMA: tiled tensor copies global <-> shared, completion counted on an mbarrier / bulk async group -----------
 TC_DEVICE void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-TC_DEVICE void tma_load_5d(uint32_t dst_smem, const void* tensor_map, int c0, int c1, int c2, int c3, int c4,
-                           uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-      ::"r"(dst_smem), "l"(tensor_map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
-      : "memory");
-}
-
 TC_DEVICE void tma_load_4d(uint32_t dst_smem, const void* tensor_map, int c0, int c1, int c2, int c3, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -202,60 +192,9 @@ TC_DEVICE void tma_store_3d(const void* tensor_map, int c0, int c1, int c2, uint
                "r"(c1), "r"(c2), "r"(src_smem)
                : "memory");
 }
-// shared -> global tile store through a tensor map (bulk async-group completion); out-of-bounds parts clipped
-TC_DEVICE void tma_store_5d(const void* tensor_map, int c0, int c1, int c2, int c3, int c4, uint32_t src_smem) {
-  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(tensor_map),
-               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(src_smem)
-               : "memory");
-}
 TC_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed stores of this thread have finished READING shared memory (the source may be overwritten)
 TC_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
-// ---- asynchronous global -> shared copies (LDGSTS); src_bytes = 0 zero-fills the 16 destination bytes --------
-TC_DEVICE void cp_async16(uint32_t smem_addr, const void* gptr, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
-}
-TC_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-TC_DEVICE void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// Asynchronously stage a [128 rows x 64] 16-bit tile (row stride in elements) into the core-matrix
-// layout with NT threads. Rows >= valid_rows are zero-filled. 8 lanes cover one 128-byte core-matrix
-// column (conflict-free shared-memory writes), 4 such groups cover 64 contiguous bytes of each row.
-template <int NT, typename T>
-TC_DEVICE void cp_async_tile64(uint32_t smem_tile, const T* gbase, long long row_stride, int valid_rows) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r_in8 = lane & 7, c_lo = lane >> 3;
-  constexpr int kWarps = NT / 32;
-#pragma unroll
-  for (int it = 0; it < 32 / kWarps; ++it) {
-    const int u = it * kWarps + warp;          // 0..31: (row group, chunk half)
-    const int row = (u >> 1) * 8 + r_in8;
-    const int c = (u & 1) * 4 + c_lo;
-    const bool ok = row < valid_rows;
-    cp_async16(smem_tile + tile64_off(row, c), gbase + (ok ? (long long)row * row_stride + c * 8 : 0), ok ? 16u : 0u);
-  }
-}
-
-// Same for a [128 x 128] 16-bit tile (bias): columns >= valid_cols and rows >= valid_rows zero-filled.
-template <int NT, typename T>
-TC_DEVICE void cp_async_tile128(uint32_t smem_tile, const T* gbase, long long row_stride, int valid_rows,
-                                int valid_cols) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r_in8 = lane & 7, c_lo = lane >> 3;
-  constexpr int kWarps = NT / 32;
-#pragma unroll
-  for (int it = 0; it < 64 / kWarps; ++it) {
-    const int u = it * kWarps + warp;          // 0..63: (row group, chunk quarter)
-    const int row = (u >> 2) * 8 + r_in8;
-    const int c = (u & 3) * 4 + c_lo;
-    const bool ok = row < valid_rows && c * 8 < valid_cols;
-    cp_async16(smem_tile + tile128_off(row, c), gbase + (ok ? (long long)row * row_stride + c * 8 : 0), ok ? 16u : 0u);
-  }
-}
 
 }  // namespace tc
 }  // namespace ub

@@ -23,26 +23,6 @@ EncodeFn encode_fn() {
   return fn;
 }
 
-bool encode5(CUtensorMap* map, const void* base, bool bf16, const cuuint64_t (&dims)[5], const cuuint64_t (&strides)[4],
-             const cuuint32_t (&box)[5]) {
-  EncodeFn fn = encode_fn();
-  if (fn == nullptr) return false;
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5,
-                        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    fprintf(stderr,
-            "cuTensorMapEncodeTiled -> %d  base=%p dims={%llu,%llu,%llu,%llu,%llu} strides={%llu,%llu,%llu,%llu} "
-            "box={%u,%u,%u,%u,%u}\n",
-            (int)r, base, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
-            (unsigned long long)dims[3], (unsigned long long)dims[4], (unsigned long long)strides[0],
-            (unsigned long long)strides[1], (unsigned long long)strides[2], (unsigned long long)strides[3], box[0], box[1],
-            box[2], box[3], box[4]);
-  }
-  return r == CUDA_SUCCESS;
-}
-
 bool encode_sw128(CUtensorMap* map, const void* base, bool bf16, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                   const cuuint32_t* box) {
   EncodeFn fn = encode_fn();
@@ -70,21 +50,6 @@ bool make_bias_tile_map_sw128(CUtensorMap* map, const void* base, bool bf16, int
   const cuuint64_t strides[2] = {(cuuint64_t)Lk * 2, (cuuint64_t)Lq * Lk * 2};
   const cuuint32_t box[3] = {64, 128, 1};
   return encode_sw128(map, base, bf16, 3, dims, strides, box);
-}
-
-bool make_head_tile_map(CUtensorMap* map, const void* base, bool bf16, int B, int L, int H, long long sb, long long sl,
-                        int box_rows) {
-  const cuuint64_t dims[5] = {8, 8, (cuuint64_t)H * 8, (cuuint64_t)(L / 8), (cuuint64_t)B};
-  const cuuint64_t strides[4] = {(cuuint64_t)sl * 2, 16, (cuuint64_t)sl * 16, (cuuint64_t)sb * 2};
-  const cuuint32_t box[5] = {8, 8, 8, (cuuint32_t)(box_rows / 8), 1};
-  return encode5(map, base, bf16, dims, strides, box);
-}
-
-bool make_bias_tile_map(CUtensorMap* map, const void* base, bool bf16, int NB, int Lq, int Lk) {
-  const cuuint64_t dims[5] = {8, 8, (cuuint64_t)(Lk / 8), (cuuint64_t)(Lq / 8), (cuuint64_t)NB};
-  const cuuint64_t strides[4] = {(cuuint64_t)Lk * 2, 16, (cuuint64_t)Lk * 16, (cuuint64_t)Lq * Lk * 2};
-  const cuuint32_t box[5] = {8, 8, 16, 16, 1};
-  return encode5(map, base, bf16, dims, strides, box);
 }
 
 }  // namespace ub

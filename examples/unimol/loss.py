@@ -20,7 +20,7 @@ class UniMolLoss(UnicoreLoss):
         tgt_tokens = sample["target"]["tokens_target"]
         masked_tokens = tgt_tokens.ne(self.padding_idx)
         sample_size = masked_tokens.long().sum()
-        utils.mask_to_index(masked_tokens)  # resolved before the encoder is launched (cached for the head below)
+        utils.request_mask_index(masked_tokens)  # count read queued ahead of the encoder (consumed by the head below)
         logits, pred_dist, pred_coord, x_norm, delta_norm = model(
             **sample["net_input"], encoder_masked_tokens=masked_tokens
         )

@@ -141,3 +141,30 @@ def test_gradient_sinks_remove_the_accumulate_kernels():
             torch.cuda.synchronize()
         counts[name] = sum(e.count for e in prof.key_averages() if "CUDAFunctor_add" in e.key)
     assert counts["direct"] < counts["plain"] - 10, counts
+
+
+@pytest.mark.gpu
+def test_loss_curve_tracks_the_reference_arm(tmp_path):
+    """Full BERT-base (fp16, batch 32 x 512, dropout off) on this GPU, same initial weights and batches: the logged
+    loss of 12 updates under this framework (tcgen05 attention, fused norms, fused optimizer) and under the unmodified
+    reference must agree to the logged precision.  The 100-step curves are kept in profiles/loss_curve_bert_base_*."""
+    import json
+    import subprocess
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(repo, "baseline", "_ref", "unicore")):
+        pytest.skip("reference arm (baseline/_ref) is not installed")
+    init = str(tmp_path / "init.pt")
+    curves = {}
+    for impl in ("reference", "ours"):
+        out = subprocess.run(
+            [sys.executable, os.path.join(repo, "tools", "loss_parity.py"), "--gpu", "--impl", impl, "--init", init,
+             "--steps", "12", "--dropout", "0.0", "--lr", "3e-4"],
+            capture_output=True, text=True, timeout=600, cwd=repo)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+        curves[impl] = json.loads(line)["losses"]
+    ours, ref = curves["ours"], curves["reference"]
+    assert all(v is not None for v in ours + ref), (ours, ref)
+    assert ours[-1] < ours[0] - 0.5, ours          # it trains
+    assert max(abs(a - b) for a, b in zip(ours, ref)) < 0.02, (ours, ref)

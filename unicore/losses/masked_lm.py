@@ -22,10 +22,9 @@ class MaskedLMLoss(UnicoreLoss):
         target = sample["target"]
         masked_tokens = target.ne(self.padding_idx)
         sample_size = masked_tokens.int().sum()
-        # resolve the masked positions NOW (one polled host read, cached for the LM head and the
-        # target gather below): the wait happens while the launch queue is still empty, instead of
-        # draining the GPU between the encoder and the LM head
-        utils.mask_to_index(masked_tokens)
+        # start resolving the masked positions NOW (asynchronous count read, consumed by the LM head and the target
+        # gather below): the copy is queued ahead of the encoder, so nobody waits for it
+        utils.request_mask_index(masked_tokens)
         logits = model(**sample["net_input"], masked_tokens=masked_tokens)
         target = target.reshape(-1).index_select(0, utils.mask_to_index(masked_tokens))
         loss = ops.softmax_cross_entropy(logits, target, ignore_index=self.padding_idx)

@@ -239,7 +239,23 @@ def tolist(t: torch.Tensor) -> list:
     return _host_reader.read(t).view(t.shape).tolist()
 
 
-_mask_index_cache = (None, None)
+_mask_index_cache = (None, None, None)   # (weakref of the mask, indices or None, pending count read or None)
+
+
+def request_mask_index(mask: torch.Tensor) -> None:
+    """Start resolving ``mask_to_index(mask)`` without waiting: the number of True entries is summed on the device and
+    copied to pinned host memory asynchronously.  A masked-LM loss calls this BEFORE the model runs; by the time the LM
+    head asks for the indices the copy - queued ahead of the whole encoder - has long completed, so the host neither
+    stalls nor lets the launch queue run dry (a blocking read at this point cost ~0.25 ms of idle GPU per step)."""
+    global _mask_index_cache
+    ref = _mask_index_cache[0]
+    if ref is not None and ref() is mask:
+        return
+    flat = mask.reshape(-1)
+    pending = None
+    if flat.is_cuda and hasattr(torch, "nonzero_static"):
+        pending = AsyncHostRead(flat.sum())
+    _mask_index_cache = (weakref.ref(mask), None, pending)
 
 
 def mask_to_index(mask: torch.Tensor) -> torch.Tensor:
@@ -247,24 +263,26 @@ def mask_to_index(mask: torch.Tensor) -> torch.Tensor:
 
     ``x[mask]`` synchronises inside ``nonzero`` and its backward sorts the indices; a masked-LM step
     indexes with the same mask twice (features and targets).  This computes the indices once per
-    mask object: one polled host read of the count, then ``nonzero_static`` (no further sync); use
-    ``index_select`` with the result (its backward is a plain ``index_add``).
+    mask object: one host read of the count (started early by ``request_mask_index``), then
+    ``nonzero_static`` (no further sync); use ``index_select`` with the result (its backward is a
+    plain ``index_add``).
     """
     global _mask_index_cache
-    ref, idx = _mask_index_cache
-    if ref is not None and ref() is mask:
+    ref, idx, pending = _mask_index_cache
+    if ref is None or ref() is not mask:
+        request_mask_index(mask)
+        ref, idx, pending = _mask_index_cache
+    if idx is not None:
         return idx
     flat = mask.reshape(-1)
-    idx = None
-    if flat.is_cuda and hasattr(torch, "nonzero_static"):
+    if pending is not None:
         try:
-            n = int(item(flat.sum()))
-            idx = torch.nonzero_static(flat, size=n).squeeze(1)
+            idx = torch.nonzero_static(flat, size=int(pending.get())).squeeze(1)
         except (RuntimeError, NotImplementedError):
             idx = None
     if idx is None:
         idx = flat.nonzero(as_tuple=False).squeeze(1)
-    _mask_index_cache = (weakref.ref(mask), idx)
+    _mask_index_cache = (ref, idx, None)
     return idx
 
 
