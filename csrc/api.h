@@ -128,6 +128,13 @@ void launch_pair_tail_fwd(const void* z, const void* z0, const unsigned char* ke
 void launch_pair_tail_bwd(const void* d_pair, const void* d_delta, const void* z, const unsigned char* key_pad, void* dz,
                           void* dz0, int B, int H, int Lq, int Lk, int dtype, cudaStream_t stream);
 
+// Embedding gradient without a sort: grad[token[r], :] (+)= dy[r, :], fp32 accumulation in `scratch` [vocab, cols]
+// (persistent, all zero between calls) with `touched` [vocab] row flags; rows equal to padding_idx contribute nothing.
+// accumulate != 0: add to grad (the optimizer's arena view); else touched rows are overwritten (grad pre-zeroed).
+void launch_embedding_bwd(const void* dy, const long long* tokens, float* scratch, unsigned char* touched, void* grad,
+                          long long rows, int cols, long long vocab, long long padding_idx, int accumulate, int dtype,
+                          cudaStream_t stream);
+
 void launch_gbf_fwd(const void* d, const long long* edge, const void* mul_w, const void* bias_w, const void* means,
                     const void* stds, void* y, long long n, int K, int dtype, cudaStream_t stream);
 // part: float[gbf_parts(n, K)][2 * K] per-CTA partial (d mean, d std); hist: float[2 * E] zero-initialised (d mul, d bias)

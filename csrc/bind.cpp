@@ -456,6 +456,29 @@ Tensor column_sum(const Tensor& x, const OptTensor& sink) {
   return out;
 }
 
+// grad[tokens[r], :] (+)= dy[r, :]  (csrc/fused/embedding.cu); scratch fp32 [V, D] and touched uint8 [V] are persistent,
+// zero between calls.  `grad` is either the parameter's arena view (accumulate) or a zero-filled tensor.
+void embedding_bwd(const Tensor& dy, const Tensor& tokens, int64_t padding_idx, Tensor scratch, Tensor touched, Tensor grad,
+                   bool accumulate) {
+  check_cuda_contig(dy, "dy");
+  check_cuda_contig(tokens, "tokens");
+  check_cuda_contig(grad, "grad");
+  TORCH_CHECK(dy.scalar_type() == at::kHalf || dy.scalar_type() == at::kBFloat16, "embedding_bwd supports fp16 / bf16");
+  TORCH_CHECK(grad.scalar_type() == dy.scalar_type() && grad.dim() == 2 && tokens.scalar_type() == at::kLong);
+  const int cols = (int)grad.size(1);
+  const long long vocab = grad.size(0);
+  TORCH_CHECK(dy.size(-1) == cols && cols % 8 == 0 && dy.numel() / cols == tokens.numel(), "embedding_bwd: shape mismatch");
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(dy.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad.data_ptr()) & 15) == 0,
+              "embedding_bwd needs 16-byte aligned rows");
+  TORCH_CHECK(scratch.is_cuda() && scratch.is_contiguous() && scratch.scalar_type() == at::kFloat && scratch.numel() == vocab * cols);
+  TORCH_CHECK(touched.is_cuda() && touched.is_contiguous() && touched.scalar_type() == at::kByte && touched.numel() == vocab);
+  const c10::cuda::CUDAGuard guard(dy.device());
+  ub::launch_embedding_bwd(dy.data_ptr(), tokens.data_ptr<int64_t>() == nullptr ? nullptr : reinterpret_cast<const long long*>(tokens.data_ptr<int64_t>()),
+                           scratch.data_ptr<float>(), touched.data_ptr<uint8_t>(), grad.data_ptr(), tokens.numel(), cols, vocab,
+                           padding_idx, accumulate ? 1 : 0, dtype_tag(dy), cur_stream());
+  check_launch("embedding_bwd");
+}
+
 std::tuple<Tensor, Tensor, Tensor, Tensor, int64_t, int64_t> bias_dropout_add_ln_fwd(
     const Tensor& x, const OptTensor& bias, const Tensor& residual, const Tensor& gamma, const Tensor& beta, double p,
     double eps) {
@@ -742,6 +765,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bias_gelu_fwd", &bias_gelu_fwd);
   m.def("bias_gelu_bwd", &bias_gelu_bwd, pybind11::arg("dy"), pybind11::arg("x"), pybind11::arg("bias"),
         pybind11::arg("dbias_sink") = pybind11::none());
+  m.def("embedding_bwd", &embedding_bwd);
   m.def("column_sum", &column_sum, pybind11::arg("x"), pybind11::arg("sink") = pybind11::none());
   m.def("bias_dropout_add_ln_fwd", &bias_dropout_add_ln_fwd);
   m.def("bias_dropout_add_ln_bwd", &bias_dropout_add_ln_bwd, pybind11::arg("dy"), pybind11::arg("summed"), pybind11::arg("mean"),

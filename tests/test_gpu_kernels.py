@@ -409,6 +409,43 @@ def test_bias_gelu(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("vocab,dim,shape", [(30522, 768, (32, 512)), (100, 64, (7, 13)), (5000, 512, (1, 1))])
+def test_embedding_sort_free_backward(dtype, vocab, dim, shape):
+    """fp32-accumulated red scatter + finalize == the fp32 reference; heavy duplicates, padding rows, two calls in a row
+    (the persistent scratch must come back clean), accumulate-in-place mode."""
+    ops = _ops()
+    torch.manual_seed(21)
+    pad = 1
+    w = (torch.randn(vocab, dim, device="cuda") * 0.1).to(dtype).requires_grad_(True)
+    tok = torch.randint(0, vocab, shape, device="cuda")
+    tok.view(-1)[::5] = 3          # one very frequent token
+    tok.view(-1)[1::7] = pad       # padding positions contribute nothing
+    dy = torch.randn(*shape, dim, device="cuda").to(dtype)
+    for _ in range(2):
+        w.grad = None
+        y = ops.embedding(tok, w, pad)
+        assert torch.equal(y, F.embedding(tok, w, pad))
+        y.backward(dy)
+        ref = torch.zeros(vocab, dim, device="cuda", dtype=torch.float32)
+        keep = tok.view(-1) != pad
+        ref.index_add_(0, tok.view(-1)[keep], dy.view(-1, dim).float()[keep])
+        scale = max(1.0, ref.abs().max().item())
+        assert maxdiff(w.grad, ref) / scale < TOL[dtype]
+        assert w.grad[pad].abs().max().item() == 0.0
+    # accumulate into an existing gradient buffer (what the gradient arena does)
+    native = ops.native()
+    from unicore_b200.ops import fused_ops
+
+    scratch, touched = fused_ops._scratch_for(w)
+    assert scratch.abs().max().item() == 0.0 and touched.max().item() == 0
+    base = torch.randn(vocab, dim, device="cuda").to(dtype)
+    acc = base.clone()
+    native.embedding_bwd(dy, tok, pad, scratch, touched, acc, True)
+    assert maxdiff(acc, base.float() + ref) / scale < TOL[dtype] * 2
+    assert scratch.abs().max().item() == 0.0 and touched.max().item() == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("rows,din,dout", [(16384, 768, 2304), (4001, 512, 512), (37, 64, 256)])
 def test_linear_with_column_sum_bias_grad(dtype, rows, din, dout):
     ops = _ops()

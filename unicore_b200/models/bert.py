@@ -105,7 +105,7 @@ class BertModel(BaseUnicoreModel):
     def forward(self, src_tokens, masked_tokens=None, features_only=False, classification_head_name=None, **kwargs):
         if classification_head_name is not None:
             features_only = True
-        x = self.embed_tokens(src_tokens)
+        x = ops.embedding(src_tokens, self.embed_tokens.weight, self.embed_tokens.padding_idx)   # sort-free backward
         x = x + self.embed_positions.weight[: src_tokens.size(1), :]
         padding_mask = self._padding_mask(src_tokens, x)
         x = self.sentence_encoder(x, padding_mask=padding_mask)

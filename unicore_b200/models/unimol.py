@@ -239,7 +239,7 @@ class UniMolModel(BaseUnicoreModel):
     def forward(self, src_tokens, src_distance, src_coord, src_edge_type, encoder_masked_tokens=None,
                 features_only=False, **kwargs):
         padding_mask = src_tokens.eq(self.padding_idx)
-        x = self.embed_tokens(src_tokens)
+        x = ops.embedding(src_tokens, self.embed_tokens.weight, self.embed_tokens.padding_idx)
         n_node = src_distance.size(-1)
         gbf_feature = self.gbf(src_distance, src_edge_type)
         graph_attn_bias = ops.pair_to_heads(self.gbf_proj(gbf_feature)).view(-1, n_node, n_node)

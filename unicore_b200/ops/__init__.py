@@ -9,6 +9,7 @@ from .attention_ops import (  # noqa: F401
 from .fused_ops import (  # noqa: F401
     bias_dropout_add_layer_norm,
     bias_gelu,
+    embedding,
     gaussian_basis,
     gaussian_basis_reference,
     linear,
