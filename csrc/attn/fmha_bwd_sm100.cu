@@ -52,7 +52,8 @@ constexpr uint32_t kOffQ = 0;          // 3 x 16 KB (128-byte-swizzled rows)
 constexpr uint32_t kOffDO = 49152;     // 3 x 16 KB
 constexpr uint32_t kOffK = 98304;
 constexpr uint32_t kOffV = 114688;
-constexpr uint32_t kOffP = 131072;     // 32 KB, core-matrix layout (written by the math warps)
+constexpr uint32_t kOffP = 131072;     // 32 KB, core-matrix layout (written by the math warps; as the MN-major A operand
+                                       // of dV this measured 2 % faster than the two-box swizzled layout dS uses)
 constexpr uint32_t kOffDS = 163840;    // 2 x 32 KB: bias tile, then dS (in place); two 64-column swizzled boxes each
 constexpr uint32_t kOffKAdd = 229376;  // float[128]
 constexpr uint32_t kOffBar = kOffKAdd + 512;

@@ -42,7 +42,7 @@ constexpr int kBlockN = 128;   // keys per tile
 constexpr int kHeadDim = 64;
 constexpr int kFwdThreads = 256;
 constexpr uint32_t kTmemCols = 256;
-constexpr uint32_t kTmemColS = 0, kTmemColO = 128;
+constexpr uint32_t kTmemColS = 0, kTmemColO = 128, kTmemColP = 192;   // P (16-bit, 64 columns) when it feeds PV from TMEM
 
 constexpr uint32_t kSmemQ = 0;
 constexpr uint32_t kSmemK = 16384;
@@ -73,7 +73,11 @@ UB_DEVICE uint32_t pack2<__nv_bfloat16>(float a, float b) {
     if (trace != nullptr) trace[j * 12 + (slot)] = clock64();                               \
   } while (0)
 
-template <typename T>
+// kPTmem: the probabilities are handed to the second MMA through tensor memory (tcgen05.st + A operand from TMEM)
+// instead of a 32 KB shared-memory tile: the P V product then reads only V from shared memory (16 KB instead of 48 KB of
+// operand traffic per tile - tcgen05.mma sustains about half of the nominal 128 B/clk of operand reads next to the
+// softmax threads' own shared-memory traffic, so the M128 N64 product is operand-bound).
+template <typename T, bool kPTmem>
 __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_constant__ FmhaFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -258,6 +262,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
     for (int c = 0; c < 2; ++c) {
       const int col0 = half * 64 + c * 32;
       uint32_t keep_word = 0u;   // bit (lane * 16 + i) = pair i (keys col0 + 2i, col0 + 2i + 1), lane = key parity
+      uint32_t pw[16];           // kPTmem: the 32 probabilities of this chunk, packed
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         uint32_t km[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
@@ -281,8 +286,14 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
           psum2 = add2(psum2, pr);
           o.w[e] = pack2<T>(pr.x, pr.y) & km[e];
         }
-        *reinterpret_cast<Vec16*>(smem + kSmemP + tile128_off(r, (col0 >> 3) + v)) = o;
+        if (kPTmem) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pw[v * 4 + e] = o.w[e];
+        } else {
+          *reinterpret_cast<Vec16*>(smem + kSmemP + half * 16384 + sw128_off(r, c * 4 + v)) = o;   // two 64-key swizzled boxes
+        }
       }
+      if (kPTmem) tmem_st16(lane_base + kTmemColP + half * 32 + c * 16, pw);   // keys col0 .. col0+31 of my row
       if (drop && bits_row != nullptr && row_valid && key_tile0 + col0 < p.Lk) bits_row[(key_tile0 + col0) >> 5] = keep_word;
     }
     l_run += psum2.x + psum2.y;
@@ -300,7 +311,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
     }
     UB_TRACE(10);
     mbar_wait(bar_v, (uint32_t)(j & 1));   // V_j has landed
-    fence_proxy_async_smem();      // my P stores (generic proxy) before the tensor core (async proxy) reads them
+    if (kPTmem) tmem_wait_st();    // my P columns are in tensor memory
+    else fence_proxy_async_smem(); // my P stores (generic proxy) before the tensor core (async proxy) reads them
     fence_before_thread_sync();
     __syncthreads();
     UB_TRACE(11);
@@ -308,11 +320,13 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fmha_fwd_kernel(const __grid_c
       fence_after_thread_sync();
 #pragma unroll
       for (int kk = 0; kk < kBlockN / 16; ++kk) {
-        // A = P [128 q x 128 keys] K-major: 16 keys per step = 2 core matrices of 128 B
-        const uint64_t da = make_smem_desc(smem_base + kSmemP + kk * 256, 128, 2048);
-        // B = V [64 d x 128 keys] MN-major view of the row-major [key][d] tile: 16 keys = 2 x 1024 B
+        // A = P [128 q x 128 keys] K-major in two 64-key swizzled boxes: a 16-key step is +32 B inside a box
+        const uint64_t da = make_smem_desc_sw128(smem_base + kSmemP + (kk >> 2) * 16384 + (kk & 3) * 32);
+        const uint32_t ta = tmem_base + kTmemColP + kk * 8;   // kPTmem: 16 keys = 8 columns of packed pairs
+        // B = V [64 d x 128 keys] MN-major view of the row-major [key][d] tile: 16 keys = 2 x 1024 B (swizzled)
         const uint64_t db = make_smem_desc_sw128(smem_base + kSmemV + kk * 2048);
-        umma_f16_ss(tmem_base + kTmemColO, da, db, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        if (kPTmem) umma_f16_ts(tmem_base + kTmemColO, ta, db, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        else umma_f16_ss(tmem_base + kTmemColO, da, db, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
       }
       umma_commit(bar_o);
     }
@@ -365,14 +379,20 @@ void launch_fmha_fwd(const FmhaFwdParams& p, cudaStream_t stream) {
     return;
   }
   dim3 grid((p.Lq + kBlockM - 1) / kBlockM, p.H, p.B);
+  static const bool p_in_smem = [] {
+    const char* e = getenv("UNICORE_B200_FMHA_P");
+    return e != nullptr && e[0] == 's';   // "smem": the earlier hand-over of P through shared memory
+  }();
+  auto run = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes);
+    kern<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(p);
+  };
   if (p.is_bf16) {
-    auto kern = fmha_fwd_kernel<__nv_bfloat16>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes);
-    kern<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(p);
+    if (p_in_smem) run(fmha_fwd_kernel<__nv_bfloat16, false>);
+    else run(fmha_fwd_kernel<__nv_bfloat16, true>);
   } else {
-    auto kern = fmha_fwd_kernel<__half>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes);
-    kern<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(p);
+    if (p_in_smem) run(fmha_fwd_kernel<__half, false>);
+    else run(fmha_fwd_kernel<__half, true>);
   }
 }
 

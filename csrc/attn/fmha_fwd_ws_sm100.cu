@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
       auto issue_pv = [&](int g, int j) {   // O_g += P_g V: 8 x (K = 16), V presented MN-major
 #pragma unroll
         for (int kk = 0; kk < kBlockN / 16; ++kk) {
-          const uint64_t da = make_smem_desc(smem_base + kSmP + g * kTile2 + kk * 256, 128, 2048);
+          const uint64_t da = make_smem_desc_sw128(smem_base + kSmP + g * kTile2 + (kk >> 2) * kTile + (kk & 3) * 32);
           const uint64_t db = make_smem_desc_sw128(smem_base + kSmV + kk * 2048);
           umma_f16_ss(tmem_base + kTmemO + g * 64, da, db, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fmha_fwd_ws_kernel(const __grid
               psum2 = add2(psum2, pr);
               o.w[e] = pack2<T>(pr.x, pr.y) & km[e];
             }
-            *reinterpret_cast<Vec16*>(sP + tile128_off(r, (col0 >> 3) + v)) = o;
+            *reinterpret_cast<Vec16*>(sP + half * kTile + sw128_off(r, c * 4 + v)) = o;   // two 64-key swizzled boxes
           }
           if (drop && bits_row != nullptr && row_valid && key_tile0 + col0 < p.Lk)
             bits_row[(key_tile0 + col0) >> 5] = keep_word;

@@ -122,6 +122,18 @@ TC_DEVICE void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, ui
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (K-major only) is read from tensor memory - lane = row, two 16-bit
+// elements per 32-bit column, 8 columns per K = 16 step - so it costs no shared-memory bandwidth.
+TC_DEVICE void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+
 // ---- TMEM <-> registers (32x32b: thread i of the warp <-> lane base+i; N consecutive columns) ------------------
 TC_DEVICE void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

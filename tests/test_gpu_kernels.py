@@ -409,6 +409,28 @@ def test_bias_gelu(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_relative_position_bias_as_one_hot_gemm(dtype):
+    """The rel-pos bias computed as W^T E (cached one-hot of the bucket table) equals the embedding lookup bit for bit,
+    and its weight gradient equals the fp32 scatter-add."""
+    from unicore.modules import TransformerEncoder
+
+    torch.manual_seed(5)
+    enc = TransformerEncoder(encoder_layers=1, embed_dim=64, ffn_embed_dim=128, attention_heads=12, max_seq_len=256,
+                             rel_pos=True).cuda().to(dtype)
+    x = torch.zeros(2, 200, 64, device="cuda", dtype=dtype)
+    w = enc.relative_attention_bias.weight
+    bias = enc.get_rel_pos_bias(x)
+    bucket = enc.rp_bucket[:200, :200]
+    ref = F.embedding(bucket, w).permute(2, 0, 1)
+    assert bias.shape == (12, 200, 200) and torch.equal(bias, ref)
+    g = torch.randn_like(bias)
+    bias.backward(g)
+    want = torch.zeros(w.shape, device="cuda", dtype=torch.float32)
+    want.index_add_(0, bucket.reshape(-1), g.permute(1, 2, 0).reshape(-1, 12).float())
+    assert maxdiff(w.grad, want) / want.abs().max().item() < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("vocab,dim,shape", [(30522, 768, (32, 512)), (100, 64, (7, 13)), (5000, 512, (1, 1))])
 def test_embedding_sort_free_backward(dtype, vocab, dim, shape):
     """fp32-accumulated red scatter + finalize == the fp32 reference; heavy duplicates, padding rows, two calls in a row

@@ -257,8 +257,26 @@ class _StackMixin:
         if self.rp_bucket.device != x.device:
             self.rp_bucket = self.rp_bucket.to(x.device)
         seq_len = x.size(1)
-        values = F.embedding(self.rp_bucket[:seq_len, :seq_len], self.relative_attention_bias.weight)
+        weight = self.relative_attention_bias.weight
+        if weight.is_cuda and weight.dtype in (torch.float16, torch.bfloat16):
+            # The bucket table is a constant: with its one-hot matrix E [bins, L*L] (cached) the lookup is the GEMM
+            # W^T E - it lands directly in [H, L, L] order (no permute copy), and autograd's backward is the GEMM
+            # dBias E^T with fp32 accumulation instead of ATen's embedding backward (a radix sort of L*L indices plus
+            # a segmented reduction: ~0.2 ms and 12 launches per BERT-base step).  Same values: each output element is
+            # one table entry times 1.
+            return (weight.t() @ self._bucket_one_hot(seq_len, weight)).view(-1, seq_len, seq_len)
+        values = F.embedding(self.rp_bucket[:seq_len, :seq_len], weight)
         return values.permute(2, 0, 1).contiguous()
+
+    def _bucket_one_hot(self, seq_len, like):
+        key = (seq_len, like.device, like.dtype)
+        cache = getattr(self, "_rp_one_hot", None)
+        if cache is None or cache[0] != key:
+            idx = self.rp_bucket[:seq_len, :seq_len].reshape(1, -1)
+            one_hot = torch.zeros(self.rel_pos_bins, idx.numel(), dtype=like.dtype, device=like.device)
+            one_hot.scatter_(0, idx, 1.0)
+            self._rp_one_hot = cache = (key, one_hot)
+        return cache[1]
 
     def _embed_prologue(self, emb, padding_mask):
         x = self.emb_layer_norm(emb)
