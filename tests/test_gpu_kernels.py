@@ -415,9 +415,9 @@ def test_relative_position_bias_as_one_hot_gemm(dtype):
     from unicore.modules import TransformerEncoder
 
     torch.manual_seed(5)
-    enc = TransformerEncoder(encoder_layers=1, embed_dim=64, ffn_embed_dim=128, attention_heads=12, max_seq_len=256,
+    enc = TransformerEncoder(encoder_layers=1, embed_dim=96, ffn_embed_dim=128, attention_heads=12, max_seq_len=256,
                              rel_pos=True).cuda().to(dtype)
-    x = torch.zeros(2, 200, 64, device="cuda", dtype=dtype)
+    x = torch.zeros(2, 200, 96, device="cuda", dtype=dtype)
     w = enc.relative_attention_bias.weight
     bias = enc.get_rel_pos_bias(x)
     bucket = enc.rp_bucket[:200, :200]
