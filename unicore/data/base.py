@@ -1,10 +1,9 @@
-"""Dataset base classes.
+"""Dataset base classes (reference ``data/unicore_dataset.py:14-91`` and ``data/base_wrapper_dataset.py:12-61``).
 
-``UnicoreDataset`` = ``torch.utils.data.Dataset`` + the hooks the batching/iteration machinery
-needs (``collater``, ``ordered_indices``, ``batch_by_size``, epoch notifications, optional
-prefetch).  ``BaseWrapperDataset`` forwards all of them to an inner dataset so that wrappers
-override only what they change.  Parity: reference ``data/unicore_dataset.py:14-91`` and
-``data/base_wrapper_dataset.py:12-61``.
+``UnicoreDataset`` is a ``torch.utils.data.Dataset`` plus the hooks the batching / iteration machinery calls:
+``collater``, ``ordered_indices``, ``batch_by_size``, epoch notifications and optional prefetching.
+``BaseWrapperDataset`` answers every one of those hooks by asking the dataset it wraps, so a concrete wrapper overrides
+only what it changes.
 """
 import numpy as np
 import torch.utils.data
@@ -13,13 +12,13 @@ from . import data_utils
 
 
 class EpochListening:
-    """Mixin: receives ``set_epoch`` at the start of every epoch."""
+    """Mixin for objects that are told when an epoch begins."""
 
     @property
     def can_reuse_epoch_itr_across_epochs(self):
-        """True when the set of batches does not depend on the epoch, which lets the task keep
-        one ``EpochBatchIterator`` alive across epochs. Datasets that override ``set_epoch`` to
-        change sizes/order must leave this False."""
+        """True when the set of batches does not depend on the epoch, so that the task may keep one
+        ``EpochBatchIterator`` alive across epochs.  A dataset whose ``set_epoch`` changes sizes or order must leave
+        this False."""
         return False
 
     def set_epoch(self, epoch):
@@ -34,36 +33,32 @@ class UnicoreDataset(torch.utils.data.Dataset, EpochListening):
         raise NotImplementedError
 
     def collater(self, samples):
-        """Merge a list of items into a mini-batch (dict / tensor)."""
+        """List of items -> mini-batch (dict / tensor)."""
         raise NotImplementedError
 
     def ordered_indices(self):
-        """Index order used to form batches (identity by default)."""
+        """The order in which items are grouped into batches; identity unless overridden."""
         return np.arange(len(self), dtype=np.int64)
 
-    @property
-    def supports_prefetch(self):
-        return False
-
-    def attr(self, attr: str, index: int):
-        return getattr(self, attr, None)
-
-    def prefetch(self, indices):
-        raise NotImplementedError
-
     def batch_by_size(self, indices, batch_size=None, required_batch_size_multiple=1):
-        """Chunk ``indices`` into batches of ``batch_size`` items."""
+        """``indices`` cut into batches of ``batch_size`` items."""
         return data_utils.batch_by_size(
             indices, batch_size=batch_size, required_batch_size_multiple=required_batch_size_multiple
         )
 
-    @property
-    def supports_fetch_outside_dataloader(self):
-        return True
+    def attr(self, attr: str, index: int):
+        return getattr(self, attr, None)
+
+    # -- optional capabilities ------------------------------------------------------------------------------------
+    supports_prefetch = False
+    supports_fetch_outside_dataloader = True
+
+    def prefetch(self, indices):
+        raise NotImplementedError
 
 
 class BaseWrapperDataset(UnicoreDataset):
-    """Delegates every hook to ``self.dataset``."""
+    """Every hook is answered by ``self.dataset``."""
 
     def __init__(self, dataset):
         super().__init__()
@@ -76,16 +71,16 @@ class BaseWrapperDataset(UnicoreDataset):
         return len(self.dataset)
 
     def collater(self, samples):
-        if hasattr(self.dataset, "collater"):
-            return self.dataset.collater(samples)
-        return torch.utils.data.default_collate(samples)
+        inner = getattr(self.dataset, "collater", None)
+        return torch.utils.data.default_collate(samples) if inner is None else inner(samples)
 
     def ordered_indices(self):
         return self.dataset.ordered_indices()
 
-    @property
-    def supports_prefetch(self):
-        return getattr(self.dataset, "supports_prefetch", False)
+    def batch_by_size(self, indices, batch_size=None, required_batch_size_multiple=1):
+        return self.dataset.batch_by_size(
+            indices, batch_size=batch_size, required_batch_size_multiple=required_batch_size_multiple
+        )
 
     def attr(self, attr: str, index: int):
         return self.dataset.attr(attr, index)
@@ -93,20 +88,14 @@ class BaseWrapperDataset(UnicoreDataset):
     def prefetch(self, indices):
         self.dataset.prefetch(indices)
 
-    def batch_by_size(self, indices, batch_size=None, required_batch_size_multiple=1):
-        return self.dataset.batch_by_size(
-            indices, batch_size=batch_size, required_batch_size_multiple=required_batch_size_multiple
-        )
-
-    @property
-    def can_reuse_epoch_itr_across_epochs(self):
-        return self.dataset.can_reuse_epoch_itr_across_epochs
-
     def set_epoch(self, epoch):
         super().set_epoch(epoch)
-        if hasattr(self.dataset, "set_epoch"):
-            self.dataset.set_epoch(epoch)
+        notify = getattr(self.dataset, "set_epoch", None)
+        if notify is not None:
+            notify(epoch)
 
-    @property
-    def supports_fetch_outside_dataloader(self):
-        return getattr(self.dataset, "supports_fetch_outside_dataloader", True)
+    # capabilities are the wrapped dataset's (with the base class defaults for plain torch datasets)
+    supports_prefetch = property(lambda self: getattr(self.dataset, "supports_prefetch", False))
+    supports_fetch_outside_dataloader = property(
+        lambda self: getattr(self.dataset, "supports_fetch_outside_dataloader", True))
+    can_reuse_epoch_itr_across_epochs = property(lambda self: self.dataset.can_reuse_epoch_itr_across_epochs)
