@@ -168,3 +168,18 @@ def test_loss_curve_tracks_the_reference_arm(tmp_path):
     assert all(v is not None for v in ours + ref), (ours, ref)
     assert ours[-1] < ours[0] - 0.5, ours          # it trains
     assert max(abs(a - b) for a, b in zip(ours, ref)) < 0.02, (ours, ref)
+
+
+@pytest.mark.gpu
+def test_reading_the_loss_does_not_wait_for_the_rest_of_the_update():
+    """Single process: the loss statistics are staged to the host behind the forward pass, so ``out["loss"]`` is
+    answered from host numbers without materialising the device-resident meters (gradient norm ...), and it is the
+    value the full materialisation reports."""
+    trainer, outs = _run(["--deferred-overflow-check"], 3)
+    out = outs[-1]
+    assert out._values is None                      # nothing has been brought to the host on demand yet
+    loss = out["loss"]
+    assert isinstance(loss, float) and out._values is None
+    assert "loss" in out and "no_such_key" not in out and out.get("no_such_key", 7) == 7
+    everything = dict(out.items())                  # now the rest (gnorm, clip, ...) is read
+    assert everything["loss"] == loss and "gnorm" in everything

@@ -260,11 +260,25 @@ class LazyStats(object):
             self._values, self._agg = values, None
         return self._values
 
+    def _single(self, key):
+        """One value without materialising the rest: a meter that already holds host numbers (the loss statistics of a
+        single-process run, staged behind the forward pass) answers at once; device-resident ones (the gradient norm)
+        are only waited for when somebody asks for THEM."""
+        if self._values is not None:
+            return self._values[key]
+        if key == "sample_size":
+            return self._sample_size
+        if key in self._DROPPED or key.startswith("_") or key not in self._agg:
+            raise KeyError(key)
+        return self._agg.get_smoothed_value(key)
+
     def __getitem__(self, key):
-        return self._materialise()[key]
+        return self._single(key)
 
     def __contains__(self, key):
-        return key in self._materialise()
+        if self._values is not None:
+            return key in self._values
+        return key == "sample_size" or (key in self._agg and key not in self._DROPPED and not key.startswith("_"))
 
     def __iter__(self):
         return iter(self._materialise())
@@ -276,7 +290,10 @@ class LazyStats(object):
         return repr(self._materialise())
 
     def get(self, key, default=None):
-        return self._materialise().get(key, default)
+        try:
+            return self._single(key)
+        except KeyError:
+            return default
 
     def keys(self):
         return self._materialise().keys()

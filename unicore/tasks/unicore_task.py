@@ -13,7 +13,7 @@ from typing import Any, Callable, Dict, List
 
 import torch
 
-from unicore import metrics
+from unicore import metrics, utils
 from unicore.data import UnicoreDataset, data_utils, iterators
 
 logger = logging.getLogger(__name__)
@@ -144,6 +144,9 @@ class UnicoreTask(object):
             value, sample_size, logging_output = loss(model, sample)
         if ignore_grad:
             value = value * 0
+        # single process: the statistics need no cross-rank reduction, so their copy to the host can start right here,
+        # behind the forward pass (``utils.stage_logging_output``); with several ranks they travel in the optimizer tail
+        utils.stage_logging_output(logging_output, enabled=getattr(self.args, "distributed_world_size", 1) == 1)
         with torch.autograd.profiler.record_function("backward"):
             optimizer.backward(value)
         return value, sample_size, logging_output

@@ -519,6 +519,8 @@ class Trainer(object):
                 metrics.log_scalar("clip", (g > self.args.clip_norm).to(g.dtype) * 100, priority=500, round=1)
         with metrics.aggregate() as agg:
             if logging_outputs is not None:
+                # (single process: the scalars were staged to the host behind the forward pass - host numbers from here)
+                logging_outputs = [utils.resolve_logging_output(log) for log in logging_outputs]
                 self.task.reduce_metrics(logging_outputs, self.get_loss())
             if "loss" not in agg:
                 if "loss" not in self._warned:

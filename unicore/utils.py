@@ -239,6 +239,43 @@ def tolist(t: torch.Tensor) -> list:
     return _host_reader.read(t).view(t.shape).tolist()
 
 
+# ---- logging outputs on their way to the host -------------------------------------------------------------------------
+_staged_logs = {}
+
+
+def stage_logging_output(log, enabled=True) -> None:
+    """Start copying the device scalars of one micro-batch's logging output to pinned host memory NOW - a loss calls
+    this between its forward and the backward launch, so the copy sits in the stream right behind the forward pass.
+    ``resolve_logging_output`` later swaps the host numbers in.  Reading ``train_step(...)["loss"]`` then waits for the
+    end of the FORWARD pass instead of the end of the whole update: a caller that reads the loss every step (an
+    end-to-end benchmark, a notebook) keeps the launch queue a full backward pass ahead of the device."""
+    if not enabled or not isinstance(log, dict):
+        return
+    keys = [k for k, v in log.items() if torch.is_tensor(v) and v.is_cuda and v.numel() == 1]
+    if not keys:
+        return
+    packed = torch.stack([log[k].detach().reshape(()).double() for k in keys])
+    _staged_logs[id(log)] = (log, keys, AsyncHostRead(packed))
+    if len(_staged_logs) > 64:   # logging outputs that were never resolved (aborted steps): do not grow forever
+        for stale in list(_staged_logs)[:-32]:
+            _staged_logs.pop(stale, None)
+
+
+def resolve_logging_output(log):
+    """The logging output with its staged device scalars replaced by python floats (waits for the staged copy, i.e. for
+    the forward pass that produced them); unchanged when nothing was staged."""
+    entry = _staged_logs.pop(id(log), None)
+    if entry is None or entry[0] is not log:
+        return log
+    _, keys, pending = entry
+    numbers = pending.get()
+    numbers = numbers if isinstance(numbers, list) else [numbers]
+    resolved = dict(log)
+    for key, number in zip(keys, numbers):
+        resolved[key] = number
+    return resolved
+
+
 _mask_index_cache = (None, None, None)   # (weakref of the mask, indices or None, pending count read or None)
 
 
