@@ -13,10 +13,13 @@
 //     3. softmax in ONE pass over registers: thread = (query row, 64-key half); TMEM lane = row.
 //        tcgen05.ld, scale/bias FMA and exp2 argument on packed fp32x2 (FFMA2), row max exchanged
 //        between the two halves through shared memory, Philox dropout decided two keys per HSET2
-//        (the 0xffff/0 masks AND the packed P; keep bits are stored for backward), P -> shared
-//        memory, O rescaled in TMEM (32 columns per thread)
-//     4. O += P V_j            8 x tcgen05.mma (V presented MN-major from the same row-major bytes);
-//        V_j is only waited for here, so its latency hides behind the softmax
+//        (the 0xffff/0 masks AND the packed P; keep bits are stored for backward), P -> tensor memory
+//        columns [192,256) with tcgen05.st (two 16-bit probabilities per column), O rescaled in TMEM only when the
+//        row maximum has moved by more than the slack (lazy rescaling)
+//     4. O += P V_j            8 x tcgen05.mma with the A operand (P) read from TENSOR MEMORY and V presented MN-major
+//        from the same row-major bytes; V_j is only waited for here, so its latency hides behind the softmax.
+//        (P through a shared-memory tile - UNICORE_B200_FMHA_P=smem - costs a 32 KB store and a 32 KB operand read per
+//        tile: 0.120 instead of 0.118 ms with the tile 128-byte-swizzled, 0.137 ms with unswizzled core matrices.)
 //   q/k/v are read through strides straight out of the packed in_proj output; O is written as
 //   [B, Lq, H, 64] so that out_proj consumes it without a transpose.
 // Two CTAs are resident per SM (113 KB smem, 256 TMEM columns, <= 128 registers/thread) so one CTA's

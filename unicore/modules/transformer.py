@@ -258,7 +258,8 @@ class _StackMixin:
             self.rp_bucket = self.rp_bucket.to(x.device)
         seq_len = x.size(1)
         weight = self.relative_attention_bias.weight
-        if weight.is_cuda and weight.dtype in (torch.float16, torch.bfloat16):
+        one_hot_bytes = self.rel_pos_bins * seq_len * seq_len * 2
+        if weight.is_cuda and weight.dtype in (torch.float16, torch.bfloat16) and one_hot_bytes <= (64 << 20):
             # The bucket table is a constant: with its one-hot matrix E [bins, L*L] (cached) the lookup is the GEMM
             # W^T E - it lands directly in [H, L, L] order (no permute copy), and autograd's backward is the GEMM
             # dBias E^T with fp32 accumulation instead of ATen's embedding backward (a radix sort of L*L indices plus
