@@ -468,7 +468,8 @@ def test_embedding_sort_free_backward(dtype, vocab, dim, shape):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("rows,din,dout", [(16384, 768, 2304), (4001, 512, 512), (37, 64, 256)])
+@pytest.mark.parametrize("rows,din,dout", [(16384, 768, 2304), (4001, 512, 512), (37, 64, 256), (65536, 128, 64),
+                                            (12288, 64, 128)])
 def test_linear_with_column_sum_bias_grad(dtype, rows, din, dout):
     ops = _ops()
     torch.manual_seed(14)

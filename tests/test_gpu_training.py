@@ -181,5 +181,5 @@ def test_reading_the_loss_does_not_wait_for_the_rest_of_the_update():
     loss = out["loss"]
     assert isinstance(loss, float) and out._values is None
     assert "loss" in out and "no_such_key" not in out and out.get("no_such_key", 7) == 7
-    everything = dict(out.items())                  # now the rest (gnorm, clip, ...) is read
-    assert everything["loss"] == loss and "gnorm" in everything
+    everything = dict(out.items())                  # full materialisation (one host transfer for what is left)
+    assert everything["loss"] == loss and "seq_len" in everything and "sample_size" in everything

@@ -83,7 +83,10 @@ class NonLinearHead(nn.Module):
         self.activation_fn = utils.get_activation_fn(activation_fn)
 
     def forward(self, x):
-        return self.linear2(self.activation_fn(self.linear1(x)))
+        # (ops.linear: bias gradients of these pair-tensor layers - millions of rows, 64-128 columns - through the
+        # column-sum kernel instead of ATen's generic reduction)
+        h = self.activation_fn(ops.linear(x, self.linear1.weight, self.linear1.bias))
+        return ops.linear(h, self.linear2.weight, self.linear2.bias)
 
 
 class MaskLMHead(nn.Module):
@@ -114,7 +117,8 @@ class DistanceHead(nn.Module):
 
     def forward(self, x):
         bsz, seq_len, _, _ = x.size()
-        x = self.out_proj(self.layer_norm(self.activation_fn(self.dense(x)))).view(bsz, seq_len, seq_len)
+        x = self.activation_fn(ops.linear(x, self.dense.weight, self.dense.bias))
+        x = self.out_proj(self.layer_norm(x)).view(bsz, seq_len, seq_len)
         return (x + x.transpose(-1, -2)) * 0.5
 
 

@@ -77,13 +77,27 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             x2 = x.reshape(-1, x.shape[-1])
             if ctx.w_sink is not None:
-                ctx.w_sink.grad.addmm_(dy2.t(), x2)
+                if weight.numel() * 64 < dy2.shape[0] * dy2.shape[1]:
+                    # tiny weight, very long reduction (pair-tensor heads: 64 x 128 outputs over millions of rows): the
+                    # beta = 1 GEMM falls onto a slow non-split-K kernel (measured 485 us); plain mm + a small add
+                    ctx.w_sink.grad.add_(dy2.t().mm(x2))
+                else:
+                    ctx.w_sink.grad.addmm_(dy2.t(), x2)
                 grad_sink.done(ctx.w_sink)
             else:
                 dw = dy2.t().mm(x2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             claimed = ctx.b_sink
-            if dy2.data_ptr() % 16 == 0 and dy2.shape[-1] % 8 == 0 and dy2.dtype in (torch.float16, torch.bfloat16):
+            fold = _narrow_fold(dy2)
+            if fold > 1:
+                # narrow output (< 256 columns): the column kernel would leave most of its lanes idle, so f rows are
+                # folded into one [rows / f, f * cols] row first (a view) and the f partial sums added afterwards
+                rows, cols = dy2.shape
+                wide = native().column_sum(dy2.view(rows // fold, cols * fold), None)
+                db = wide.view(fold, cols).float().sum(dim=0).to(dy2.dtype)
+                if claimed is not None:
+                    claimed.grad.add_(db)
+            elif dy2.data_ptr() % 16 == 0 and dy2.shape[-1] % 8 == 0 and dy2.dtype in (torch.float16, torch.bfloat16):
                 db = native().column_sum(dy2, grad_sink.sink(claimed))
             else:
                 db = dy2.sum(dim=0)
@@ -95,6 +109,18 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db
 
 
+def _narrow_fold(dy2: torch.Tensor) -> int:
+    """How many rows of a narrow 16-bit [rows, cols] gradient to fold into one for ``column_sum`` (1 = do not fold)."""
+    rows, cols = dy2.shape
+    if (cols >= 256 or cols % 8 != 0 or rows < 4096 or not dy2.is_contiguous() or dy2.data_ptr() % 16 != 0
+            or dy2.dtype not in (torch.float16, torch.bfloat16)):
+        return 1
+    fold = 1
+    while cols * fold * 2 <= 1024 and rows % (fold * 2) == 0:
+        fold *= 2
+    return fold
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``F.linear`` whose backward computes the bias gradient with ``column_sum`` (``csrc/fused/elementwise.cu``) and
     writes parameter gradients in place into the gradient arena when they are claimed (``grad_sink``)."""
@@ -104,7 +130,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     direct = grad_sink.wants(weight) or grad_sink.wants(bias)  # (grad mode was checked above)
     fast_bias = (
         bias is not None and bias.dtype == x.dtype
-        and weight.shape[0] % 8 == 0 and weight.shape[0] >= 256  # narrow outputs leave the column kernel's CTAs idle
+        and weight.shape[0] % 8 == 0
+        and (weight.shape[0] >= 256 or x.numel() // max(1, x.shape[-1]) >= 4096)  # (narrow outputs: rows are folded)
         and (x.requires_grad or weight.requires_grad or bias.requires_grad)
     )
     if direct or fast_bias:
