@@ -321,9 +321,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
       if (drop && ok && key_tile0 + col0 < p.Lk) keep = p.drop_bits[stat_idx * words_per_row + ((key_tile0 + col0) >> 5)];
     };
     // dQ_i partial of this key tile -> 16-bit partial buffer (16 of the 64 columns per thread)
-    auto read_out_dq = [&](int i) {
-      mbar_wait(bar(kBarDq), (uint32_t)(i & 1));
-      fence_after_thread_sync();
+    auto read_out_dq = [&](int i) {   // (the caller has waited for kBarDq phase i)
       uint32_t acc[16];
       tmem_ld16(lane_base + kColDQ + (uint32_t)(i & 1) * 64 + quarter * 16, acc);
       tmem_wait_ld();
@@ -424,6 +422,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
         const uint32_t off_ds = (uint32_t)(quarter >> 1) * 16384u + sw128_off(r, (quarter & 1) * 4 + v);
         *reinterpret_cast<Vec16*>(smem + offDS + off_ds) = od[v];   // in place over the consumed bias chunk
       }
+      // dQ_{i-1} finished long ago, but its barrier phase must be OBSERVED before this thread lets dQ_i be issued (the
+      // arrival below): a parity wait that falls two phases behind would wait for ever.  (compute-sanitizer's slow-down
+      // exposed exactly that when this wait sat after the arrival.)
+      if (i > 0) {
+        mbar_wait(bar(kBarDq), par ^ 1);
+        fence_after_thread_sync();
+      }
       fence_proxy_async_smem();   // my P / dS stores (generic proxy) before the tensor core (async proxy) reads them
       fence_before_thread_sync();
       bwd_warp_arrive(bar(kBarPds), lane);
@@ -433,6 +438,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fmha_bwd_kernel(const __grid_c
       if (i > 0) read_out_dq(i - 1);
       UB_BTRACE(7);
     }
+    mbar_wait(bar(kBarDq), (uint32_t)((n_qtiles - 1) & 1));
+    fence_after_thread_sync();
     read_out_dq(n_qtiles - 1);
 
     // ---- epilogue: dK_j, dV_j (16 of the 64 columns per thread) ------------------------------------------------
