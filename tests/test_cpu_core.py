@@ -435,3 +435,27 @@ def test_iterator_resume_with_a_different_world_size():
     fresh = make(2, 0)
     fresh.load_state_dict({"epoch": 3, "iterations_in_epoch": 0, "shuffle": True, "len": 8})
     assert fresh.next_epoch_idx == 3 and len(list(fresh.next_epoch_itr(shuffle=True))) == 8
+
+
+def test_staged_logging_outputs_and_lazy_step_statistics():
+    """CPU semantics of the early statistics path: nothing is staged for host tensors (the logging output comes back
+    unchanged), and ``LazyStats`` answers single keys without materialising the rest."""
+    import torch
+
+    from unicore import metrics, utils
+    from unicore.engine.update import LazyStats
+
+    log = {"loss": torch.tensor(3.0), "bsz": 4}
+    utils.stage_logging_output(log)                 # no CUDA scalars: a no-op
+    assert utils.resolve_logging_output(log) is log
+    with metrics.aggregate() as agg:
+        metrics.log_scalar("loss", 2.5, 4, round=3)
+        metrics.log_scalar("gnorm", torch.tensor(1.25), round=3)
+        metrics.log_scalar("_hidden", 1.0)
+    stats = LazyStats(agg, 4)
+    assert stats["loss"] == 2.5 and stats._values is None
+    assert stats.get("missing", "dflt") == "dflt" and "loss" in stats and "_hidden" not in stats
+    assert stats["sample_size"] == 4
+    full = dict(stats.items())
+    assert full["loss"] == 2.5 and abs(float(full["gnorm"]) - 1.25) < 1e-6 and "_hidden" not in full
+    assert stats._values is not None and stats["loss"] == 2.5
