@@ -255,3 +255,43 @@ def test_trainer_recovers_from_oom_in_forward_backward():
     trainer.task.train_step = broken
     with pytest.raises(RuntimeError, match="shape mismatch"):
         trainer.train_step([batches[0]])
+
+
+def test_narrow_bias_gradient_fold_rule():
+    """``ops.linear``'s rule for folding rows of a narrow gradient before the column-sum kernel."""
+    import torch
+
+    from unicore_b200.ops.fused_ops import _narrow_fold
+
+    def fold(rows, cols, dtype=torch.float16):
+        return _narrow_fold(torch.zeros(rows, cols, dtype=dtype))
+
+    assert fold(65536, 64) == 16          # 64 x 16 = 1024 columns
+    assert fold(12288, 128) == 8
+    assert fold(4096 * 3, 8) == 128       # capped by 1024 / cols
+    assert fold(4098, 64) == 2            # rows only divisible by 2
+    assert fold(65536, 256) == 1          # wide enough as it is
+    assert fold(1000, 64) == 1            # too few rows to matter
+    assert fold(65536, 60) == 1           # not a multiple of 8 columns
+    assert fold(65536, 64, torch.float32) == 1
+
+
+def test_embedding_and_vocab_projection_fall_back_on_cpu():
+    """Without the native extension in play both ops are the plain PyTorch formulations (same values and gradients)."""
+    import torch
+    import torch.nn.functional as F
+
+    from unicore import ops
+
+    torch.manual_seed(3)
+    w = torch.randn(50, 16, requires_grad=True)
+    tok = torch.randint(0, 50, (4, 7))
+    y = ops.embedding(tok, w, 1)
+    assert torch.equal(y, F.embedding(tok, w, 1))
+    y.sum().backward()
+    g = w.grad.clone()
+    w.grad = None
+    F.embedding(tok, w, 1).sum().backward()
+    assert torch.equal(g, w.grad)
+    x = torch.randn(5, 16)
+    assert torch.allclose(ops.vocab_projection(x, w, None), F.linear(x, w))
